@@ -1,0 +1,248 @@
+"""Synthetic inputs and seeded synthetic weights (no datasets / checkpoints are reachable offline).
+
+``param_spec`` enumerates the reference checkpoint's keys and shapes for a model config (SURVEY.md
+Appendix B; key names are the attribute paths of ``FocalFormer3D`` and its sub-modules, e.g.
+``pts_bbox_head.heatmap_head.0.conv.weight`` from ``focal_decoder.py:202-221``).  The same spec validates
+real checkpoints at load time and drives ``make_state_dict`` for benchmarks and parity tests.
+"""
+import math
+import zlib
+import numpy as np
+import torch
+
+
+def _bn(spec, name, c):
+    spec[name + ".weight"] = ((c,), "bn_w")
+    spec[name + ".bias"] = ((c,), "bn_b")
+    spec[name + ".running_mean"] = ((c,), "bn_m")
+    spec[name + ".running_var"] = ((c,), "bn_v")
+    spec[name + ".num_batches_tracked"] = ((), "count")
+
+
+def _inverted_residual(spec, name, cin, cout, expand):
+    hid = cin * expand
+    i = 0
+    if expand != 1:
+        spec[f"{name}.conv.0.0.weight"] = ((hid, cin, 1, 1), ("w", cin))
+        _bn(spec, f"{name}.conv.0.1", hid)
+        i = 1
+    spec[f"{name}.conv.{i}.0.weight"] = ((hid, 1, 3, 3), ("w", 9))
+    _bn(spec, f"{name}.conv.{i}.1", hid)
+    spec[f"{name}.conv.{i + 1}.weight"] = ((cout, hid, 1, 1), ("w", hid))
+    _bn(spec, f"{name}.conv.{i + 2}", cout)
+
+
+def param_spec(model_cfg):
+    """name -> (shape, init kind) for every tensor of the reference state dict (LiDAR-only configs)."""
+    s = {}
+    ve = model_cfg["pts_voxel_encoder"]
+    me = model_cfg["pts_middle_encoder"]
+    if ve["type"] == "HardVFE":
+        fc = ve["feat_channels"][0]
+        s["pts_voxel_encoder.vfe_layers.0.linear.weight"] = ((fc, ve["in_channels"]), ("w", ve["in_channels"]))
+        _bn(s, "pts_voxel_encoder.vfe_layers.0.norm", fc)
+    # --- SparseEncoder (mmdet3d v0.17.1; spconv-v1 weight layout [kD,kH,kW,Cin,Cout])
+    p = "pts_middle_encoder"
+    base = me.get("base_channels", 16)
+    taps = (3.0, 10.0, 16.0, 21.0)        # measured mean active taps per SubM level on LiDAR-like clouds
+    s[f"{p}.conv_input.0.weight"] = ((3, 3, 3, me["in_channels"], base), ("spw_in", me["in_channels"] * taps[0]))
+    _bn(s, f"{p}.conv_input.1", base)
+    cin = base
+    enc = me["encoder_channels"]
+    for i, blocks in enumerate(enc):
+        for j, cout in enumerate(blocks):
+            q = f"{p}.encoder_layers.encoder_layer{i + 1}.{j}"
+            if j == len(blocks) - 1 and i != len(enc) - 1:
+                s[f"{q}.0.weight"] = ((3, 3, 3, cin, cout), ("spw", cin * taps[min(i, 3)] * 0.6))
+                _bn(s, f"{q}.1", cout)
+            else:
+                for n in (1, 2):
+                    s[f"{q}.conv{n}.weight"] = ((3, 3, 3, cout, cout), ("spw", cout * taps[min(i, 3)] * n))
+                    _bn(s, f"{q}.bn{n}", cout)
+            cin = cout
+    oc = me.get("output_channels", 128)
+    s[f"{p}.conv_out.0.weight"] = ((3, 1, 1, cin, oc), ("w", cin * 2))
+    _bn(s, f"{p}.conv_out.1", oc)
+    # --- SECOND
+    bb = model_cfg["pts_backbone"]
+    inf = [bb["in_channels"], *bb["out_channels"][:-1]]
+    for i, n in enumerate(bb["layer_nums"]):
+        c = bb["out_channels"][i]
+        s[f"pts_backbone.blocks.{i}.0.weight"] = ((c, inf[i], 3, 3), ("w", inf[i] * 9))
+        _bn(s, f"pts_backbone.blocks.{i}.1", c)
+        for l in range(n):
+            s[f"pts_backbone.blocks.{i}.{3 * (l + 1)}.weight"] = ((c, c, 3, 3), ("w", c * 9))
+            _bn(s, f"pts_backbone.blocks.{i}.{3 * (l + 1) + 1}", c)
+    # --- SECONDFPN
+    nk = model_cfg["pts_neck"]
+    for i, c in enumerate(nk["out_channels"]):
+        st = nk["upsample_strides"][i]
+        ci = nk["in_channels"][i]
+        if st > 1 or not nk.get("use_conv_for_no_stride", False):
+            s[f"pts_neck.deblocks.{i}.0.weight"] = ((ci, c, st, st), ("w", ci))       # ConvTranspose2d [Cin,Cout,k,k]
+        else:
+            s[f"pts_neck.deblocks.{i}.0.weight"] = ((c, ci, 1, 1), ("w", ci))
+        _bn(s, f"pts_neck.deblocks.{i}.1", c)
+    # --- FocalEncoder
+    ne = model_cfg["imgpts_neck"]
+    hc = ne["hidden_channel"]
+    s["imgpts_neck.shared_conv_pts.weight"] = ((hc, ne["in_channels_pts"], 3, 3), ("w", ne["in_channels_pts"] * 9))
+    s["imgpts_neck.shared_conv_pts.bias"] = ((hc,), "b")
+    for i in range(ne["num_layers"] or 0):
+        _inverted_residual(s, f"imgpts_neck.fusion_blocks.{i}.P_IML", hc, hc, 2)
+        _inverted_residual(s, f"imgpts_neck.fusion_blocks.{i}.P_out_proj", 2 * hc, hc, 1)
+        _inverted_residual(s, f"imgpts_neck.fusion_blocks.{i}.P_integration", 2 * hc, hc, 1)
+    if ne.get("extra_feat"):
+        s["imgpts_neck.extra_output.conv.weight"] = ((hc, hc, 3, 3), ("w", hc * 9))
+        _bn(s, "imgpts_neck.extra_output.bn", hc)
+    # --- FocalDecoder
+    hd = model_cfg["pts_bbox_head"]
+    h = "pts_bbox_head"
+    hc = hd["hidden_channel"]
+    nc = hd["num_classes"]
+    if hd.get("multiscale"):
+        for n in ("dconv", "dconv2"):
+            s[f"{h}.{n}.conv.weight"] = ((hc, hc, 3, 3), ("w", hc * 9))
+            _bn(s, f"{h}.{n}.bn", hc)
+    if hd.get("roi_feats"):
+        pre = hd["roi_feats"] ** 2 * hc * (3 if hd.get("multiscale") else 1)
+        hr = hd.get("hidden_channel_roi", 512)
+        step = 4 if hd.get("roi_dropout_rate", 0.0) > 1e-4 else 3
+        for i, chl in enumerate((hr, hr, hc)):
+            s[f"{h}.roi_mlp.{i * step}.weight"] = ((chl, pre), ("w", pre))
+            _bn(s, f"{h}.roi_mlp.{i * step + 1}", chl)
+            pre = chl
+
+    def heat(name):
+        s[f"{name}.0.conv.weight"] = ((hc, hc, 3, 3), ("w", hc * 9))
+        _bn(s, f"{name}.0.bn", hc)
+        s[f"{name}.1.weight"] = ((nc, hc, 3, 3), ("w", hc * 9))
+        s[f"{name}.1.bias"] = ((nc,), "heat_b")
+    heat(f"{h}.heatmap_head")
+    stages = (hd.get("multistage_heatmap") or 0) + (1 if hd.get("reuse_first_heatmap") else 0)
+    if hd.get("input_img", True) or hd.get("iterbev_wo_img"):
+        if stages:
+            for i in range(stages):
+                if not (i == 0 and hd.get("reuse_first_heatmap")):
+                    heat(f"{h}.heatmap_head_img.{i}")
+        else:
+            heat(f"{h}.heatmap_head_img")
+    s[f"{h}.class_encoding.weight"] = ((hc, nc, 1), ("w", nc))
+    s[f"{h}.class_encoding.bias"] = ((hc,), "b")
+    dc = hd["decoder_cfg"]
+    tl = dc["transformerlayers"]
+    ff = tl["feedforward_channels"]
+    msda = tl["attn_cfgs"][1]
+    nh, nl, npt = msda["num_heads"], msda["num_levels"], msda["num_points"]
+    for i in range(hd["num_decoder_layers"]):
+        s[f"{h}.pos_embed_learned.{i}.layers.0.weight"] = ((hc, 256), ("w", 256))
+        s[f"{h}.pos_embed_learned.{i}.layers.0.bias"] = ((hc,), "b")
+        s[f"{h}.pos_embed_learned.{i}.layers.1.weight"] = ((hc, hc), ("w", hc))
+        s[f"{h}.pos_embed_learned.{i}.layers.1.bias"] = ((hc,), "b")
+        for j in range(dc["num_layers"]):
+            q = f"{h}.decoder.{i}.layers.{j}"
+            s[f"{q}.attentions.0.attn.in_proj_weight"] = ((3 * hc, hc), ("w", hc))
+            s[f"{q}.attentions.0.attn.in_proj_bias"] = ((3 * hc,), "b")
+            s[f"{q}.attentions.0.attn.out_proj.weight"] = ((hc, hc), ("w", hc))
+            s[f"{q}.attentions.0.attn.out_proj.bias"] = ((hc,), "b")
+            s[f"{q}.attentions.1.sampling_offsets.weight"] = ((nh * nl * npt * 2, hc), ("w_small", hc))
+            s[f"{q}.attentions.1.sampling_offsets.bias"] = ((nh * nl * npt * 2,), "offs_b")
+            s[f"{q}.attentions.1.attention_weights.weight"] = ((nh * nl * npt, hc), ("w", hc))
+            s[f"{q}.attentions.1.attention_weights.bias"] = ((nh * nl * npt,), "b")
+            s[f"{q}.attentions.1.value_proj.weight"] = ((hc, hc), ("w", hc))
+            s[f"{q}.attentions.1.value_proj.bias"] = ((hc,), "b")
+            s[f"{q}.attentions.1.output_proj.weight"] = ((hc, hc), ("w", hc))
+            s[f"{q}.attentions.1.output_proj.bias"] = ((hc,), "b")
+            s[f"{q}.ffns.0.layers.0.0.weight"] = ((ff, hc), ("w", hc))
+            s[f"{q}.ffns.0.layers.0.0.bias"] = ((ff,), "b")
+            s[f"{q}.ffns.0.layers.1.weight"] = ((hc, ff), ("w", ff))
+            s[f"{q}.ffns.0.layers.1.bias"] = ((hc,), "b")
+            for n in range(3):
+                s[f"{q}.norms.{n}.weight"] = ((hc,), "ln_w")
+                s[f"{q}.norms.{n}.bias"] = ((hc,), "b")
+        heads = dict(hd["common_heads"])
+        heads["heatmap"] = (nc, hd.get("num_heatmap_convs", 2))
+        for name, (k, nconv) in heads.items():
+            assert nconv == 2
+            s[f"{h}.prediction_heads.{i}.{name}.0.conv.weight"] = ((64, hc, 1), ("w", hc))
+            _bn(s, f"{h}.prediction_heads.{i}.{name}.0.bn", 64)
+            s[f"{h}.prediction_heads.{i}.{name}.1.weight"] = ((k, 64, 1), ("w_small", 64))
+            s[f"{h}.prediction_heads.{i}.{name}.1.bias"] = ((k,), "heat_b" if name == "heatmap" else "b")
+    return s
+
+
+def _gen(name, seed):
+    g = torch.Generator()
+    g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+    return g
+
+
+def make_state_dict(model_cfg, seed=0):
+    """Deterministic synthetic weights (per-key seeded, fp32, CPU).  Gains are chosen so activations stay
+    O(1) through the ~40 stacked layers and the heatmaps have well separated peaks."""
+    sd = {}
+    for name, (shape, kind) in param_spec(model_cfg).items():
+        g = _gen(name, seed)
+        if kind == "count":
+            sd[name] = torch.zeros((), dtype=torch.long)
+            continue
+        if isinstance(kind, tuple):
+            k, fan = kind
+            gain = {"w": 1.0, "w_small": 0.5, "spw": 1.2, "spw_in": 1.2}[k]
+            t = torch.randn(shape, generator=g) * (gain / math.sqrt(fan))
+            if k == "spw_in":            # raw inputs: metres (|x|~30), intensity 0..255, dt
+                t[..., :3, :] /= 20.0
+                if shape[3] > 3:
+                    t[..., 3, :] /= 128.0
+        elif kind == "bn_w" or kind == "ln_w":
+            t = 0.8 + 0.4 * torch.rand(shape, generator=g)
+        elif kind == "bn_v":
+            t = 0.7 + 0.6 * torch.rand(shape, generator=g)
+        elif kind in ("bn_b", "bn_m", "b"):
+            t = 0.05 * torch.randn(shape, generator=g)
+        elif kind == "heat_b":
+            t = torch.full(shape, -2.19) + 0.05 * torch.randn(shape, generator=g)
+        elif kind == "offs_b":
+            t = 1.5 * torch.randn(shape, generator=g)
+        else:
+            raise KeyError(kind)
+        sd[name] = t.float()
+    return sd
+
+
+def synth_points(n_points, pc_range, seed=0, n_sweeps=10, n_beams=32, n_features=5):
+    """Seeded nuScenes-shaped multi-sweep cloud: log-uniform ranges over beams,
+    uniform azimuth, a ground plane, plus box-like clusters; intensity U(0,255); dt in {0,0.05,...}."""
+    rng = np.random.default_rng(seed)
+    r = np.asarray(pc_range, np.float32)
+    half = float(min(r[3], r[4]))
+    n_obj = n_points // 5
+    n_bg = n_points - n_obj
+    rad = np.exp(rng.uniform(np.log(1.0), np.log(half * 1.3), n_bg))
+    az = rng.uniform(-np.pi, np.pi, n_bg)
+    beam = rng.integers(0, n_beams, n_bg)
+    elev = np.deg2rad(-30.0 + 40.0 * beam / max(n_beams - 1, 1))
+    x, y = rad * np.cos(az), rad * np.sin(az)
+    z = np.maximum(rad * np.tan(elev) + 1.8 - 1.8, r[2] + 0.3 + 0.02 * rng.standard_normal(n_bg))
+    z = np.minimum(z, r[5] - 0.05)
+    # objects: gaussian blobs on the ground
+    n_boxes = 40
+    centers = rng.uniform(-half * 0.9, half * 0.9, (n_boxes, 2))
+    which = rng.integers(0, n_boxes, n_obj)
+    ox = centers[which, 0] + rng.normal(0, 0.8, n_obj)
+    oy = centers[which, 1] + rng.normal(0, 0.4, n_obj)
+    oz = r[2] + 0.5 + np.abs(rng.normal(0, 0.6, n_obj))
+    pts = np.zeros((n_points, n_features), np.float32)
+    pts[:, 0] = np.concatenate([x, ox])
+    pts[:, 1] = np.concatenate([y, oy])
+    pts[:, 2] = np.concatenate([z, oz])
+    if n_features > 3:
+        pts[:, 3] = rng.uniform(0, 255, n_points)
+    if n_features > 4:
+        pts[:, 4] = rng.integers(0, n_sweeps, n_points) * 0.05
+    perm = rng.permutation(n_points)
+    pts = pts[perm]
+    # PointsRangeFilter of the reference pipeline: keep in-range points only
+    m = ((pts[:, 0] > r[0]) & (pts[:, 0] < r[3]) & (pts[:, 1] > r[1]) & (pts[:, 1] < r[4])
+         & (pts[:, 2] > r[2]) & (pts[:, 2] < r[5]))
+    return np.ascontiguousarray(pts[m])

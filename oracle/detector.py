@@ -1,0 +1,85 @@
+"""Oracle: FocalFormer3D detector assembly (LiDAR-only eval forward).  TEST INFRASTRUCTURE.
+
+Follows ``projects/mmdet3d_plugin/models/detectors/focalformer3d.py``: extract_pts_feat :155-175,
+extract_feat :177-187, voxelize :189-209, simple_test_pts :306-319, simple_test :321-332.
+Module attribute names reproduce the reference state-dict keys so one
+state dict drives both this oracle and the CUDA product.
+"""
+import torch
+from torch import nn
+
+from .voxelize import voxelize_batch, HardSimpleVFE, HardVFE
+from .sparse import SparseEncoder
+from .bev import SECOND, SECONDFPN, FocalEncoder
+from .head import FocalDecoder
+
+
+def _strip(d):
+    return {k: v for k, v in d.items() if k != "type"}
+
+
+class FocalFormer3D(nn.Module):
+    def __init__(self, pts_voxel_layer=None, pts_voxel_encoder=None, pts_middle_encoder=None, pts_backbone=None,
+                 pts_neck=None, imgpts_neck=None, pts_bbox_head=None, train_cfg=None, test_cfg=None,
+                 input_img=True, input_pts=True, **unused):
+        super().__init__()
+        assert not input_img and input_pts, "oracle covers the LiDAR-only configs"
+        self.voxel_cfg = pts_voxel_layer
+        ve = _strip(pts_voxel_encoder)
+        if pts_voxel_encoder["type"] == "HardSimpleVFE":
+            self.pts_voxel_encoder = HardSimpleVFE(**ve)
+        else:
+            self.pts_voxel_encoder = HardVFE(in_channels=ve["in_channels"], feat_channels=ve["feat_channels"])
+        self.pts_middle_encoder = SparseEncoder(**_strip(pts_middle_encoder))
+        self.pts_backbone = SECOND(**_strip(pts_backbone))
+        self.pts_neck = SECONDFPN(**_strip(pts_neck))
+        self.imgpts_neck = FocalEncoder(**_strip(imgpts_neck))
+        head = _strip(pts_bbox_head)
+        head["test_cfg"] = test_cfg["pts"] if test_cfg and "pts" in test_cfg else test_cfg
+        self.pts_bbox_head = FocalDecoder(**head)
+
+    def voxelize(self, points):
+        mv = self.voxel_cfg["max_voxels"]
+        mv = mv[1] if isinstance(mv, (tuple, list)) else mv              # eval picks max_voxels[1]
+        return voxelize_batch(points, self.voxel_cfg["voxel_size"], self.voxel_cfg["point_cloud_range"],
+                              self.voxel_cfg["max_num_points"], mv)
+
+    @torch.no_grad()
+    def extract_pts_feat(self, points, stages=None):
+        voxels, num_points, coors = self.voxelize(points)
+        vf = self.pts_voxel_encoder(voxels, num_points, coors)
+        batch_size = int(coors[-1, 0]) + 1
+        x = self.pts_middle_encoder(vf, coors, batch_size)
+        if stages is not None:
+            stages.update(voxels=voxels, num_points=num_points, coors=coors, voxel_features=vf, middle=x)
+        x = self.pts_backbone(x)
+        if stages is not None:
+            stages["backbone"] = x
+        x = self.pts_neck(x)
+        if stages is not None:
+            stages["neck"] = x[0]
+        return x
+
+    @torch.no_grad()
+    def forward_raw(self, points, stages=None):
+        """points: list[B] of [Ni, F] -> (head output dict, list of per-scene result dicts)."""
+        pts_feats = self.extract_pts_feat(points, stages)
+        _, new_pts = self.imgpts_neck(None, pts_feats[0], None)
+        if stages is not None:
+            stages["conv_feat"] = new_pts[0]
+            stages["stage_feats"] = list(new_pts[1])
+        outs = self.pts_bbox_head([new_pts[0], list(new_pts[1])], None, None)
+        res = self.pts_bbox_head.get_bboxes(outs)
+        return outs[0][0], res
+
+    def simple_test(self, points, img_metas=None, img=None, rescale=False):
+        _, res = self.forward_raw(points)
+        return [dict(pts_bbox=dict(boxes_3d=r["boxes_3d"], scores_3d=r["scores_3d"], labels_3d=r["labels_3d"]))
+                for r in res]
+
+
+def build_oracle(model_cfg):
+    cfg = _strip(model_cfg)
+    m = FocalFormer3D(**cfg)
+    m.eval()
+    return m
