@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/sec of the FocalFormer3D_L per-scene forward (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # ours (libff3d.so), one process per GPU
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPUs (oracle port)
+
+A step = one forward of the hot path over one batch (--bs scenes per GPU, default 4 = BASELINE.json configs[1]:
+FocalFormer3D_L, synthetic nuScenes 10-sweep clouds of ~300k points, 0.075 m voxels, 180x180 BEV).  Pure data
+parallel: every rank runs its own scenes (weak scaling), NCCL only for the barrier / max-over-ranks timing.
+Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scenes/sec FocalFormer3D_L (nuScenes 10-sweep) forward"
+WORKLOAD = "FocalFormer3D_L LiDAR, synthetic nuScenes 10-sweep ~300k pts/scene, 0.075 m voxels, 180x180 BEV"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bs", type=int, default=4, help="scenes per GPU per step")
+    ap.add_argument("--points", type=int, default=300000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-scenes", type=int, default=1)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scenes(cfg, n_scenes, n_points, seed0):
+    import torch
+    from focalformer3d_b200.synth import synth_points
+    rng = cfg["pts_voxel_layer"]["point_cloud_range"]
+    return [torch.from_numpy(synth_points(n_points, rng, seed=seed0 + s)) for s in range(n_scenes)]
+
+
+def time_oracle(cfg, sd, scenes, warmup, steps):
+    """The reference algorithm (oracle port) on the host CPUs, all threads; one scene per step."""
+    import torch
+    from oracle.detector import build_oracle
+    torch.set_num_threads(os.cpu_count())
+    o = build_oracle(cfg)
+    o.load_state_dict(sd, strict=True)
+    for i in range(warmup):
+        o.simple_test([scenes[i % len(scenes)]])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        o.simple_test([scenes[(warmup + i) % len(scenes)]])
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from focalformer3d_b200.config import load_config, default_config_path
+    from focalformer3d_b200.synth import make_state_dict
+    cfg = load_config(default_config_path())["model"]
+    sd = make_state_dict(cfg, 0)
+    scenes = make_scenes(cfg, 2, args.points, 0)
+    sps, sec = time_oracle(cfg, sd, scenes, args.warmup, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenes_per_step": 1, "points_per_scene": args.points},
+        "cpu_baseline": {"value": sps, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"1 full-size scene per step x {args.steps} steps (oracle port of the reference algorithm: "
+                                   "rulebook gather+mm+scatter sparse conv, ATen conv2d, nn.MultiheadAttention, grid_sample MSDA; "
+                                   "the reference itself needs mmcv/mmdet3d/spconv which are not installable offline)"},
+        "e2e": {"value": sps, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def spconv_traffic(rec):
+    """algorithmic bytes/flops of one sparse conv launch: features in+out once, weights once, pairs."""
+    import torch
+    label, s, e, _, _, n_dev, meta = rec
+    n_out = int(n_dev.item())
+    nbr = meta["nbr"][:, :n_out]
+    pairs = int((nbr >= 0).sum().item())
+    n_in = int(torch.unique(nbr[nbr >= 0]).numel()) if pairs else 0
+    by = 4.0 * (n_in * meta["cin"] + n_out * meta["cout"] + meta["taps"] * meta["cin"] * meta["cout"]) + 8.0 * pairs
+    return by, 2.0 * pairs * meta["cin"] * meta["cout"], n_out, pairs
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from focalformer3d_b200.config import load_config, default_config_path
+    from focalformer3d_b200.synth import make_state_dict
+    from focalformer3d_b200.model import build_model
+    from focalformer3d_b200 import ops
+    cfg = load_config(default_config_path())["model"]
+    sd = make_state_dict(cfg, 0)
+    model = build_model(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.cuda().prepare("cuda")
+    # data-parallel sharding: rank r owns scenes r*bs .. r*bs+bs-1 of every step (DistributedSampler(shuffle=False) order)
+    host = [p.pin_memory() for p in make_scenes(cfg, args.bs, args.points, seed0=rank * args.bs)]
+    dev = [p.cuda() for p in host]
+    h2d = sum(p.numel() * 4 for p in host)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_dev():
+        model.forward_raw(dev)
+
+    d2h_bytes = [0]
+
+    def step_e2e():
+        pts = [p.cuda(non_blocking=True) for p in host]                       # H2D from pinned memory, every step
+        out = model.simple_test(pts)                                          # public API; results land on the host
+        d2h_bytes[0] = sum(o["pts_bbox"]["boxes_3d"].numel() * 4 + o["pts_bbox"]["scores_3d"].numel() * 4
+                           + o["pts_bbox"]["labels_3d"].numel() * 4 for o in out)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count
+    ms = timed(step_dev, args.steps)
+    launches = ops.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    scenes = args.bs * world * args.steps
+    value = scenes / (ms / 1e3)
+    e2e = scenes / (ms_e2e / 1e3)
+
+    # ---- instrumented passes (outside the timed region): per-stage ms and per-kernel roofline
+    stage_ms, roof = {}, None
+    if rank == 0:
+        reps = 3
+        agg = {}
+        for _ in range(reps):
+            ops.prof.start()
+            model.forward_raw(dev)
+            torch.cuda.synchronize()
+            ops.prof.stop()
+            for k, v in ops.prof.stage_ms().items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v / reps
+            for rec in ops.prof.records:
+                label, s, e, fl, by = rec[:5]
+                t = s.elapsed_time(e)
+                if fl is None:
+                    by, fl, _, _ = spconv_traffic(rec)
+                a = agg.setdefault(label, [0.0, 0.0, 0.0, 0])
+                a[0] += t / reps; a[1] += fl / reps; a[2] += by / reps; a[3] += 1
+        pk = peaks()
+        kinds = {"spconv": [0.0, 0.0, 0.0], "conv": [0.0, 0.0, 0.0], "linear": [0.0, 0.0, 0.0]}
+        for label, (t, fl, by, _) in agg.items():
+            k = "spconv" if label.startswith("spconv") else "conv" if label.startswith("conv") else "linear"
+            kinds[k][0] += t; kinds[k][1] += fl; kinds[k][2] += by
+        step_ms = sum(stage_ms.values())
+        dom = max(kinds, key=lambda k: kinds[k][0])
+        t, fl, by = kinds[dom]
+        if dom == "spconv":
+            ach = by / (t * 1e-3) / 1e9
+            roof = {"kernel": "igemm_kernel<SPARSE> (rulebook gather-GEMM, all SparseEncoder layers)", "bound": "hbm",
+                    "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                    "peak_source": pk["src"], "share_of_step": t / step_ms, "tflops": fl / (t * 1e-3) / 1e12}
+        else:
+            ach = fl / (t * 1e-3) / 1e12
+            name = "igemm_kernel<CONV2D> (dense BEV convs)" if dom == "conv" else "igemm_kernel<ROWS> (linear layers)"
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "share_of_step": t / step_ms,
+                    "note": "fp32 SIMT FMA path (parity-exact); tensor-pipe peak is the denominator the spec asks for"}
+        roof["by_kernel_family_ms"] = {k: round(v[0], 3) for k, v in kinds.items()}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sps, sec = time_oracle(cfg, sd, [h.clone() for h in host[:1]], 0, args.cpu_baseline_scenes)
+        cpu = {"value": sps, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{args.cpu_baseline_scenes} full-size scene(s), no warm-up (oracle port; {sec:.1f} s/scene)"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": args.bs, "global_batch": args.bs * world,
+                       "points_per_scene": args.points, "parallelism": f"dp{world}",
+                       "l2": "no flush needed: per-step activations (~2 GB) far exceed the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes[0],
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,306 @@
+// Hard voxelisation (deterministic, first-appearance voxel order, first max_points points per voxel in input
+// order) + per-voxel mean, for a whole batch in one pass and without any host synchronisation.
+//
+// Replaces the reference's per-sample loop over [upstream] mmdet3d hard_voxelize
+// (projects/mmdet3d_plugin/models/detectors/focalformer3d.py:189-209), whose CUDA path scans all earlier
+// points per point (O(N^2) worst case) and counts voxels in a <<<1,1>>> kernel.
+//
+// Algorithm (all O(N), HBM-bound):
+//   1. hash-insert every in-range point's voxel key; atomicMin keeps the FIRST point index per voxel
+//   2. flag first points, exclusive-scan the flags -> first-appearance rank of every voxel
+//   3. per-sample counts / caps / output bases (tiny kernel)
+//   4. every point inserts its index into its voxel's max_points-slot list with an atomicMin cascade:
+//      slot s ends up holding the (s+1)-th smallest point index, i.e. input order, deterministically
+//   5. gather: voxels[M,P,F], num_points, coors(b,z,y,x) and the mean over the kept points
+#include "common.cuh"
+
+namespace ff3d {
+
+constexpr int kEmptyIdx = 0x7f7f7f7f;
+constexpr int SCAN_ELEMS = 2048;  // per block (256 threads x 8)
+
+struct VoxP {
+  int n_total, n_feat, batch;
+  int off[FF3D_MAX_BATCH + 1];
+  float vs[3], r0[3];
+  int g[3];  // grid x,y,z
+  int max_points, max_voxels;
+};
+
+__device__ __forceinline__ int sample_of(const VoxP& p, int i) {
+  int b = 0;
+  while (b + 1 < p.batch && i >= p.off[b + 1]) ++b;
+  return b;
+}
+
+__global__ void vox_hash_kernel(const float* __restrict__ pts, VoxP p, uint32_t* hkeys, int* hfirst, int hmask,
+                                int* pt_slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_total) return;
+  const float* q = pts + (size_t)i * p.n_feat;
+  // same fp32 arithmetic as the reference op: floor((p - range_min) / voxel_size)
+  int cx = (int)floorf((q[0] - p.r0[0]) / p.vs[0]);
+  int cy = (int)floorf((q[1] - p.r0[1]) / p.vs[1]);
+  int cz = (int)floorf((q[2] - p.r0[2]) / p.vs[2]);
+  int slot = -1;
+  if (cx >= 0 && cx < p.g[0] && cy >= 0 && cy < p.g[1] && cz >= 0 && cz < p.g[2]) {
+    int b = sample_of(p, i);
+    uint32_t key = (uint32_t)(((b * p.g[2] + cz) * p.g[1] + cy) * p.g[0] + cx);
+    bool ins;
+    slot = hash_insert(hkeys, hmask, key, &ins);
+    atomicMin(&hfirst[slot], i);
+  }
+  pt_slot[i] = slot;
+}
+
+__global__ void vox_flag_kernel(const int* __restrict__ pt_slot, const int* __restrict__ hfirst, int n, int* flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = pt_slot[i];
+  flag[i] = (s >= 0 && hfirst[s] == i) ? 1 : 0;
+}
+
+// ---- 3-kernel exclusive scan over int32 (out has n+1 entries; out[n] = total)
+__global__ void scan_reduce_kernel(const int* __restrict__ in, int n, int* bsum) {
+  __shared__ int sh[8];
+  int base = blockIdx.x * SCAN_ELEMS;
+  int s = 0;
+  for (int k = threadIdx.x; k < SCAN_ELEMS; k += blockDim.x) {
+    int i = base + k;
+    if (i < n) s += in[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    bsum[blockIdx.x] = t;
+  }
+}
+__global__ void scan_bsum_kernel(int* bsum, int nb) {  // single block, in-place exclusive scan
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? bsum[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int incl = sh[threadIdx.x];
+    if (i < nb) bsum[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bsum[nb] = carry;
+}
+__global__ void scan_apply_kernel(const int* __restrict__ in, int n, const int* __restrict__ bsum, int* out) {
+  // 256 threads, 8 consecutive elements per thread
+  __shared__ int sh[256];
+  int base = blockIdx.x * SCAN_ELEMS + threadIdx.x * 8;
+  int v[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int run = bsum[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = bsum[gridDim.x];
+}
+
+int exclusive_scan_i32(const int* in, int* out, int n, int* bsum, cudaStream_t st) {
+  int nb = cdiv(n, SCAN_ELEMS);
+  scan_reduce_kernel<<<nb, 256, 0, st>>>(in, n, bsum);
+  scan_bsum_kernel<<<1, 1024, 0, st>>>(bsum, nb);
+  scan_apply_kernel<<<nb, 256, 0, st>>>(in, n, bsum, out);
+  return check_launch("exclusive_scan_i32");
+}
+
+// per-sample counts, caps and output bases.  meta: [0..B) rank_base, [B..2B) out_base
+__global__ void vox_meta_kernel(const int* __restrict__ rank, VoxP p, int* meta, int* n_voxels_dev) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int total = 0;
+  for (int b = 0; b < p.batch; ++b) {
+    int r0 = rank[p.off[b]], r1 = rank[p.off[b + 1]];
+    int c = r1 - r0;
+    if (c > p.max_voxels) c = p.max_voxels;
+    meta[b] = r0;
+    meta[p.batch + b] = total;
+    n_voxels_dev[1 + b] = c;
+    total += c;
+  }
+  n_voxels_dev[0] = total;
+}
+
+__global__ void vox_assign_kernel(const int* __restrict__ pt_slot, const int* __restrict__ hfirst,
+                                  const uint32_t* __restrict__ hkeys, const int* __restrict__ rank,
+                                  const int* __restrict__ meta, VoxP p, int* slots, int* coors) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_total) return;
+  int s = pt_slot[i];
+  if (s < 0) return;
+  int f = hfirst[s];
+  int b = sample_of(p, i);
+  int local = rank[f] - meta[b];
+  if (local >= p.max_voxels) return;  // voxel created after the cap: its points are dropped
+  int vid = meta[p.batch + b] + local;
+  if (f == i) {
+    uint32_t key = hkeys[s];
+    int x = key % p.g[0];
+    uint32_t r = key / p.g[0];
+    int y = r % p.g[1];
+    r /= p.g[1];
+    int z = r % p.g[2];
+    coors[vid * 4 + 0] = b;
+    coors[vid * 4 + 1] = z;
+    coors[vid * 4 + 2] = y;
+    coors[vid * 4 + 3] = x;
+  }
+  // atomicMin cascade: slot k keeps the (k+1)-th smallest point index of the voxel
+  int v = i;
+  int* sl = slots + (size_t)vid * p.max_points;
+  for (int k = 0; k < p.max_points; ++k) {
+    int old = atomicMin(&sl[k], v);
+    if (old == kEmptyIdx) break;
+    v = old > v ? old : v;
+  }
+}
+
+__global__ void vox_gather_kernel(const float* __restrict__ pts, const int* __restrict__ slots,
+                                  const int* __restrict__ n_voxels_dev, VoxP p, float* voxels, int* num_points,
+                                  float* mean_feats, int mean_ld) {
+  int vid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vid >= n_voxels_dev[0]) return;
+  const int* sl = slots + (size_t)vid * p.max_points;
+  float sum[8];
+  for (int c = 0; c < 8; ++c) sum[c] = 0.f;
+  int cnt = 0;
+  for (int k = 0; k < p.max_points; ++k) {
+    int pi = sl[k];
+    float* vo = voxels ? voxels + ((size_t)vid * p.max_points + k) * p.n_feat : nullptr;
+    if (pi != kEmptyIdx) {
+      ++cnt;
+      const float* q = pts + (size_t)pi * p.n_feat;
+      for (int c = 0; c < p.n_feat; ++c) {
+        float v = q[c];
+        if (c < 8) sum[c] += v;
+        if (vo) vo[c] = v;
+      }
+    } else if (vo) {
+      for (int c = 0; c < p.n_feat; ++c) vo[c] = 0.f;
+    }
+  }
+  num_points[vid] = cnt;
+  if (mean_feats) {
+    float inv = (float)cnt;
+    for (int c = 0; c < mean_ld; ++c) mean_feats[(size_t)vid * mean_ld + c] = (c < p.n_feat && c < 8) ? sum[c] / inv : 0.f;
+  }
+}
+
+static int next_pow2(long long v) {
+  long long p = 1;
+  while (p < v) p <<= 1;
+  return (int)p;
+}
+
+struct VoxWs {
+  size_t hkeys, hfirst, pt_slot, flag, rank, bsum, meta, slots, total;
+  int hsize;
+};
+static VoxWs vox_layout(int n_total, int batch, int max_voxels, int max_points) {
+  VoxWs w;
+  w.hsize = next_pow2(2LL * (n_total > 0 ? n_total : 1));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  w.hkeys = take(sizeof(uint32_t) * w.hsize);
+  w.hfirst = take(sizeof(int) * w.hsize);
+  w.pt_slot = take(sizeof(int) * (size_t)n_total);
+  w.flag = take(sizeof(int) * (size_t)n_total);
+  w.rank = take(sizeof(int) * ((size_t)n_total + 1));
+  w.bsum = take(sizeof(int) * (cdiv(n_total, SCAN_ELEMS) + 2));
+  w.meta = take(sizeof(int) * 2 * FF3D_MAX_BATCH);
+  w.slots = take(sizeof(int) * (size_t)batch * max_voxels * max_points);
+  w.total = o;
+  return w;
+}
+
+}  // namespace ff3d
+
+extern "C" size_t ff3d_voxelize_workspace_bytes(int n_total, int batch, int max_voxels, int max_points) {
+  return ff3d::vox_layout(n_total, batch, max_voxels, max_points).total;
+}
+
+extern "C" int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, const int* batch_offsets_host,
+                                  int batch, const float* voxel_size3, const float* pc_range6, int max_points,
+                                  int max_voxels, float* voxels, int* coors, int* num_points, float* mean_feats,
+                                  int mean_ld, int* n_voxels_dev, void* workspace, size_t workspace_bytes,
+                                  ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(batch >= 1 && batch <= FF3D_MAX_BATCH, "voxelize: batch=%d out of range", batch);
+  FF3D_REQUIRE(n_feat >= 3 && n_feat <= 8, "voxelize: n_feat=%d (3..8 supported)", n_feat);
+  FF3D_REQUIRE(points && coors && num_points && n_voxels_dev && workspace, "voxelize: null pointer");
+  FF3D_REQUIRE(max_points >= 1 && max_voxels >= 1, "voxelize: bad caps");
+  VoxP p;
+  p.n_total = n_total; p.n_feat = n_feat; p.batch = batch;
+  for (int b = 0; b <= batch; ++b) p.off[b] = batch_offsets_host[b];
+  FF3D_REQUIRE(p.off[0] == 0 && p.off[batch] == n_total, "voxelize: batch offsets do not cover n_total");
+  long long cells = batch;
+  for (int a = 0; a < 3; ++a) {
+    p.vs[a] = voxel_size3[a];
+    p.r0[a] = pc_range6[a];
+    p.g[a] = (int)lrintf((pc_range6[3 + a] - pc_range6[a]) / voxel_size3[a]);
+    cells *= p.g[a];
+  }
+  FF3D_REQUIRE(cells < 0xFFFFFFFFLL, "voxelize: grid too large for 32-bit voxel keys");
+  p.max_points = max_points; p.max_voxels = max_voxels;
+  VoxWs w = vox_layout(n_total, batch, max_voxels, max_points);
+  if (workspace_bytes < w.total) {
+    set_error("voxelize: workspace %zu < required %zu", workspace_bytes, w.total);
+    return FF3D_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  char* base = static_cast<char*>(workspace);
+  uint32_t* hkeys = reinterpret_cast<uint32_t*>(base + w.hkeys);
+  int* hfirst = reinterpret_cast<int*>(base + w.hfirst);
+  int* pt_slot = reinterpret_cast<int*>(base + w.pt_slot);
+  int* flag = reinterpret_cast<int*>(base + w.flag);
+  int* rank = reinterpret_cast<int*>(base + w.rank);
+  int* bsum = reinterpret_cast<int*>(base + w.bsum);
+  int* meta = reinterpret_cast<int*>(base + w.meta);
+  int* slots = reinterpret_cast<int*>(base + w.slots);
+  cudaMemsetAsync(hkeys, 0xFF, sizeof(uint32_t) * w.hsize, st);
+  cudaMemsetAsync(hfirst, 0x7f, sizeof(int) * w.hsize, st);
+  cudaMemsetAsync(slots, 0x7f, sizeof(int) * (size_t)batch * max_voxels * max_points, st);
+  if (n_total == 0) {
+    cudaMemsetAsync(n_voxels_dev, 0, sizeof(int) * (1 + batch), st);
+    return check_launch("voxelize(empty)");
+  }
+  int nb = cdiv(n_total, 256);
+  vox_hash_kernel<<<nb, 256, 0, st>>>(points, p, hkeys, hfirst, w.hsize - 1, pt_slot);
+  vox_flag_kernel<<<nb, 256, 0, st>>>(pt_slot, hfirst, n_total, flag);
+  int rc = exclusive_scan_i32(flag, rank, n_total, bsum, st);
+  if (rc) return rc;
+  vox_meta_kernel<<<1, 32, 0, st>>>(rank, p, meta, n_voxels_dev);
+  vox_assign_kernel<<<nb, 256, 0, st>>>(pt_slot, hfirst, hkeys, rank, meta, p, slots, coors);
+  vox_gather_kernel<<<cdiv((long long)batch * max_voxels, 128), 128, 0, st>>>(points, slots, n_voxels_dev, p, voxels,
+                                                                             num_points, mean_feats, mean_ld);
+  return check_launch("ff3d_voxelize_hard");
+}

@@ -1,0 +1,751 @@
+"""Host-side mirror of the reference's plugin modules for the per-scene forward path.
+
+Registered ``type`` strings (same as the reference registry): ``FocalFormer3D``
+(projects/mmdet3d_plugin/models/detectors/focalformer3d.py:26), ``FocalEncoder`` (models/necks/focal_encoder.py:89),
+``FocalDecoder`` (models/dense_heads/focal_decoder.py:33), ``TransFusionBBoxCoder``
+(core/bbox/coders/transfusion_bbox_coder.py:7) plus stand-ins for the upstream types the shipped configs name
+(``HardSimpleVFE``, ``SparseEncoder``, ``SECOND``, ``SECONDFPN``).  Every module is an ``nn.Module`` whose parameter
+names reproduce the reference checkpoint keys, so ``load_state_dict`` / ``load_checkpoint`` work unchanged; the
+arithmetic runs in libff3d.so (no PyTorch compute fallback: without the library the import of ``.ops`` fails).
+"""
+import math
+import torch
+from torch import nn
+
+from .config import DETECTORS, NECKS, HEADS, BBOX_CODERS, VOXEL_ENCODERS, MIDDLE_ENCODERS, BACKBONES
+from .synth import param_spec
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, ACT_RELU6
+
+
+# ------------------------------------------------------------------------------------------------ param tree
+class ParamTree(nn.Module):
+    """nn.Module whose (nested) parameter/buffer names are exactly the given spec keys."""
+
+    def build_params(self, spec):
+        for name, (shape, kind) in spec.items():
+            parts = name.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, ParamTree())
+                mod = mod._modules[p]
+            leaf = parts[-1]
+            if kind == "count":
+                mod.register_buffer(leaf, torch.zeros((), dtype=torch.long))
+            elif kind in ("bn_m", "bn_v"):
+                mod.register_buffer(leaf, torch.zeros(shape) if kind == "bn_m" else torch.ones(shape))
+            else:
+                mod.register_parameter(leaf, nn.Parameter(torch.zeros(shape), requires_grad=False))
+
+    def flat(self):
+        return {k: v.detach() for k, v in self.state_dict().items()}
+
+
+def sub_spec(spec, prefix):
+    n = len(prefix) + 1
+    return {k[n:]: v for k, v in spec.items() if k.startswith(prefix + ".")}
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def bn_scale_shift(sd, name, eps):
+    s = sd[name + ".weight"].double() / torch.sqrt(sd[name + ".running_var"].double() + eps)
+    b = sd[name + ".bias"].double() - sd[name + ".running_mean"].double() * s
+    return s, b
+
+
+def pack_taps(w_tco, dev):
+    """[taps, cin, cout] (float64/32) -> device fp32 [taps, pad4(cin), pad4(cout)]"""
+    t, ci, co = w_tco.shape
+    out = torch.zeros((t, _pad4(ci), _pad4(co)), dtype=torch.float32)
+    out[:, :ci, :co] = w_tco.float()
+    return out.contiguous().to(dev)
+
+
+def pack_conv2d(w, scale=None, dev="cuda"):
+    """nn.Conv2d weight [cout, cin, kh, kw] (optionally BN-scaled per cout) -> [kh*kw, cin, cout]."""
+    w = w.double()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1)
+    co, ci, kh, kw = w.shape
+    return pack_taps(w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co), dev)
+
+
+def pack_linear(w, scale=None, dev="cuda"):
+    """nn.Linear / Conv1d(k=1) weight [out, in(,1)] -> [1, in, out]."""
+    w = w.double().reshape(w.shape[0], -1)
+    if scale is not None:
+        w = w * scale.view(-1, 1)
+    return pack_taps(w.t().unsqueeze(0), dev)
+
+
+def vec(v, dev, n=None):
+    v = v.float()
+    if n is not None and v.numel() < n:
+        v = torch.cat([v, torch.zeros(n - v.numel())])
+    return v.contiguous().to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ components
+@VOXEL_ENCODERS.register_module()
+class HardSimpleVFE(ParamTree):
+    """[upstream] mmdet3d HardSimpleVFE: the mean is fused into ff3d_voxelize_hard (mean_feats output)."""
+
+    def __init__(self, num_features=4, **kw):
+        super().__init__()
+        self.num_features = num_features
+
+
+@MIDDLE_ENCODERS.register_module()
+class SparseEncoder(ParamTree):
+    """[upstream] mmdet3d v0.17.1 SparseEncoder (cfg FocalFormer3D_L.py:198-206) on the gather-GEMM kernel."""
+
+    def __init__(self, in_channels, sparse_shape, output_channels=128, base_channels=16,
+                 encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                 encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, (0, 1, 1)), (0, 0)), block_type="basicblock",
+                 order=("conv", "norm", "act"), spec=None, **kw):
+        super().__init__()
+        assert block_type == "basicblock" and tuple(order) == ("conv", "norm", "act")
+        self.in_channels, self.sparse_shape, self.output_channels = in_channels, tuple(sparse_shape), output_channels
+        self.base_channels, self.encoder_channels, self.encoder_paddings = base_channels, encoder_channels, encoder_paddings
+        self.build_params(spec)
+        self.pk = None
+        self.cap_growth = (4.0, 1.0, 1.0, 1.0)
+
+    def prepare(self, dev):
+        sd = self.flat()
+        eps = 1e-3
+
+        def sp(wname, bnname):
+            w = sd[wname].double()                           # [kD,kH,kW,cin,cout]
+            s, b = bn_scale_shift(sd, bnname, eps)
+            w = (w * s.view(1, 1, 1, 1, -1)).reshape(-1, w.shape[3], w.shape[4])
+            return pack_taps(w, dev), vec(b, dev)
+
+        pk = {"conv_input": sp("conv_input.0.weight", "conv_input.1")}
+        for i, blocks in enumerate(self.encoder_channels):
+            for j in range(len(blocks)):
+                q = f"encoder_layers.encoder_layer{i + 1}.{j}"
+                if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                    pk[q] = sp(f"{q}.0.weight", f"{q}.1")
+                else:
+                    pk[q + ".1"] = sp(f"{q}.conv1.weight", f"{q}.bn1")
+                    pk[q + ".2"] = sp(f"{q}.conv2.weight", f"{q}.bn2")
+        pk["conv_out"] = sp("conv_out.0.weight", "conv_out.1")
+        self.pk = pk
+
+    def forward(self, vox, batch, bev_out, overflow):
+        """vox: dict from ops.voxelize; bev_out [B,H,W,2*C] zero-initialised NHWC buffer (channel = d*C + c)."""
+        dev = vox["mean"].device
+        cap1 = vox["coors"].shape[0]
+        lvl = ops.SparseLevel(vox["coors"], vox["n_dev"][:1], cap1, batch, self.sparse_shape)
+        lvl.build_hash()
+        w, b = self.pk["conv_input"]
+        x = torch.empty((cap1, w.shape[-1]), dtype=torch.float32, device=dev)
+        ops.sparse_conv(vox["mean"], lvl.subm_map(), lvl.n_dev, w, b, x, act=ACT_RELU)
+        self.level_sizes = [lvl.n_dev]
+        for i, blocks in enumerate(self.encoder_channels):
+            for j, cout in enumerate(blocks):
+                q = f"encoder_layers.encoder_layer{i + 1}.{j}"
+                if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                    pad = self.encoder_paddings[i][j]
+                    p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
+                    cap_out = int(lvl.cap * self.cap_growth[i])
+                    nl, nbr = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow)
+                    w, b = self.pk[q]
+                    y = torch.empty((nl.cap, cout), dtype=torch.float32, device=dev)
+                    ops.sparse_conv(x, nbr, nl.n_dev, w, b, y, act=ACT_RELU)
+                    lvl, x = nl, y
+                    self.level_sizes.append(lvl.n_dev)
+                else:
+                    nbr = lvl.subm_map()
+                    w1, b1 = self.pk[q + ".1"]
+                    w2, b2 = self.pk[q + ".2"]
+                    t = torch.empty_like(x)
+                    ops.sparse_conv(x, nbr, lvl.n_dev, w1, b1, t, act=ACT_RELU)
+                    y = torch.empty_like(x)
+                    ops.sparse_conv(t, nbr, lvl.n_dev, w2, b2, y, act=ACT_RELU, res=x)
+                    x = y
+        # conv_out: SparseConv3d k(3,1,1) s(2,1,1) p0 + BN + ReLU, scattered straight into the NHWC BEV grid
+        nl, nbr = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), lvl.cap, overflow)
+        self.level_sizes.append(nl.n_dev)
+        Cc = self.output_channels
+        assert bev_out.shape[-1] == nl.shape[0] * Cc and bev_out.is_contiguous()
+        off = nl.bev_offsets(bev_out.shape[-1], Cc)
+        w, b = self.pk["conv_out"]
+        ops.sparse_conv(x, nbr, nl.n_dev, w, b, bev_out, act=ACT_RELU, y_off=off, cout=Cc)
+        return bev_out
+
+
+@BACKBONES.register_module()
+class SECOND(ParamTree):
+    """[upstream] mmdet3d SECOND (cfg FocalFormer3D_L.py:207-214)."""
+
+    def __init__(self, in_channels=128, out_channels=(128, 128, 256), layer_nums=(3, 5, 5), layer_strides=(2, 2, 2),
+                 norm_cfg=None, conv_cfg=None, spec=None, in_depth=1, **kw):
+        super().__init__()
+        self.in_channels, self.out_channels, self.layer_nums, self.layer_strides = in_channels, list(out_channels), list(layer_nums), list(layer_strides)
+        self.eps = (norm_cfg or {}).get("eps", 1e-3)
+        self.in_depth = in_depth
+        self.build_params(spec)
+        self.pk = None
+
+    def prepare(self, dev):
+        sd = self.flat()
+        self.pk = []
+        for i, n in enumerate(self.layer_nums):
+            layers = []
+            for l in range(n + 1):
+                w = sd[f"blocks.{i}.{3 * l}.weight"]
+                s, b = bn_scale_shift(sd, f"blocks.{i}.{3 * l + 1}", self.eps)
+                if i == 0 and l == 0 and self.in_depth > 1:
+                    # reference channel order after .dense().view is c*D + d; the BEV scatter writes d*C + c
+                    co, ci, kh, kw = w.shape
+                    D = self.in_depth
+                    w = w.view(co, ci // D, D, kh, kw).permute(0, 2, 1, 3, 4).reshape(co, ci, kh, kw)
+                layers.append((pack_conv2d(w, s, dev), vec(b, dev)))
+            self.pk.append(layers)
+
+    def forward(self, x):
+        outs = []
+        B, H, W, _ = x.shape
+        for i, layers in enumerate(self.pk):
+            st = self.layer_strides[i]
+            for l, (w, b) in enumerate(layers):
+                s = st if l == 0 else 1
+                Ho, Wo = ((H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1)
+                y = torch.empty((B, Ho, Wo, self.out_channels[i]), dtype=torch.float32, device=x.device)
+                ops.conv2d(x, w, b, y, 3, stride=s, act=ACT_RELU)
+                x, H, W = y, Ho, Wo
+            outs.append(x)
+        return outs
+
+
+@NECKS.register_module()
+class SECONDFPN(ParamTree):
+    """[upstream] mmdet3d SECONDFPN (cfg FocalFormer3D_L.py:215-222): level outputs written into channel slices."""
+
+    def __init__(self, in_channels=(128, 128, 256), out_channels=(256, 256, 256), upsample_strides=(1, 2, 4),
+                 norm_cfg=None, upsample_cfg=None, conv_cfg=None, use_conv_for_no_stride=False, spec=None, **kw):
+        super().__init__()
+        self.in_channels, self.out_channels, self.strides = list(in_channels), list(out_channels), list(upsample_strides)
+        self.use_conv = use_conv_for_no_stride
+        self.eps = (norm_cfg or {}).get("eps", 1e-3)
+        self.build_params(spec)
+        self.pk = None
+
+    def prepare(self, dev):
+        sd = self.flat()
+        self.pk = []
+        for i, oc in enumerate(self.out_channels):
+            st = self.strides[i]
+            s, b = bn_scale_shift(sd, f"deblocks.{i}.1", self.eps)
+            w = sd[f"deblocks.{i}.0.weight"].double()
+            if st > 1 or not self.use_conv:
+                # ConvTranspose2d [cin, cout, k, k], k == stride: one 1x1 GEMM per (dy, dx) output lattice
+                taps = [pack_taps((w[:, :, dy, dx] * s.view(1, -1)).unsqueeze(0), dev) for dy in range(st) for dx in range(st)]
+                self.pk.append(("deconv", st, taps, vec(b, dev)))
+            else:
+                self.pk.append(("conv", 1, pack_conv2d(w, s, dev), vec(b, dev)))
+
+    def forward(self, xs, out):
+        """xs: list of NHWC level tensors; out [B,H,W,sum(out_channels)]."""
+        c0 = 0
+        for i, (kind, st, w, b) in enumerate(self.pk):
+            oc = self.out_channels[i]
+            view = out[..., c0:c0 + oc]
+            if kind == "conv":
+                ops.conv2d(xs[i], w, b, view, 1, act=ACT_RELU)
+            else:
+                for dy in range(st):
+                    for dx in range(st):
+                        ops.conv2d(xs[i], w[dy * st + dx], b, view, 1, act=ACT_RELU, up=(st, dy, dx))
+            c0 += oc
+        return out
+
+
+class _IR:
+    """torchvision InvertedResidual (focal_encoder.py:36-38) packed: optional 1x1 expand, dw3x3, 1x1 project."""
+
+    def __init__(self, sd, name, expand, dev, eps=1e-5):
+        i = 0
+        self.expand = None
+        if expand != 1:
+            s, b = bn_scale_shift(sd, f"{name}.conv.0.1", eps)
+            self.expand = (pack_conv2d(sd[f"{name}.conv.0.0.weight"], s, dev), vec(b, dev))
+            i = 1
+        s, b = bn_scale_shift(sd, f"{name}.conv.{i}.1", eps)
+        wd = sd[f"{name}.conv.{i}.0.weight"].double() * s.view(-1, 1, 1, 1)          # [C,1,3,3]
+        self.dw = (wd.reshape(wd.shape[0], 9).t().contiguous().float().to(dev), vec(b, dev))
+        s, b = bn_scale_shift(sd, f"{name}.conv.{i + 2}", eps)
+        self.proj = (pack_conv2d(sd[f"{name}.conv.{i + 1}.weight"], s, dev), vec(b, dev))
+
+    def run(self, x, out, res=None):
+        B, H, W, _ = x.shape
+        hid = self.dw[0].shape[1]
+        if self.expand is not None:
+            t = torch.empty((B, H, W, hid), dtype=torch.float32, device=x.device)
+            ops.conv2d(x, self.expand[0], self.expand[1], t, 1, act=ACT_RELU6)
+            x = t
+        t2 = torch.empty((B, H, W, hid), dtype=torch.float32, device=x.device)
+        ops.dwconv3x3(x, self.dw[0], self.dw[1], t2, act=ACT_RELU6)
+        ops.conv2d(t2, self.proj[0], self.proj[1], out, 1, act=ACT_NONE, res=res)
+        return out
+
+
+@NECKS.register_module()
+class FocalEncoder(ParamTree):
+    """models/necks/focal_encoder.py:90-222, LiDAR-only 'bevfusionmb2' path (input_img=False, iterbev_wo_img=True)."""
+
+    def __init__(self, num_layers=2, in_channels_img=64, in_channels_pts=384, hidden_channel=128, bn_momentum=0.1,
+                 bias="auto", iterbev="bevfusion", max_points_height=5, multistage_heatmap=False, input_img=True,
+                 input_pts=True, iterbev_wo_img=False, extra_feat=False, iter_bev_cam=False, cam_lss=False,
+                 newbevpool=False, pc_range=None, img_scale=None, spec=None, **kw):
+        super().__init__()
+        if input_img or not input_pts or iterbev != "bevfusionmb2" or not iterbev_wo_img:
+            raise NotImplementedError("FocalEncoder: only the LiDAR-only bevfusionmb2 path is built (SURVEY.md 8f: "
+                                      "camera/fusion branches are the next scope row)")
+        self.num_layers = num_layers or 0
+        self.hidden = hidden_channel
+        self.multistage_heatmap, self.extra_feat = multistage_heatmap, extra_feat
+        self.build_params(spec)
+        self.pk = None
+
+    def prepare(self, dev):
+        sd = self.flat()
+        pk = {"shared": (pack_conv2d(sd["shared_conv_pts.weight"], None, dev), vec(sd["shared_conv_pts.bias"], dev))}
+        for i in range(self.num_layers):
+            q = f"fusion_blocks.{i}"
+            pk[q] = (_IR(sd, q + ".P_IML", 2, dev), _IR(sd, q + ".P_out_proj", 1, dev), _IR(sd, q + ".P_integration", 1, dev))
+        if self.extra_feat:
+            s, b = bn_scale_shift(sd, "extra_output.bn", 1e-5)
+            pk["extra"] = (pack_conv2d(sd["extra_output.conv.weight"], s, dev), vec(b, dev))
+        self.pk = pk
+
+    def forward(self, pts_feats, extra_out=None):
+        """pts_feats [B,H,W,512] NHWC.  Returns (conv_feat view, [stage feature views...], extra view)."""
+        B, H, W, _ = pts_feats.shape
+        dev, hc = pts_feats.device, self.hidden
+        cat1 = torch.empty((B, H, W, 2 * hc), dtype=torch.float32, device=dev)
+        feat = cat1[..., :hc]
+        ops.conv2d(pts_feats, self.pk["shared"][0], self.pk["shared"][1], feat, 3, act=ACT_NONE)   # :204
+        conv_feat = feat
+        stages = []
+        for i in range(self.num_layers):
+            iml, outp, integ = self.pk[f"fusion_blocks.{i}"]
+            cat2 = torch.empty((B, H, W, 2 * hc), dtype=torch.float32, device=dev)
+            cat2[..., hc:].copy_(feat)                                       # cat((P_Aug, lidar_feat)) :78
+            iml.run(feat, cat1[..., hc:], res=feat)                          # P2P = P_IML(lidar) :76 -> cat((lidar, P2P))
+            outp.run(cat1, cat2[..., :hc])                                   # :77
+            last = i == self.num_layers - 1
+            nxt = torch.empty((B, H, W, hc if last else 2 * hc), dtype=torch.float32, device=dev)
+            new_feat = nxt[..., :hc]
+            integ.run(cat2, new_feat)                                        # :78
+            stages.append(new_feat)
+            feat, cat1 = new_feat, nxt
+        extra = None
+        if self.extra_feat and stages:
+            extra = extra_out if extra_out is not None else torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
+            ops.conv2d(stages[-1], self.pk["extra"][0], self.pk["extra"][1], extra, 3, act=ACT_NONE)   # :218-219
+        return conv_feat, stages, extra
+
+
+@BBOX_CODERS.register_module()
+class TransFusionBBoxCoder:
+    """core/bbox/coders/transfusion_bbox_coder.py:8-22 (parameters only; decode runs in ff3d_box_decode)."""
+
+    def __init__(self, pc_range, out_size_factor, voxel_size, post_center_range=None, score_threshold=None,
+                 code_size=8, **kw):
+        self.pc_range, self.out_size_factor, self.voxel_size = list(pc_range), out_size_factor, list(voxel_size)
+        self.post_center_range, self.score_threshold, self.code_size = post_center_range, score_threshold, code_size
+        if score_threshold:
+            raise NotImplementedError("score_threshold > 0 is not used by any shipped config")
+
+    @property
+    def cell(self):
+        return (self.out_size_factor * self.voxel_size[0], self.out_size_factor * self.voxel_size[1])
+
+
+@HEADS.register_module()
+class FocalDecoder(ParamTree):
+    """models/dense_heads/focal_decoder.py:34 -- eval forward (:522-992) + get_bboxes (:1313-1413)."""
+
+    def __init__(self, num_proposals=128, hidden_channel=128, hidden_channel_roi=512, num_classes=4,
+                 num_decoder_layers=1, num_heads=8, initialize_by_heatmap=False, nms_kernel_size=1,
+                 common_heads=dict(), num_heatmap_convs=2, bias="auto", train_cfg=None, test_cfg=None, bbox_coder=None,
+                 multiscale=False, multistage_heatmap=False, reuse_first_heatmap=False, extra_feat=False,
+                 heatmap_box=False, bevpos=False, input_img=True, iterbev_wo_img=False, mask_heatmap_mode="poscls",
+                 roi_feats=0, roi_dropout_rate=0.0, roi_expand_ratio=1.0, roi_based_reg=False, classaware_reg=False,
+                 boxpos=None, decoder_cfg=None, spec=None, **unused):
+        super().__init__()
+        if not (initialize_by_heatmap and multiscale and bevpos and extra_feat and mask_heatmap_mode == "poscls") \
+                or heatmap_box or classaware_reg or boxpos is not None:
+            raise NotImplementedError("FocalDecoder: only the shipped FocalFormer3D LiDAR head variant is built")
+        stages = (multistage_heatmap or 0) + (1 if reuse_first_heatmap else 0)
+        if stages < 1:
+            raise NotImplementedError("FocalDecoder: single-stage (DeformFormer3D) head is a later scope row")
+        self.num_classes, self.num_proposals, self.hc = num_classes, num_proposals, hidden_channel
+        self.num_decoder_layers, self.num_heads = num_decoder_layers, num_heads
+        self.nms_kernel_size, self.test_cfg = nms_kernel_size, test_cfg
+        self.stages, self.reuse_first = stages, reuse_first_heatmap
+        self.roi_feats, self.roi_based_reg = roi_feats, roi_based_reg
+        self.roi_expand_ratio = [roi_expand_ratio] * num_decoder_layers if isinstance(roi_expand_ratio, float) else list(roi_expand_ratio)
+        self.roi_step = 4 if roi_dropout_rate > 1e-4 else 3
+        self.common_heads = dict(common_heads)
+        self.bbox_coder = BBOX_CODERS.build(bbox_coder)
+        tl = decoder_cfg["transformerlayers"]
+        self.n_layers = decoder_cfg["num_layers"]
+        self.ffn_ch = tl["feedforward_channels"]
+        m = tl["attn_cfgs"][1]
+        self.n_levels, self.n_points = m["num_levels"], m["num_points"]
+        assert tl["attn_cfgs"][0]["num_heads"] == num_heads and m["num_heads"] == num_heads
+        ds = test_cfg["dataset"]
+        self.exempt = (8, 9) if ds == "nuScenes" else (1, 2) if ds == "Waymo" else (1, 0)
+        # hard-coded in the reference (focal_decoder.py:903-906), NOT the config range
+        self.roi_range = (-54.0, -54.0, 54.0, 54.0) if ds == "nuScenes" else (-75.2, -75.2, 75.2, 75.2)
+        self.has_vel = "vel" in self.common_heads
+        self.build_params(spec)
+        self.pk = None
+
+    # ---- weights
+    def prepare(self, dev):
+        sd = self.flat()
+        hc, nc = self.hc, self.num_classes
+        pk = {}
+
+        def heat(name):
+            s, b = bn_scale_shift(sd, f"{name}.0.bn", 1e-5)
+            return (pack_conv2d(sd[f"{name}.0.conv.weight"], s, dev), vec(b, dev),
+                    pack_conv2d(sd[f"{name}.1.weight"], None, dev), vec(sd[f"{name}.1.bias"], dev))
+        pk["heat"] = []
+        for i in range(self.stages):
+            pk["heat"].append(heat("heatmap_head") if (i == 0 and self.reuse_first) else heat(f"heatmap_head_img.{i}"))
+        pk["cls_w"] = sd["class_encoding.weight"].reshape(hc, nc).t().contiguous().float().to(dev)      # [C, Cf]
+        pk["cls_b"] = vec(sd["class_encoding.bias"], dev)
+        for n in ("dconv", "dconv2"):
+            s, b = bn_scale_shift(sd, f"{n}.bn", 1e-5)
+            pk[n] = (pack_conv2d(sd[f"{n}.conv.weight"], s, dev), vec(b, dev))
+        if self.roi_feats:
+            g2, L = self.roi_feats ** 2, self.n_levels
+            w0 = sd["roi_mlp.0.weight"].double()                           # [512, (lvl, c, pt)] focal_decoder.py:919
+            w0 = w0.view(w0.shape[0], L, hc, g2).permute(0, 1, 3, 2).reshape(w0.shape[0], -1)   # -> (lvl, pt, c)
+            ws = [w0, sd[f"roi_mlp.{self.roi_step}.weight"].double(), sd[f"roi_mlp.{2 * self.roi_step}.weight"].double()]
+            pk["roi"] = []
+            for i, w in enumerate(ws):
+                s, b = bn_scale_shift(sd, f"roi_mlp.{i * self.roi_step + 1}", 1e-5)
+                pk["roi"].append((pack_linear(w, s, dev), vec(b, dev)))
+        pk["dim_t"] = (10000 ** (2 * (torch.arange(128, dtype=torch.float32) // 2) / 128)).to(dev)
+        pk["stage"] = []
+        for i in range(self.num_decoder_layers):
+            st = {"pos": [(pack_linear(sd[f"pos_embed_learned.{i}.layers.{j}.weight"], None, dev),
+                           vec(sd[f"pos_embed_learned.{i}.layers.{j}.bias"], dev)) for j in range(2)]}
+            layers, vw, vb = [], [], []
+            for j in range(self.n_layers):
+                q = f"decoder.{i}.layers.{j}"
+                ipw, ipb = sd[f"{q}.attentions.0.attn.in_proj_weight"], sd[f"{q}.attentions.0.attn.in_proj_bias"]
+                lay = dict(
+                    qk=(pack_linear(ipw[:2 * hc], None, dev), vec(ipb[:2 * hc], dev)),
+                    v=(pack_linear(ipw[2 * hc:], None, dev), vec(ipb[2 * hc:], dev)),
+                    o=(pack_linear(sd[f"{q}.attentions.0.attn.out_proj.weight"], None, dev),
+                       vec(sd[f"{q}.attentions.0.attn.out_proj.bias"], dev)),
+                    oa=(pack_linear(torch.cat([sd[f"{q}.attentions.1.sampling_offsets.weight"],
+                                               sd[f"{q}.attentions.1.attention_weights.weight"]]), None, dev),
+                        vec(torch.cat([sd[f"{q}.attentions.1.sampling_offsets.bias"],
+                                       sd[f"{q}.attentions.1.attention_weights.bias"]]), dev)),
+                    op=(pack_linear(sd[f"{q}.attentions.1.output_proj.weight"], None, dev),
+                        vec(sd[f"{q}.attentions.1.output_proj.bias"], dev)),
+                    f1=(pack_linear(sd[f"{q}.ffns.0.layers.0.0.weight"], None, dev), vec(sd[f"{q}.ffns.0.layers.0.0.bias"], dev)),
+                    f2=(pack_linear(sd[f"{q}.ffns.0.layers.1.weight"], None, dev), vec(sd[f"{q}.ffns.0.layers.1.bias"], dev)),
+                    ln=[(vec(sd[f"{q}.norms.{n}.weight"], dev), vec(sd[f"{q}.norms.{n}.bias"], dev)) for n in range(3)])
+                layers.append(lay)
+                vw.append(sd[f"{q}.attentions.1.value_proj.weight"])
+                vb.append(sd[f"{q}.attentions.1.value_proj.bias"])
+            st["layers"] = layers
+            st["vproj"] = (pack_linear(torch.cat(vw), None, dev), vec(torch.cat(vb), dev))   # 3 layers batched: N = 3*hc
+            # prediction heads: 6 x (Conv1d hc->64 + BN + ReLU, Conv1d 64->k): one GEMM + one block-diagonal GEMM
+            names = list(self.common_heads.keys()) + ["heatmap"]
+            ks = [self.common_heads[n][0] for n in self.common_heads] + [nc]
+            w1, b1 = [], []
+            w2 = torch.zeros((sum(ks), 64 * len(names)), dtype=torch.float64)
+            b2, r0 = [], 0
+            for hi, (n, k) in enumerate(zip(names, ks)):
+                q = f"prediction_heads.{i}.{n}"
+                s, b = bn_scale_shift(sd, f"{q}.0.bn", 1e-5)
+                w1.append(sd[f"{q}.0.conv.weight"].double().reshape(64, hc) * s.view(-1, 1))
+                b1.append(b)
+                w2[r0:r0 + k, hi * 64:(hi + 1) * 64] = sd[f"{q}.1.weight"].double().reshape(k, 64)
+                b2.append(sd[f"{q}.1.bias"].double())
+                r0 += k
+            st["head1"] = (pack_linear(torch.cat(w1), None, dev), vec(torch.cat(b1), dev))
+            st["head2"] = (pack_linear(w2, None, dev), vec(torch.cat(b2), dev, _pad4(sum(ks))))
+            st["pred_dim"] = sum(ks)
+            pk["stage"].append(st)
+        self.pk = pk
+        self._bev_pos_cache = {}
+
+    def _bev_pos_embed(self, i, geom, W0, H0, dev):
+        """pos_embed_learned[i](sine(bev_pos / (W,H))) for all pyramid cells (focal_decoder.py:883-885): input
+        independent, computed once per (stage, geometry) with the same kernels and cached."""
+        key = (i, tuple(geom.shapes))
+        if key not in self._bev_pos_cache:
+            pos = []
+            for lvl, (h, w) in enumerate(geom.shapes):
+                scale = float(2 ** lvl)
+                ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+                pos.append(torch.stack([(xs + 0.5) * scale, (ys + 0.5) * scale], -1).reshape(-1, 2))
+            pos = torch.cat(pos).contiguous().to(dev)
+            self._bev_pos_cache[key] = self._pos_mlp(i, pos, W0, H0)
+        return self._bev_pos_cache[key]
+
+    def _pos_mlp(self, i, pos, W0, H0):
+        st = self.pk["stage"][i]
+        sine = ops.sine_embed(pos, W0, H0, self.pk["dim_t"])
+        h = ops.linear(sine, st["pos"][0][0], st["pos"][0][1], act=ACT_RELU)
+        return ops.linear(h, st["pos"][1][0], st["pos"][1][1])
+
+    # ---- forward
+    def forward(self, conv_feat, stage_feats, ms_value, geom):
+        """conv_feat / stage_feats: NHWC views [B,H,W,hc]; ms_value [B, n_tokens, hc] with level 0 (= extra feature)
+        already written.  Returns the reference's head dict (channel-major tensors) plus raw token-major state."""
+        pk = self.pk
+        B, H, W, hc = conv_feat.shape
+        dev = conv_feat.device
+        nc, k = self.num_classes, self.num_proposals
+        nq = k * self.stages
+        feats = ([conv_feat] if self.reuse_first else []) + list(stage_feats)
+        assert len(feats) == self.stages
+        # --- HIP stages (:588-791)
+        acc_mask = torch.ones((B, nc, H, W), dtype=torch.float32, device=dev)
+        q_feat = torch.empty((B * nq, hc), dtype=torch.float32, device=dev)
+        q_pos = torch.empty((B * nq, 2), dtype=torch.float32, device=dev)
+        q_score = torch.empty((B * nq, nc), dtype=torch.float32, device=dev)
+        q_label = torch.empty((B * nq,), dtype=torch.int32, device=dev)
+        dense_heatmaps, nms_heats, tops = [], [], []
+        for s in range(self.stages):
+            w1, b1, w2, b2 = pk["heat"][s]
+            t = torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
+            ops.conv2d(feats[s], w1, b1, t, 3, act=ACT_RELU)
+            logits = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)
+            ops.conv2d(t, w2, b2, logits[..., :nc], 3, act=ACT_NONE)
+            nms_heat = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
+            top = torch.empty((B, k), dtype=torch.int32, device=dev)
+            ops.hip_stage(logits, acc_mask, nms_heat, feats[s], pk["cls_w"], pk["cls_b"], k, self.nms_kernel_size,
+                          self.exempt, s * k, nq, top, q_feat, q_pos, q_score, q_label)
+            dense_heatmaps.append(logits)
+            nms_heats.append(nms_heat)
+            tops.append(top)
+            ops.mark(f"hip_stage{s}")
+        # --- multi-scale pyramid (:810-823): dconv / dconv2 write levels 1, 2 of the value buffer
+        lv = [ms_value[:, geom.starts[l]:geom.starts[l] + h * w].view(B, h, w, hc) for l, (h, w) in enumerate(geom.shapes)]
+        ops.conv2d(lv[0], pk["dconv"][0], pk["dconv"][1], lv[1], 3, stride=2, act=ACT_RELU)
+        ops.conv2d(lv[1], pk["dconv2"][0], pk["dconv2"][1], lv[2], 3, stride=2, act=ACT_RELU)
+        ops.mark("pyramid")
+        # --- decoder stages (:826-958)
+        preds, prev = [], None
+        x = q_feat
+        heads, d = self.num_heads, hc // self.num_heads
+        LP = self.n_levels * self.n_points
+        n_off = heads * LP * 2
+        for i in range(self.num_decoder_layers):
+            st = pk["stage"][i]
+            qpe = self._pos_mlp(i, q_pos, W, H)                                           # :869-872
+            bev_pe = self._bev_pos_embed(i, geom, W, H, dev)
+            valin = torch.empty_like(ms_value)
+            ops.add_bcast_rows(ms_value, bev_pe, valin)                                    # :886
+            vproj = ops.linear(valin.view(B * geom.n_tokens, hc), st["vproj"][0], st["vproj"][1])
+            vproj = vproj.view(B, geom.n_tokens, -1)
+            ops.mark(f"pos+value_proj{i}")
+            if self.roi_feats and prev is not None:                                        # :890-922
+                g = self.roi_feats
+                roi = torch.empty((B * nq, self.n_levels * g * g * hc), dtype=torch.float32, device=dev)
+                ops.roi_sample(prev, ms_value, geom, hc, g, self.roi_expand_ratio[i], self.bbox_coder.cell,
+                               self.bbox_coder.pc_range, self.roi_range, roi, B, nq)
+                h1 = ops.linear(roi, pk["roi"][0][0], pk["roi"][0][1], act=ACT_RELU)
+                h2 = ops.linear(h1, pk["roi"][1][0], pk["roi"][1][1], act=ACT_RELU)
+                x = ops.linear(h2, pk["roi"][2][0], pk["roi"][2][1], act=ACT_RELU, res=x, res_after_act=True)
+                ops.mark(f"roi{i}")
+            for j in range(self.n_layers):                                                 # [upstream] decoder layer
+                lay = st["layers"][j]
+                qk = ops.linear(x, lay["qk"][0], lay["qk"][1], x2=qpe)
+                v = ops.linear(x, lay["v"][0], lay["v"][1])
+                att = torch.empty((B * nq, hc), dtype=torch.float32, device=dev)
+                ops.mha_core(qk[:, :hc], qk[:, hc:], v, att, B, nq, heads, d)
+                y = ops.linear(att, lay["o"][0], lay["o"][1], res=x)
+                x1 = ops.layernorm(y, *lay["ln"][0])
+                oa = ops.linear(x1, lay["oa"][0], lay["oa"][1], x2=qpe)
+                samp = torch.empty((B * nq, hc), dtype=torch.float32, device=dev)
+                ops.msda(vproj, j * hc, geom, self.n_points, q_pos, W, H, oa[:, :n_off], oa[:, n_off:], samp, B, nq, heads, d)
+                y = ops.linear(samp, lay["op"][0], lay["op"][1], res=x1)
+                x2_ = ops.layernorm(y, *lay["ln"][1])
+                f = ops.linear(x2_, lay["f1"][0], lay["f1"][1], act=ACT_RELU)
+                y = ops.linear(f, lay["f2"][0], lay["f2"][1], res=x2_)
+                x = ops.layernorm(y, *lay["ln"][2])
+            hh = ops.linear(x, st["head1"][0], st["head1"][1], act=ACT_RELU)               # :939
+            pred = ops.linear(hh, st["head2"][0], st["head2"][1], cout=st["pred_dim"])
+            q_pos = q_pos.clone()
+            ops.head_update(pred, q_pos, prev if (self.roi_based_reg and prev is not None) else None)   # :945-957
+            preds.append(pred)
+            prev = pred
+            ops.mark(f"decoder{i}")
+        self._state = dict(B=B, nq=nq, q_score=q_score, q_label=q_label, last=preds[-1])
+        return self._pack(preds, q_score, q_label, dense_heatmaps, nms_heats, tops, B, nq, q_feat)
+
+    def _pack(self, preds, q_score, q_label, dense_heatmaps, nms_heats, tops, B, nq, q_feat0):
+        """Reference output layout (:960-992): per-key [B, k, n_stage*nq] channel-major tensors."""
+        cols, c0 = {}, 0
+        for n, (kdim, _) in self.common_heads.items():
+            cols[n] = (c0, c0 + kdim)
+            c0 += kdim
+        cols["heatmap"] = (c0, c0 + self.num_classes)
+        res = {}
+        for n, (a, b) in cols.items():
+            res[n] = torch.cat([p[:, a:b].reshape(B, nq, b - a).transpose(1, 2) for p in preds], dim=-1)
+        res["query_heatmap_score"] = q_score.view(B, nq, -1).transpose(1, 2)
+        nc = self.num_classes
+        res["dense_heatmap"] = [l[..., :nc].permute(0, 3, 1, 2) for l in dense_heatmaps]
+        res["query_labels"] = q_label.view(B, nq).long()
+        res["_nms_heatmap"] = nms_heats
+        res["_top_proposals"] = tops
+        res["_query_feat0"] = q_feat0.view(B, nq, -1)
+        self._cls_col = cols["heatmap"][0]
+        return res
+
+    def get_bboxes(self):
+        """get_bboxes (:1313-1413) with nms_type=None, generalised over the batch.  Returns device tensors:
+        boxes [B,nq,code-1], scores [B,nq], labels [B,nq], keep [B,nq]."""
+        st = self._state
+        B, nq = st["B"], st["nq"]
+        dev = st["last"].device
+        code = 9 if self.has_vel else 7
+        boxes = torch.empty((B * nq, code), dtype=torch.float32, device=dev)
+        scores = torch.empty((B * nq,), dtype=torch.float32, device=dev)
+        labels = torch.empty((B * nq,), dtype=torch.int32, device=dev)
+        keep = torch.empty((B * nq,), dtype=torch.uint8, device=dev)
+        bc = self.bbox_coder
+        ops.box_decode(st["last"], self._cls_col, self.has_vel, st["q_score"], st["q_label"], self.num_classes, bc.cell,
+                       bc.pc_range, bc.post_center_range, boxes, scores, labels, keep)
+        return boxes.view(B, nq, code), scores.view(B, nq), labels.view(B, nq), keep.view(B, nq)
+
+
+@DETECTORS.register_module()
+class FocalFormer3D(nn.Module):
+    """models/detectors/focalformer3d.py:27 -- inference forward (simple_test :321-332) on libff3d.so."""
+
+    def __init__(self, pts_voxel_layer=None, pts_voxel_encoder=None, pts_middle_encoder=None, pts_backbone=None,
+                 pts_neck=None, imgpts_neck=None, pts_bbox_head=None, train_cfg=None, test_cfg=None, input_img=True,
+                 input_pts=True, img_backbone=None, img_neck=None, **unused):
+        super().__init__()
+        if input_img or not input_pts or img_backbone is not None:
+            raise NotImplementedError("FocalFormer3D: camera / fusion configs are the next scope row (SURVEY.md 8f)")
+        cfg = dict(pts_voxel_layer=pts_voxel_layer, pts_voxel_encoder=pts_voxel_encoder,
+                   pts_middle_encoder=pts_middle_encoder, pts_backbone=pts_backbone, pts_neck=pts_neck,
+                   imgpts_neck=imgpts_neck, pts_bbox_head=pts_bbox_head, test_cfg=test_cfg)
+        spec = param_spec(cfg)
+        self.voxel_cfg = dict(pts_voxel_layer)
+        self.pts_voxel_encoder = VOXEL_ENCODERS.build(pts_voxel_encoder)
+        self.pts_middle_encoder = MIDDLE_ENCODERS.build(pts_middle_encoder, spec=sub_spec(spec, "pts_middle_encoder"))
+        depth = self._bev_depth(self.pts_middle_encoder)
+        self.pts_backbone = BACKBONES.build(pts_backbone, spec=sub_spec(spec, "pts_backbone"), in_depth=depth)
+        self.pts_neck = NECKS.build(pts_neck, spec=sub_spec(spec, "pts_neck"))
+        self.imgpts_neck = NECKS.build(imgpts_neck, spec=sub_spec(spec, "imgpts_neck"))
+        tcfg = test_cfg["pts"] if (test_cfg and "pts" in test_cfg) else test_cfg
+        self.pts_bbox_head = HEADS.build(pts_bbox_head, spec=sub_spec(spec, "pts_bbox_head"), test_cfg=tcfg)
+        self._prepared_on = None
+
+    @staticmethod
+    def _bev_depth(me):
+        d = me.sparse_shape[0]
+        for i, blocks in enumerate(me.encoder_channels[:-1]):
+            pad = me.encoder_paddings[i][len(blocks) - 1]
+            pz = pad[0] if isinstance(pad, (list, tuple)) else pad
+            d = (d + 2 * pz - 3) // 2 + 1
+        return (d - 3) // 2 + 1
+
+    def prepare(self, device="cuda"):
+        """Fold BatchNorm, pack weights into kernel layouts on the device (call after load_state_dict)."""
+        dev = torch.device(device)
+        for m in (self.pts_middle_encoder, self.pts_backbone, self.pts_neck, self.imgpts_neck, self.pts_bbox_head):
+            m.prepare(dev)
+        self._prepared_on = dev
+        return self
+
+    # ---- the hot path
+    @torch.no_grad()
+    def forward_raw(self, points, keep_stages=False):
+        """points: list[B] of CUDA float32 [Ni, F].  Returns (head dict, (boxes, scores, labels, keep), stages)."""
+        if self._prepared_on is None:
+            raise RuntimeError("call model.prepare(device) after loading weights")
+        dev = self._prepared_on
+        B = len(points)
+        offs = [0]
+        for p in points:
+            offs.append(offs[-1] + int(p.shape[0]))
+        allp = torch.cat([p.to(dev, torch.float32) for p in points], 0).contiguous() if B > 1 else points[0].to(dev, torch.float32).contiguous()
+        vc = self.voxel_cfg
+        mv = vc["max_voxels"]
+        mv = mv[1] if isinstance(mv, (tuple, list)) else mv
+        mv = min(mv, max(int(p.shape[0]) for p in points))
+        ops.mark("start")
+        vox = ops.voxelize(allp, offs, vc["voxel_size"], vc["point_cloud_range"], vc["max_num_points"], mv,
+                           mean_ld=_pad4(max(self.pts_middle_encoder.in_channels, 8)), want_voxels=keep_stages)
+        ops.mark("voxelize+vfe")
+        me = self.pts_middle_encoder
+        depth = self._bev_depth(me)
+        H, W = me.sparse_shape[1] // 8, me.sparse_shape[2] // 8
+        bev = torch.zeros((B, H, W, depth * me.output_channels), dtype=torch.float32, device=dev)
+        overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+        me(vox, B, bev, overflow)
+        ops.mark("sparse_encoder")
+        xs = self.pts_backbone(bev)
+        ops.mark("second")
+        neck = torch.empty((B, H, W, sum(self.pts_neck.out_channels)), dtype=torch.float32, device=dev)
+        self.pts_neck(xs, neck)
+        ops.mark("secondfpn")
+        head = self.pts_bbox_head
+        geom = ops.LevelGeom([(H >> l, W >> l) for l in range(head.n_levels)])
+        ms_value = torch.empty((B, geom.n_tokens, head.hc), dtype=torch.float32, device=dev)
+        extra_view = ms_value[:, :H * W].view(B, H, W, head.hc)
+        conv_feat, stage_feats, extra = self.imgpts_neck(neck, extra_out=extra_view)
+        ops.mark("focal_encoder")
+        res = head(conv_feat, stage_feats, ms_value, geom)
+        det = head.get_bboxes()
+        ops.mark("heads+decode")
+        self._overflow = overflow
+        stages = None
+        if keep_stages:
+            stages = dict(vox=vox, bev=bev, backbone=xs, neck=neck, conv_feat=conv_feat, stage_feats=stage_feats,
+                          extra=extra, ms_value=ms_value, overflow=overflow, level_sizes=me.level_sizes)
+        return res, det, stages
+
+    def simple_test(self, points, img_metas=None, img=None, rescale=False):
+        """Reference signature (focalformer3d.py:321): list of dict(pts_bbox=dict(boxes_3d, scores_3d, labels_3d)) on CPU."""
+        _, (boxes, scores, labels, keep), _ = self.forward_raw(points)
+        if int(self._overflow.item()):
+            raise RuntimeError("sparse encoder level capacity exceeded; raise SparseEncoder.cap_growth")
+        out = []
+        for b in range(boxes.shape[0]):
+            m = keep[b].bool()
+            bx, sc, lb = boxes[b][m], scores[b][m], labels[b][m]
+            if bx.shape[0] > 200:                                     # focal_decoder.py:1395-1400
+                inds = sc.argsort(descending=True, stable=True)[:200]
+                bx, sc, lb = bx[inds], sc[inds], lb[inds]
+            out.append(dict(pts_bbox=dict(boxes_3d=bx.cpu(), scores_3d=sc.cpu(), labels_3d=lb.cpu())))
+        return out
+
+    def forward(self, return_loss=False, rescale=True, points=None, img_metas=None, img=None, **kw):
+        """[upstream] Base3DDetector.forward -> forward_test -> simple_test(points[0], img_metas[0], img[0])."""
+        if return_loss:
+            raise NotImplementedError("training is outside the hot path built here (SURVEY.md 8f row 4)")
+        return self.simple_test(points[0], img_metas[0] if img_metas else None, img[0] if img else None, rescale)
+
+
+def build_model(model_cfg, test_cfg=None):
+    """tools/test.py:202-203 build_model(cfg.model, test_cfg=cfg.get('test_cfg'))."""
+    cfg = dict(model_cfg)
+    if test_cfg is not None and cfg.get("test_cfg") is None:
+        cfg["test_cfg"] = test_cfg
+    return DETECTORS.build(cfg)

@@ -1,0 +1,366 @@
+"""Operator-level host API over the C ABI (include/ff3d.h).  torch is used for device memory and the stream only.
+
+Feature maps are NHWC views: a tensor whose last dim is contiguous; the row stride (``ld``) and batch stride are
+read from the view, so channel slices of wider buffers (concat-free ``torch.cat`` replacements) work directly.
+"""
+import ctypes as C
+import torch
+
+from . import lib as L
+from .lib import lib, check, GemmDesc, ACT_NONE, ACT_RELU, ACT_RELU6, GEMM_ROWS, GEMM_CONV2D, GEMM_SPARSE  # noqa: F401
+
+launch_count = 0   # number of ff3d kernel-launching C calls (bench.py reports kernel launches from this)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk_f32(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise L.Ff3dError(f"{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    if t.stride(-1) != 1:
+        raise L.Ff3dError(f"{name}: last dim must be contiguous")
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+class Profiler:
+    """Optional CUDA-event instrumentation (off in the timed benchmark region): per-op (label, ms, flops, bytes)
+    records and stage markers for the per-stage ms the headline metric asks for."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []      # (label, start, end, flops, bytes, n_dev_or_None, meta)
+        self.marks = []        # (name, event)
+
+    def start(self):
+        self.enabled, self.records, self.marks = True, [], []
+
+    def stop(self):
+        self.enabled = False
+
+    def mark(self, name):
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, start, label, flops, nbytes, n_dev=None, meta=None):
+        if start is None:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.records.append((label, start, e, flops, nbytes, n_dev, meta))
+
+    def stage_ms(self):
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+prof = Profiler()
+mark = prof.mark
+
+
+# --------------------------------------------------------------------------------------------------------------
+def linear(x, w, bias=None, out=None, act=ACT_NONE, res=None, x2=None, cout=None, res_after_act=False):
+    """y = act(x @ w + bias (+ res)).  x [M, cin] row view (ld from stride), w packed [1, cin, ldw]."""
+    _chk_f32(x, "linear.x")
+    M, cin = x.shape
+    ldw = w.shape[-1]
+    cout = cout or ldw
+    if out is None:
+        out = torch.empty((M, cout), device=x.device, dtype=torch.float32)
+    d = GemmDesc()
+    d.mode, d.M, d.cin, d.cout, d.taps = GEMM_ROWS, M, cin, cout, 1
+    d.x, d.ldx, d.x2 = x.data_ptr(), x.stride(0), (x2.data_ptr() if x2 is not None else None)
+    if x2 is not None and x2.stride(0) != x.stride(0):
+        raise L.Ff3dError("linear: x2 must share x's row stride")
+    d.w, d.ldw, d.bias = w.data_ptr(), ldw, (bias.data_ptr() if bias is not None else None)
+    d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
+    d.y, d.ldy, d.act = out.data_ptr(), out.stride(0), act
+    d.res_after_act = 1 if res_after_act else 0
+    t0 = prof.begin()
+    check(lib.ff3d_igemm(C.byref(d), _stream()), "ff3d_igemm(rows)")
+    prof.end(t0, f"linear[{cin}x{cout}]", 2.0 * M * cin * cout, 4.0 * (M * cin + cin * cout + M * cout))
+    _count()
+    return out
+
+
+def _nhwc_geom(t, name):
+    _chk_f32(t, name)
+    B, H, W, Cc = t.shape
+    ld = t.stride(2)
+    if t.stride(1) != W * ld or t.stride(0) % ld != 0:
+        raise L.Ff3dError(f"{name}: not an NHWC view (strides {t.stride()})")
+    return B, H, W, Cc, ld, t.stride(0) // ld
+
+
+def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=None):
+    """NHWC conv: x [B,H,W,cin] view, w packed [k*k, cin, ldw], out [B,Ho*u,Wo*u,cout] view.
+    ``up=(u, dy, dx)`` writes onto the (oy*u+dy, ox*u+dx) lattice (transposed conv with kernel == stride)."""
+    B, H, W, cin, ldx, xbs = _nhwc_geom(x, "conv2d.x")
+    Bo, Hy, Wy, cout, ldy, ybs = _nhwc_geom(out, "conv2d.out")
+    pad = (k // 2) if pad is None else pad
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    u, dy, dx = up if up else (1, 0, 0)
+    if (Bo, Hy, Wy) != (B, Ho * u, Wo * u):
+        raise L.Ff3dError(f"conv2d: out shape {tuple(out.shape)} != expected {(B, Ho * u, Wo * u, cout)}")
+    d = GemmDesc()
+    d.mode, d.M, d.cin, d.cout, d.taps = GEMM_CONV2D, B * Ho * Wo, cin, cout, k * k
+    d.x, d.ldx = x.data_ptr(), ldx
+    d.w, d.ldw, d.bias = w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
+    if res is not None:
+        rB, rH, rW, rC, ldr, rbs = _nhwc_geom(res, "conv2d.res")
+        if rbs != rH * rW or (rB, rH, rW) != (B, Ho, Wo) or u != 1:
+            raise L.Ff3dError("conv2d: residual must be a batch-dense NHWC view of the output shape")
+        d.res, d.ldres = res.data_ptr(), ldr
+    d.y, d.ldy, d.act = out.data_ptr(), ldy, act
+    d.B, d.H, d.W, d.Ho, d.Wo, d.kh, d.kw, d.stride, d.pad = B, H, W, Ho, Wo, k, k, stride, pad
+    d.x_bstride, d.y_bstride, d.y_row0 = xbs, ybs, 0
+    d.ux, d.uy, d.dx, d.dy = u, u, dx, dy
+    t0 = prof.begin()
+    check(lib.ff3d_igemm(C.byref(d), _stream()), "ff3d_igemm(conv2d)")
+    Mo = B * Ho * Wo
+    prof.end(t0, f"conv{k}x{k}s{stride}[{cin}->{cout}@{Ho}]", 2.0 * Mo * k * k * cin * cout,
+             4.0 * (B * H * W * cin + k * k * cin * cout + Mo * cout))
+    _count()
+    return out
+
+
+def sparse_conv(x, nbr, n_dev, w, bias, out, act=ACT_RELU, res=None, y_off=None, cout=None):
+    """Rulebook gather-GEMM: x [cap_in, cin] rows, nbr [taps, cap_out] int32, out [cap_out, cout] rows
+    (or an arbitrary buffer when ``y_off`` gives per-row element offsets)."""
+    _chk_f32(x, "sparse_conv.x")
+    taps, cap = nbr.shape
+    cin = x.shape[1]
+    cout = cout or w.shape[-1]
+    d = GemmDesc()
+    d.mode, d.M, d.m_dev, d.cin, d.cout, d.taps = GEMM_SPARSE, cap, n_dev.data_ptr(), cin, cout, taps
+    d.x, d.ldx = x.data_ptr(), x.stride(0)
+    d.w, d.ldw, d.bias = w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
+    d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
+    d.y, d.ldy, d.act = out.data_ptr(), (out.stride(0) if y_off is None else 0), act
+    d.nbr, d.nbr_stride = nbr.data_ptr(), nbr.stride(0)
+    d.y_off = y_off.data_ptr() if y_off is not None else None
+    t0 = prof.begin()
+    check(lib.ff3d_igemm(C.byref(d), _stream()), "ff3d_igemm(sparse)")
+    prof.end(t0, f"spconv[{taps}t {cin}->{cout}]", None, None, n_dev, dict(nbr=nbr, cin=cin, cout=cout, taps=taps,
+                                                                            x_rows=x.shape[0]))
+    _count()
+    return out
+
+
+def dwconv3x3(x, w, bias, out, act=ACT_RELU6):
+    B, H, W, Cc, ldx, xbs = _nhwc_geom(x, "dwconv.x")
+    _, _, _, _, ldy, ybs = _nhwc_geom(out, "dwconv.out")
+    if xbs != H * W or ybs != H * W:
+        raise L.Ff3dError("dwconv3x3: batch-dense views required")
+    check(lib.ff3d_dwconv3x3(_ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(out), ldy, B, H, W, Cc, act, _stream()),
+          "ff3d_dwconv3x3")
+    _count()
+    return out
+
+
+def layernorm(x, gamma, beta, out=None, eps=1e-5):
+    _chk_f32(x, "layernorm.x")
+    assert x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    check(lib.ff3d_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.shape[0], x.shape[1], eps, _stream()),
+          "ff3d_layernorm")
+    _count()
+    return out
+
+
+def add_bcast_rows(a, p, out):
+    """out[b] = a[b] + p for a [B, rows, C] contiguous, p [rows, C]."""
+    assert a.is_contiguous() and p.is_contiguous() and out.is_contiguous()
+    B, rows, Cc = a.shape
+    check(lib.ff3d_add_bcast_rows(_ptr(a), _ptr(p), _ptr(out), B, rows, Cc, _stream()), "ff3d_add_bcast_rows")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+def voxelize(points, batch_offsets, voxel_size, pc_range, max_points, max_voxels, mean_ld=8, want_voxels=False):
+    """points [N, F] (samples concatenated), batch_offsets python list [B+1].
+    Returns dict(coors [cap,4], num_points [cap], mean [cap, mean_ld], n_dev [1+B] (total, per sample), voxels?)."""
+    _chk_f32(points, "voxelize.points")
+    assert points.is_contiguous()
+    N, F = points.shape
+    B = len(batch_offsets) - 1
+    cap = B * max_voxels
+    dev = points.device
+    ws_bytes = lib.ff3d_voxelize_workspace_bytes(N, B, max_voxels, max_points)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    nump = torch.empty((cap,), dtype=torch.int32, device=dev)
+    mean = torch.empty((cap, mean_ld), dtype=torch.float32, device=dev)
+    n_dev = torch.empty((1 + B,), dtype=torch.int32, device=dev)
+    voxels = torch.empty((cap, max_points, F), dtype=torch.float32, device=dev) if want_voxels else None
+    check(lib.ff3d_voxelize_hard(_ptr(points), N, F, L.int_array(batch_offsets), B, L.float_array(voxel_size),
+                                 L.float_array(pc_range), max_points, max_voxels, _ptr(voxels), _ptr(coors),
+                                 _ptr(nump), _ptr(mean), mean_ld, _ptr(n_dev), _ptr(ws), ws_bytes, _stream()),
+          "ff3d_voxelize_hard")
+    _count(9)
+    return dict(coors=coors, num_points=nump, mean=mean, n_dev=n_dev, voxels=voxels)
+
+
+def next_pow2(v):
+    p = 1
+    while p < v:
+        p <<= 1
+    return p
+
+
+class SparseLevel:
+    """One resolution level of the sparse encoder: coordinates, device row count, hash."""
+
+    def __init__(self, coors, n_dev, cap, batch, shape):
+        self.coors, self.n_dev, self.cap, self.batch, self.shape = coors, n_dev, cap, batch, tuple(shape)
+        self.hsize = next_pow2(2 * cap)
+        self.hkeys = torch.empty((self.hsize,), dtype=torch.int32, device=coors.device)
+        self.hvals = torch.empty((self.hsize,), dtype=torch.int32, device=coors.device)
+        self.subm = None
+
+    def build_hash(self):
+        D, H, W = self.shape
+        check(lib.ff3d_sp_hash_build(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W,
+                                     _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _stream()), "ff3d_sp_hash_build")
+        _count(2)
+
+    def subm_map(self):
+        if self.subm is None:
+            D, H, W = self.shape
+            self.subm = torch.empty((27, self.cap), dtype=torch.int32, device=self.coors.device)
+            check(lib.ff3d_sp_subm_map(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W,
+                                       _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _ptr(self.subm), _stream()),
+                  "ff3d_sp_subm_map")
+            _count()
+        return self.subm
+
+    def downsample(self, k3, s3, p3, cap_out, overflow):
+        """Returns (new level with its hash built, nbr [kvol, cap_out])."""
+        D, H, W = self.shape
+        oshape = tuple((self.shape[i] + 2 * p3[i] - k3[i]) // s3[i] + 1 for i in range(3))
+        cells = self.batch * oshape[0] * oshape[1] * oshape[2]
+        cap_out = int(min(cap_out, cells))
+        dev = self.coors.device
+        coors_o = torch.empty((cap_out, 4), dtype=torch.int32, device=dev)
+        n_o = torch.empty((1,), dtype=torch.int32, device=dev)
+        lvl = SparseLevel(coors_o, n_o, cap_out, self.batch, oshape)
+        kvol = k3[0] * k3[1] * k3[2]
+        nbr = torch.empty((kvol, cap_out), dtype=torch.int32, device=dev)
+        check(lib.ff3d_sp_down_build(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W,
+                                     _ptr(self.hkeys), _ptr(self.hvals), self.hsize, L.int_array(k3), L.int_array(s3),
+                                     L.int_array(p3), _ptr(coors_o), _ptr(n_o), cap_out, oshape[0], oshape[1], oshape[2],
+                                     _ptr(lvl.hkeys), _ptr(lvl.hvals), lvl.hsize, _ptr(nbr), _ptr(overflow), _stream()),
+              "ff3d_sp_down_build")
+        _count(5)
+        return lvl, nbr
+
+    def bev_offsets(self, ld, Cc):
+        D, H, W = self.shape
+        off = torch.empty((self.cap,), dtype=torch.int32, device=self.coors.device)
+        check(lib.ff3d_sp_bev_offsets(_ptr(self.coors), _ptr(self.n_dev), self.cap, H, W, ld, Cc, _ptr(off), _stream()),
+              "ff3d_sp_bev_offsets")
+        _count()
+        return off
+
+
+# --------------------------------------------------------------------------------------------------------------
+def hip_stage(logits, acc_mask, nms_heat, feat, cls_w, cls_b, k, nms_kernel, exempt, q0, nq_total, top_idx,
+              query_feat, query_pos, query_score, query_label):
+    B, H, W, _, ldl, _ = _nhwc_geom(logits, "hip.logits")
+    _, _, _, Cf, ldf, fbs = _nhwc_geom(feat, "hip.feat")
+    if fbs != H * W:
+        raise L.Ff3dError("hip_stage: batch-dense feature view required")
+    Cc = acc_mask.shape[1]
+    ws_bytes = lib.ff3d_hip_workspace_bytes(B, Cc, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=logits.device)
+    check(lib.ff3d_hip_stage(_ptr(logits), ldl, _ptr(acc_mask), _ptr(nms_heat), _ptr(feat), ldf, Cf, _ptr(cls_w),
+                             _ptr(cls_b), B, Cc, H, W, k, nms_kernel, exempt[0], exempt[1], q0, nq_total, _ptr(top_idx),
+                             _ptr(query_feat), _ptr(query_pos), _ptr(query_score), _ptr(query_label), _ptr(ws),
+                             ws_bytes, _stream()), "ff3d_hip_stage")
+    _count(4)
+
+
+def sine_embed(pos, w, h, dim_t, out=None):
+    rows = pos.shape[0]
+    out = torch.empty((rows, 256), dtype=torch.float32, device=pos.device) if out is None else out
+    check(lib.ff3d_sine_embed(_ptr(pos), float(w), float(h), _ptr(dim_t), _ptr(out), rows, _stream()), "ff3d_sine_embed")
+    _count()
+    return out
+
+
+def mha_core(q, k, v, out, B, Nq, heads, d):
+    check(lib.ff3d_mha_core(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
+                            B, Nq, heads, d, _stream()), "ff3d_mha_core")
+    _count()
+    return out
+
+
+class LevelGeom:
+    def __init__(self, shapes):
+        self.shapes = [(int(h), int(w)) for h, w in shapes]
+        self.starts, s = [], 0
+        for h, w in self.shapes:
+            self.starts.append(s)
+            s += h * w
+        self.n_tokens = s
+        self.h = L.int_array([h for h, _ in self.shapes])
+        self.w = L.int_array([w for _, w in self.shapes])
+        self.s = L.int_array(self.starts)
+        self.L = len(self.shapes)
+
+
+def msda(value, v_col0, geom, P, ref, ref_w, ref_h, offs, attw, out, B, Nq, heads, d):
+    """value [B, n_tokens, ldv] contiguous; offs/attw row views of one [B*Nq, *] buffer."""
+    ldv = value.stride(1)
+    check(lib.ff3d_msda(_ptr(value), ldv, v_col0, value.stride(0) // ldv, geom.h, geom.w, geom.s, geom.L, P, _ptr(ref),
+                        float(ref_w), float(ref_h), _ptr(offs), offs.stride(0), _ptr(attw), attw.stride(0), _ptr(out),
+                        B, Nq, heads, d, _stream()), "ff3d_msda")
+    _count()
+    return out
+
+
+def roi_sample(query_box, value, geom, Cc, g, expand, cell, origin, roi_range, out, B, Nq):
+    ldv = value.stride(1)
+    check(lib.ff3d_roi_sample(_ptr(query_box), query_box.stride(0), _ptr(value), ldv, value.stride(0) // ldv, geom.h,
+                              geom.w, geom.s, geom.L, Cc, g, float(expand), float(cell[0]), float(cell[1]),
+                              float(origin[0]), float(origin[1]), L.float_array(roi_range), _ptr(out), B, Nq, _stream()),
+          "ff3d_roi_sample")
+    _count()
+    return out
+
+
+def head_update(pred, query_pos, prev):
+    check(lib.ff3d_head_update(_ptr(pred), pred.stride(0), _ptr(query_pos), _ptr(prev),
+                               prev.stride(0) if prev is not None else 0, pred.shape[0], _stream()), "ff3d_head_update")
+    _count()
+
+
+def box_decode(pred, cls_col, has_vel, query_score, query_label, Cc, cell, origin, post_range, boxes, scores, labels,
+               keep):
+    check(lib.ff3d_box_decode(_ptr(pred), pred.stride(0), cls_col, 1 if has_vel else 0, _ptr(query_score),
+                              _ptr(query_label), pred.shape[0], Cc, float(cell[0]), float(cell[1]), float(origin[0]),
+                              float(origin[1]), L.float_array(post_range), _ptr(boxes), _ptr(scores), _ptr(labels),
+                              _ptr(keep), _stream()), "ff3d_box_decode")
+    _count()

@@ -211,38 +211,40 @@ def make_state_dict(model_cfg, seed=0):
 
 
 def synth_points(n_points, pc_range, seed=0, n_sweeps=10, n_beams=32, n_features=5):
-    """Seeded nuScenes-shaped multi-sweep cloud: log-uniform ranges over beams,
-    uniform azimuth, a ground plane, plus box-like clusters; intensity U(0,255); dt in {0,0.05,...}."""
+    """Seeded nuScenes-shaped multi-sweep cloud: one base sweep (log-uniform ranges over the
+    beams, uniform azimuth, ground plane, box-like clusters) replicated n_sweeps times with centimetre jitter --
+    the sweeps of a mostly static scene overlap, which is what gives ~2-3 points per occupied voxel;
+    intensity U(0,255); dt = sweep * 0.05 s; shuffled; range-filtered like the reference's PointsRangeFilter."""
     rng = np.random.default_rng(seed)
     r = np.asarray(pc_range, np.float32)
     half = float(min(r[3], r[4]))
-    n_obj = n_points // 5
-    n_bg = n_points - n_obj
+    n_base = max(n_points // n_sweeps, 1)
+    n_obj = n_base // 5
+    n_bg = n_base - n_obj
     rad = np.exp(rng.uniform(np.log(1.0), np.log(half * 1.3), n_bg))
     az = rng.uniform(-np.pi, np.pi, n_bg)
     beam = rng.integers(0, n_beams, n_bg)
     elev = np.deg2rad(-30.0 + 40.0 * beam / max(n_beams - 1, 1))
     x, y = rad * np.cos(az), rad * np.sin(az)
-    z = np.maximum(rad * np.tan(elev) + 1.8 - 1.8, r[2] + 0.3 + 0.02 * rng.standard_normal(n_bg))
+    z = np.maximum(rad * np.tan(elev), r[2] + 0.3 + 0.02 * rng.standard_normal(n_bg))
     z = np.minimum(z, r[5] - 0.05)
-    # objects: gaussian blobs on the ground
     n_boxes = 40
     centers = rng.uniform(-half * 0.9, half * 0.9, (n_boxes, 2))
     which = rng.integers(0, n_boxes, n_obj)
     ox = centers[which, 0] + rng.normal(0, 0.8, n_obj)
     oy = centers[which, 1] + rng.normal(0, 0.4, n_obj)
     oz = r[2] + 0.5 + np.abs(rng.normal(0, 0.6, n_obj))
+    base = np.stack([np.concatenate([x, ox]), np.concatenate([y, oy]), np.concatenate([z, oz])], 1)
+    reps = -(-n_points // n_base)
+    xyz = np.concatenate([base + rng.normal(0, 0.03, base.shape) for _ in range(reps)])[:n_points]
+    sweep = np.repeat(np.arange(reps), n_base)[:n_points]
     pts = np.zeros((n_points, n_features), np.float32)
-    pts[:, 0] = np.concatenate([x, ox])
-    pts[:, 1] = np.concatenate([y, oy])
-    pts[:, 2] = np.concatenate([z, oz])
+    pts[:, :3] = xyz
     if n_features > 3:
         pts[:, 3] = rng.uniform(0, 255, n_points)
     if n_features > 4:
-        pts[:, 4] = rng.integers(0, n_sweeps, n_points) * 0.05
-    perm = rng.permutation(n_points)
-    pts = pts[perm]
-    # PointsRangeFilter of the reference pipeline: keep in-range points only
+        pts[:, 4] = (sweep % n_sweeps) * 0.05
+    pts = pts[rng.permutation(n_points)]
     m = ((pts[:, 0] > r[0]) & (pts[:, 0] < r[3]) & (pts[:, 1] > r[1]) & (pts[:, 1] < r[4])
          & (pts[:, 2] > r[2]) & (pts[:, 2] < r[5]))
     return np.ascontiguousarray(pts[m])

@@ -1,0 +1,210 @@
+/*
+ * ff3d.h -- C ABI of libff3d.so: the sm_100a kernels behind the FocalFormer3D per-scene forward path.
+ *
+ * Boundary rules
+ *   - plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated here.
+ *   - every entry point returns 0 on success, a negative FF3D_E* code otherwise;
+ *     ff3d_last_error() returns a thread-local message for the last failure.
+ *   - all launches are asynchronous on the given stream; no host synchronisation happens inside,
+ *     data-dependent sizes (voxel counts, active-site counts) stay in device memory (`*_dev` args).
+ *
+ * Each entry point names the reference interface it replaces.  Paths are relative to the reference
+ * repository (NVlabs/FocalFormer3D @ d5bb555); [upstream] marks the pinned third-party op the
+ * reference calls at that site (mmdet3d v0.17.1 / mmcv-full 1.3.18, not vendored in the reference tree).
+ */
+#ifndef FF3D_H_
+#define FF3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FF3D_OK 0
+#define FF3D_EINVAL (-1)   /* bad argument / unsupported shape */
+#define FF3D_ECUDA (-2)    /* CUDA runtime error at launch */
+#define FF3D_EWORKSPACE (-3)
+
+#define FF3D_ACT_NONE 0
+#define FF3D_ACT_RELU 1
+#define FF3D_ACT_RELU6 2
+
+#define FF3D_MAX_BATCH 64
+
+typedef void* ff3d_stream_t; /* cudaStream_t */
+
+const char* ff3d_last_error(void);
+int ff3d_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hard voxelisation + voxel feature mean.
+ * Replaces: [upstream] mmdet3d.ops.voxel hard_voxelize (deterministic) as called per sample from
+ *   projects/mmdet3d_plugin/models/detectors/focalformer3d.py:189-209 (FocalFormer3D.voxelize) and
+ *   [upstream] HardSimpleVFE at focalformer3d.py:166.
+ * points: [n_total, n_feat] fp32, the B samples concatenated; batch_offsets (HOST) [batch+1] row offsets.
+ * Outputs are sized for cap = batch*max_voxels rows:
+ *   voxels [cap, max_points, n_feat] (may be NULL), coors [cap,4] int32 (b,z,y,x), num_points [cap] int32,
+ *   mean_feats [cap, mean_ld] (may be NULL; columns >= n_feat are written as 0),
+ *   n_voxels_dev [1 + batch] int32: total, then per-sample counts.
+ * Voxel order = sample-major, first-appearance order inside a sample (the reference's order).
+ */
+size_t ff3d_voxelize_workspace_bytes(int n_total, int batch, int max_voxels, int max_points);
+int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, const int* batch_offsets_host, int batch,
+                       const float* voxel_size3, const float* pc_range6, int max_points, int max_voxels,
+                       float* voxels, int* coors, int* num_points, float* mean_feats, int mean_ld,
+                       int* n_voxels_dev, void* workspace, size_t workspace_bytes, ff3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse-conv rulebooks (output-stationary neighbour maps).
+ * Replaces: [upstream] mmdet3d.ops.spconv get_indice_pairs (indice_cuda.cu) as used by every
+ *   SubMConv3d / SparseConv3d of SparseEncoder (focalformer3d.py:168; cfg FocalFormer3D_L.py:198-206).
+ * A level is (coors [cap,4] int32 (b,z,y,x), n_dev int32[1], dense shape D,H,W, batch).  The hash table is
+ *   (hkeys uint32[hsize], hvals int32[hsize]), hsize a power of two >= 2*cap; the caller memsets nothing:
+ *   ff3d_sp_hash_build clears it.  nbr maps are [taps, cap] int32, -1 = no neighbour.
+ */
+int ff3d_sp_hash_build(const int* coors, const int* n_dev, int cap, int batch, int D, int H, int W,
+                       uint32_t* hkeys, int* hvals, int hsize, ff3d_stream_t stream);
+/* SubM k=3 p=1: nbr[t][o] = row of the site at coors[o] + (kz-1,ky-1,kx-1), t = (kz*3+ky)*3+kx */
+int ff3d_sp_subm_map(const int* coors, const int* n_dev, int cap, int batch, int D, int H, int W,
+                     const uint32_t* hkeys, const int* hvals, int hsize, int* nbr, ff3d_stream_t stream);
+/* SparseConv3d (kernel k3, stride s3, padding p3): creates the output level (coors_out, n_out_dev, its hash)
+ * and nbr_out [kvol, cap_out]: input row feeding output o through tap t (i = o*s - p + k).
+ * overflow_dev int32[1] is set to 1 if more than cap_out output sites exist. */
+int ff3d_sp_down_build(const int* coors_in, const int* n_in_dev, int cap_in, int batch, int D, int H, int W,
+                       const uint32_t* hkeys_in, const int* hvals_in, int hsize_in,
+                       const int* k3, const int* s3, const int* p3,
+                       int* coors_out, int* n_out_dev, int cap_out, int Do, int Ho, int Wo,
+                       uint32_t* hkeys_out, int* hvals_out, int hsize_out, int* nbr_out, int* overflow_dev,
+                       ff3d_stream_t stream);
+/* element offsets for scattering the last sparse level straight into the NHWC BEV grid:
+ * off[o] = ((b*H + y)*W + x)*ld + z*C   (replaces SparseConvTensor.dense() + view, [upstream]) */
+int ff3d_sp_bev_offsets(const int* coors, const int* n_dev, int cap, int H, int W, int ld, int C, int* off,
+                        ff3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM: y[row(m), n] = act( sum_{t,c} x[src(m,t), c] * w[t, c, n] + bias[n] + res[m, n] )
+ * One kernel family covers
+ *   mode FF3D_GEMM_ROWS   : linear / 1x1 conv (src(m,0) = m)                      -- F.linear, nn.Conv1d(k=1)
+ *   mode FF3D_GEMM_CONV2D : NHWC conv, kh x kw window, stride, zero padding        -- cuDNN conv2d in the reference
+ *   mode FF3D_GEMM_SPARSE : rulebook gather (src = nbr[t][m])                      -- [upstream] spconv indice_conv
+ * Replaces: [upstream] mmdet3d.ops.spconv indice_conv (gather + torch::mm + scatter-add per offset), the cuDNN
+ *   convs of SECOND/SECONDFPN (focalformer3d.py:169-171), FocalEncoder (focal_encoder.py:204-219), the head's
+ *   ConvModules (focal_decoder.py:588,637,819-823) and every nn.Linear / Conv1d of the decoder
+ *   (focal_decoder.py:872-939).  BatchNorm(eval) is folded into w/bias by the host.
+ */
+#define FF3D_GEMM_ROWS 0
+#define FF3D_GEMM_CONV2D 1
+#define FF3D_GEMM_SPARSE 2
+
+typedef struct ff3d_gemm_desc {
+  int mode;
+  int M;               /* rows (ROWS/CONV2D: exact; SPARSE: capacity) */
+  const int* m_dev;    /* optional device row count (SPARSE); NULL -> M */
+  int cin, cout, taps; /* cin % 4 == 0 */
+  const float* x; int ldx;         /* input rows, ldx % 4 == 0 */
+  const float* x2;                 /* optional second addend of the A operand (ROWS mode): A = x + x2 */
+  const float* w; int ldw;         /* [taps, cin, ldw], ldw % 4 == 0, ldw >= cout */
+  const float* bias;               /* [cout] or NULL */
+  const float* res; int ldres;     /* residual rows (indexed like y rows without the offset map) or NULL */
+  float* y; int ldy;
+  int act;
+  /* CONV2D geometry: input [B, H, W, cin] with batch stride x_bstride rows; output [B, Ho*uy, Wo*ux, *] */
+  int B, H, W, Ho, Wo, kh, kw, stride, pad;
+  long long x_bstride, y_bstride;  /* rows per batch element (0 -> H*W / Ho*uy*Wo*ux) */
+  long long y_row0;                /* row offset added inside each batch element */
+  int ux, uy, dx, dy;              /* output up-sampling lattice (transposed conv k=s): row=(oy*uy+dy, ox*ux+dx); 0 -> 1 */
+  /* SPARSE */
+  const int* nbr; int nbr_stride;  /* [taps, nbr_stride] */
+  const int* y_off;                /* optional per-row ELEMENT offset into y (replaces m*ldy) */
+  int res_after_act;               /* 0: act(acc+bias+res) (residual blocks); 1: act(acc+bias)+res (query_feat += roi_feat) */
+} ff3d_gemm_desc;
+
+int ff3d_igemm(const ff3d_gemm_desc* desc, ff3d_stream_t stream);
+
+/* Depthwise 3x3 stride 1 pad 1, NHWC, folded BN + activation (torchvision InvertedResidual dw conv,
+ * focal_encoder.py:36-38). x [B,H,W,C] (ldx), w [9, C], bias [C]. */
+int ff3d_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy, int B, int H, int W,
+                   int C, int act, ff3d_stream_t stream);
+
+/* y = LayerNorm(x) * gamma + beta over the last dim C (nn.LayerNorm, eps) -- [upstream] mmcv BaseTransformerLayer norms */
+int ff3d_layernorm(const float* x, const float* gamma, const float* beta, float* y, int rows, int C, float eps,
+                   ff3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hard-Instance-Probing stage: sigmoid * accumulated mask -> class-aware local-max NMS -> top-k ->
+ * query gathers -> accumulated-mask update.  Replaces focal_decoder.py:631-782 (one HIP stage).
+ * logits [B,H,W,ldl] NHWC (first C channels used); acc_mask [B,C,H,W] fp32 (in/out);
+ * nms_heat [B,C,H,W] fp32 workspace/out (the NMS'ed masked heatmap of this stage);
+ * feat [B,H,W,ldf] stage feature; cls_w [C, Cf] (class_encoding weight transposed), cls_b [Cf];
+ * outputs at query slot q0..q0+k-1 of nq_total: top_idx [B,k] int32 (flat class*H*W + pos, canonical order:
+ * descending value, ties -> lower index), query_feat [B, nq_total, Cf], query_pos [B, nq_total, 2],
+ * query_score [B, nq_total, C], query_label [B, nq_total] int32 (token-major rows).
+ * exempt_lo..exempt_hi: classes using a 1x1 window (nuScenes 8..9, Waymo 1..2), focal_decoder.py:678-683,777-780.
+ */
+size_t ff3d_hip_workspace_bytes(int B, int C, int H, int W);
+int ff3d_hip_stage(const float* logits, int ldl, float* acc_mask, float* nms_heat, const float* feat, int ldf, int Cf,
+                   const float* cls_w, const float* cls_b, int B, int C, int H, int W, int k, int nms_kernel,
+                   int exempt_lo, int exempt_hi, int q0, int nq_total, int* top_idx, float* query_feat,
+                   float* query_pos, float* query_score, int* query_label, void* workspace, size_t workspace_bytes,
+                   ff3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder pieces.
+ */
+/* gen_sineembed_for_position (models/utils/utils.py:40-66): pos [rows,2] (x,y) in BEV-cell units, divided by
+ * (w, h) inside; dim_t [128] = 10000^(2*(j//2)/128) supplied by the host;
+ * out [rows,256] = (sin/cos of y | sin/cos of x), scale 2*pi. */
+int ff3d_sine_embed(const float* pos, float w, float h, const float* dim_t, float* out, int rows, ff3d_stream_t stream);
+
+/* nn.MultiheadAttention core (softmax(QK^T/sqrt(d)) V) for the query self-attention:
+ * q,k,v [B, Nq, heads*d] with row strides ldq/ldk/ldv; out [B,Nq,heads*d].  ([upstream] mmcv MultiheadAttention) */
+int ff3d_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                  int B, int Nq, int heads, int d, ff3d_stream_t stream);
+
+/* Multi-scale deformable attention sampling.
+ * Replaces: [upstream] mmcv.ops ms_deform_attn_forward (ms_deform_attn_cuda.cu) called through
+ *   MultiScaleDeformableAttention at focal_decoder.py:927-933.
+ * value [B, n_tokens, ldv] (heads*d channels starting at column v_col0), levels (H_l, W_l, start_l) HOST arrays;
+ * ref [B,Nq,2] (x,y), divided by (ref_w, ref_h) inside (focal_decoder.py:869); offs [B,Nq,heads*L*P*2]; attw logits [B,Nq,heads*L*P] (softmax over L*P done here);
+ * out [B,Nq,heads*d]. */
+int ff3d_msda(const float* value, int ldv, int v_col0, long long v_bstride, const int* lvl_h, const int* lvl_w,
+              const int* lvl_start, int L, int P, const float* ref, float ref_w, float ref_h, const float* offs,
+              int ldoffs, const float* attw, int ldattw, float* out, int B, int Nq, int heads, int d,
+              ff3d_stream_t stream);
+
+/* ROI feature sampling (focal_decoder.py:890-919): per query a g x g grid in the (expanded) box frame, rotated by
+ * yaw, normalised by roi_range (x0,y0,x1,y1), clipped to [-2,2], bilinear (align_corners=False, zeros) on L levels.
+ * query_box [B*Nq, box_ld] rows = (centre(2) in cell units, height, log-dims(3), sin, cos, ...) -- the previous
+ * decoder stage's prediction row; value buffer [B, n_tokens, ldv] (first C columns) with level geometry as in
+ * ff3d_msda; out [B*Nq, L*g*g*C] ordered (level, point, channel). */
+int ff3d_roi_sample(const float* query_box, int box_ld, const float* value, int ldv, long long v_bstride,
+                    const int* lvl_h, const int* lvl_w, const int* lvl_start, int L, int C, int g, float expand,
+                    float cell_x, float cell_y, float origin_x, float origin_y, const float* roi_range4, float* out,
+                    int B, int Nq, ff3d_stream_t stream);
+
+/* Box-state update after the prediction heads (focal_decoder.py:945-957). pred [rows, ldp] rows =
+ * (center2, height1, dim3, rot2, [vel2], class logits...): center += query_pos; query_pos = center;
+ * with prev != NULL (roi_based_reg): dim[:2] += prev.dim[:2], rot += prev.rot. */
+int ff3d_head_update(float* pred, int ldp, float* query_pos, const float* prev, int ldprev, int rows,
+                     ff3d_stream_t stream);
+
+/* Final scoring + box decode (focal_decoder.py:1313-1321 + transfusion_bbox_coder.py:71-158, nms_type=None):
+ * pred as above (class logits at column cls_col); boxes [rows, 9|7] = (x,y,z_bottom,w,l,h,yaw[,vx,vy]),
+ * scores [rows], labels [rows] int32, keep [rows] uint8 (post_center_range test). */
+int ff3d_box_decode(const float* pred, int ldp, int cls_col, int has_vel, const float* query_score,
+                    const int* query_label, int rows, int C, float cell_x, float cell_y, float origin_x, float origin_y,
+                    const float* post_range6, float* boxes, float* scores, int* labels, unsigned char* keep,
+                    ff3d_stream_t stream);
+
+/* Misc elementwise helpers used by the head glue (all fp32). */
+int ff3d_add_rows(const float* a, const float* b, float* y, long long n, ff3d_stream_t stream);
+/* y[b, r, :] = a[b, r, :] + p[r, :]   (value + cached BEV positional embedding, focal_decoder.py:886) */
+int ff3d_add_bcast_rows(const float* a, const float* p, float* y, int B, long long rows, int C, ff3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FF3D_H_ */

@@ -1,0 +1,101 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ff3d.h declares; configs load
+(repo config and, when present, the unmodified reference configs); the checkpoint-key contract holds."""
+import os
+import re
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG_DIR = "/root/reference/projects/configs/focalformer3d"
+
+
+def _ensure_built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _ensure_built()
+    import ctypes
+    from focalformer3d_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "ff3d.h")).read()
+    declared = set(re.findall(r"\b(ff3d_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(so, name), f"{name} declared in ff3d.h but not exported by libff3d.so"
+    assert declared == set(lib.SIGNATURES), "ctypes SIGNATURES out of sync with include/ff3d.h"
+    assert lib.lib.ff3d_version() >= 100
+
+
+def test_gemm_desc_rejects_bad_arguments_without_a_gpu():
+    _ensure_built()
+    import ctypes as C
+    from focalformer3d_b200.lib import lib, GemmDesc
+    d = GemmDesc()
+    d.mode, d.M, d.cin, d.cout, d.taps = 0, 4, 6, 4, 1          # cin not a multiple of 4
+    assert lib.ff3d_igemm(C.byref(d), None) == -1
+    assert b"cin" in lib.ff3d_last_error()
+    assert lib.ff3d_voxelize_workspace_bytes(1000, 2, 100, 10) > 2 * 100 * 10 * 4
+
+
+def test_repo_config_and_param_contract():
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import param_spec, make_state_dict
+    from oracle.detector import build_oracle
+    cfg = load_config(default_config_path())
+    assert cfg.model.type == "FocalFormer3D" and cfg.plugin_dir == "projects/mmdet3d_plugin/"
+    m = scaled_model_cfg(cfg["model"], bev=16, num_proposals=8)
+    spec = param_spec(m)
+    osd = build_oracle(m).state_dict()
+    assert set(spec) == set(osd)
+    for k, (shape, _) in spec.items():
+        assert tuple(osd[k].shape) == tuple(shape), k
+    # Appendix-B names
+    for k in ("pts_middle_encoder.conv_input.0.weight", "pts_middle_encoder.encoder_layers.encoder_layer1.2.0.weight",
+              "pts_backbone.blocks.1.15.weight", "pts_neck.deblocks.1.0.weight", "imgpts_neck.shared_conv_pts.bias",
+              "imgpts_neck.fusion_blocks.0.P_IML.conv.1.0.weight", "pts_bbox_head.heatmap_head_img.1.1.bias",
+              "pts_bbox_head.roi_mlp.8.weight", "pts_bbox_head.decoder.1.layers.2.attentions.1.value_proj.weight",
+              "pts_bbox_head.prediction_heads.0.vel.1.bias"):
+        assert k in spec, k
+    assert "pts_bbox_head.heatmap_head_img.0.0.conv.weight" not in spec       # reuse_first_heatmap -> None slot
+    sd1, sd2 = make_state_dict(m, 0), make_state_dict(m, 0)
+    assert all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG_DIR), reason="reference tree not present on this box")
+def test_unmodified_reference_configs_load():
+    from focalformer3d_b200.config import load_config
+    from focalformer3d_b200.synth import param_spec
+    ref = load_config(os.path.join(REF_CFG_DIR, "FocalFormer3D_L.py"))
+    mine = load_config(os.path.join(ROOT, "configs", "focalformer3d_l.py"))
+    assert ref.model.type == "FocalFormer3D"
+    for part in ("pts_voxel_layer", "pts_voxel_encoder", "pts_middle_encoder", "pts_backbone", "pts_neck", "imgpts_neck"):
+        assert dict(ref.model[part]) == dict(mine.model[part]), part
+    rh, mh = dict(ref.model.pts_bbox_head), dict(mine.model.pts_bbox_head)
+    for k, v in mh.items():
+        assert rh[k] == v, k
+    assert dict(ref.model.test_cfg.pts) == dict(mine.model.test_cfg.pts)
+    assert set(param_spec(ref.model)) == set(param_spec(mine.model))
+    for name in sorted(os.listdir(REF_CFG_DIR)):
+        c = load_config(os.path.join(REF_CFG_DIR, name))
+        assert c.model.type in ("FocalFormer3D",), name
+
+
+def test_plugin_registers_reference_type_strings():
+    _ensure_built()
+    import importlib
+    importlib.import_module("projects.mmdet3d_plugin")
+    from focalformer3d_b200.config import DETECTORS, NECKS, HEADS, BBOX_CODERS
+    assert "FocalFormer3D" in DETECTORS and "FocalEncoder" in NECKS and "SECONDFPN" in NECKS
+    assert "FocalDecoder" in HEADS and "TransFusionBBoxCoder" in BBOX_CODERS
+
+
+def test_model_builds_and_loads_state_dict_on_cpu(tiny_cfg, tiny_sd):
+    _ensure_built()
+    from focalformer3d_b200.model import build_model
+    model = build_model(tiny_cfg)
+    missing = model.load_state_dict(tiny_sd, strict=True)
+    assert set(model.state_dict()) == set(tiny_sd)
+    with pytest.raises(RuntimeError):
+        model.forward_raw([torch.zeros(4, 5)])                 # not prepared / no device: must fail loudly

@@ -1,0 +1,402 @@
+"""Per-operator parity: every C-ABI entry point against the CPU oracle / plain torch fp32 on seeded inputs.
+Tolerances: indices, counts, coordinates, labels bit-exact; fp32 values 1e-4 abs on O(1) data unless noted."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from focalformer3d_b200 import ops as _ops
+    return _ops
+
+
+def _pack_lin(w):
+    from focalformer3d_b200.model import pack_linear
+    return pack_linear(w, None, "cuda")
+
+
+def _pack_conv(w):
+    from focalformer3d_b200.model import pack_conv2d
+    return pack_conv2d(w, None, "cuda")
+
+
+# ------------------------------------------------------------------------------------------------ voxelize
+@pytest.mark.parametrize("max_voxels,max_points", [(5000, 10), (150, 3)])
+def test_voxelize_matches_oracle(ops, max_voxels, max_points):
+    from oracle.voxelize import hard_voxelize
+    rng = np.random.default_rng(0)
+    vs, rg = [0.25, 0.25, 0.5], [-4.0, -4.0, -1.0, 4.0, 4.0, 1.0]
+    samples = []
+    for n in (4000, 0, 2500):                      # includes an empty sample
+        p = rng.uniform(-4.4, 4.4, (n, 5)).astype(np.float32)
+        p[:, 2] = rng.uniform(-1.2, 1.2, n)
+        samples.append(p)
+    offs = np.cumsum([0] + [len(s) for s in samples]).tolist()
+    allp = torch.from_numpy(np.concatenate(samples)).cuda()
+    out = ops.voxelize(allp, offs, vs, rg, max_points, max_voxels, mean_ld=8, want_voxels=True)
+    n_dev = out["n_dev"].cpu().numpy()
+    base = 0
+    for b, p in enumerate(samples):
+        v, c, n = hard_voxelize(p, vs, rg, max_points, max_voxels)
+        M = v.shape[0]
+        assert n_dev[1 + b] == M
+        sl = slice(base, base + M)
+        assert np.array_equal(out["coors"][sl].cpu().numpy(), np.concatenate([np.full((M, 1), b, np.int32), c], 1))
+        assert np.array_equal(out["num_points"][sl].cpu().numpy(), n)
+        assert np.array_equal(out["voxels"][sl].cpu().numpy(), v)                      # bit-exact copies
+        mean = v[:, :, :5].sum(1) / np.maximum(n, 1)[:, None].astype(np.float32)
+        np.testing.assert_allclose(out["mean"][sl, :5].cpu().numpy(), mean, rtol=1e-6, atol=1e-6)
+        assert (out["mean"][sl, 5:] == 0).all()
+        base += M
+    assert n_dev[0] == base
+
+
+# ------------------------------------------------------------------------------------------------ implicit GEMM
+@pytest.mark.parametrize("M,K,N,act", [(300, 128, 128, 1), (257, 256, 20, 0), (1000, 1024, 128, 0), (64, 8, 16, 2),
+                                       (130, 384, 288, 0)])
+def test_linear(ops, M, K, N, act):
+    g = torch.Generator().manual_seed(M + N)
+    x, x2 = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)
+    w, b, r = torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = (x + x2).double() @ w.double().t() + b.double() + r.double()
+    ref = {0: ref, 1: ref.relu(), 2: ref.clamp(0, 6)}[act].float()
+    bias = torch.cat([b, torch.zeros((-N) % 4)]).cuda()
+    y = ops.linear(x.cuda(), _pack_lin(w), bias, act=act, res=r.cuda(), x2=x2.cuda(), cout=N)
+    assert (y.cpu() - ref).abs().max().item() < 2e-4
+    # act before the residual add (query_feat += roi_feat)
+    y2 = ops.linear(x.cuda(), _pack_lin(w), bias, act=1, res=r.cuda(), cout=N, res_after_act=True)
+    ref2 = (x.double() @ w.double().t() + b.double()).relu() + r.double()
+    assert (y2.cpu() - ref2.float()).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", [(16, 24, 3, 1, 13, 11), (32, 64, 3, 2, 12, 12), (32, 64, 3, 2, 11, 9),
+                                                   (64, 10, 3, 1, 9, 9), (256, 128, 1, 1, 7, 5), (128, 128, 3, 1, 20, 20)])
+def test_conv2d_nhwc(ops, cin, cout, k, stride, H, W):
+    g = torch.Generator().manual_seed(cin + cout + k)
+    B = 2
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=k // 2).relu().float()
+    Ho, Wo = ref.shape[2:]
+    wide = torch.full((B, Ho, Wo, cout + 8), 7.0, device="cuda")             # channel-slice output (concat-free cat)
+    ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), _pack_conv(w), b.cuda(), wide[..., 4:4 + cout], k,
+               stride=stride, act=1)
+    assert (wide[..., 4:4 + cout].permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-4
+    assert (wide[..., :4] == 7).all() and (wide[..., 4 + cout:] == 7).all()    # neighbours untouched
+
+
+def test_conv2d_batch_strided_views_and_residual(ops):
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 16, 8, 8
+    tokens = H * W + (H // 2) * (W // 2)
+    ms = torch.randn(B, tokens, C, generator=g).cuda()
+    w = torch.randn(C, C, 3, 3, generator=g) / 12
+    lv0 = ms[:, :H * W].view(B, H, W, C)
+    lv1 = ms[:, H * W:].view(B, H // 2, W // 2, C)
+    ref = F.conv2d(lv0.permute(0, 3, 1, 2).cpu().double(), w.double(), stride=2, padding=1).float()
+    ops.conv2d(lv0, _pack_conv(w), None, lv1, 3, stride=2)
+    assert (lv1.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-4
+    x = torch.randn(B, H, W, C, generator=g).cuda()
+    out = torch.empty_like(x)
+    ops.conv2d(x, _pack_conv(w), None, out, 3, res=x)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).cpu().double(), w.double(), padding=1).float() + x.permute(0, 3, 1, 2).cpu()
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-4
+
+
+def test_transposed_conv_lattice(ops):
+    g = torch.Generator().manual_seed(9)
+    B, ci, co, H, W = 2, 32, 24, 6, 5
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(ci, co, 2, 2, generator=g) / ci ** 0.5
+    ref = F.conv_transpose2d(x.double(), w.double(), stride=2).float()
+    out = torch.empty((B, 2 * H, 2 * W, co), device="cuda")
+    from focalformer3d_b200.model import pack_taps
+    for dy in range(2):
+        for dx in range(2):
+            ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), pack_taps(w[:, :, dy, dx].unsqueeze(0), "cuda"), None,
+                       out, 1, up=(2, dy, dx))
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-4
+
+
+def test_dwconv_and_layernorm(ops):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 9, 7, generator=g) * 3
+    w, b = torch.randn(64, 1, 3, 3, generator=g), torch.randn(64, generator=g)
+    ref = F.conv2d(x, w, b, padding=1, groups=64).clamp(0, 6)
+    out = torch.empty((2, 9, 7, 64), device="cuda")
+    ops.dwconv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.reshape(64, 9).t().contiguous().cuda(), b.cuda(), out, act=2)
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 1e-5
+    y = torch.randn(77, 128, generator=g) * 2 + 1
+    gm, bt = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    o = ops.layernorm(y.cuda(), gm.cuda(), bt.cuda())
+    assert (o.cpu() - F.layer_norm(y, (128,), gm, bt)).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ sparse conv
+def _rand_level(B, shape, n, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    D, H, W = shape
+    lin = torch.randperm(B * D * H * W, generator=g)[:n]
+    idx = torch.stack([lin // (D * H * W), (lin // (H * W)) % D, (lin // W) % H, lin % W], 1).int()
+    return idx, torch.randn(n, C, generator=g)
+
+
+def _to_dense(feat, coors, n, shape, B):
+    D, H, W = shape
+    out = torch.zeros(B, D, H, W, feat.shape[1])
+    c = coors[:n].long()
+    out[c[:, 0], c[:, 1], c[:, 2], c[:, 3]] = feat[:n]
+    return out
+
+
+@pytest.mark.parametrize("k,s,p", [(None, None, None), ((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1)),
+                                   ((3, 1, 1), (2, 1, 1), (0, 0, 0))])
+def test_sparse_conv_matches_oracle(ops, k, s, p):
+    from oracle import sparse as osp
+    from focalformer3d_b200.model import pack_taps
+    B, shape, n, Ci, Co = 2, (9, 20, 20), 900, 16, 32
+    idx, feat = _rand_level(B, shape, n, Ci, 11)
+    cap = n + 50                                                   # capacity > active count
+    coors = torch.zeros((cap, 4), dtype=torch.int32)
+    coors[:n] = idx
+    x = torch.zeros((cap, Ci))
+    x[:n] = feat
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    lvl = ops.SparseLevel(coors.cuda(), n_dev, cap, B, shape)
+    lvl.build_hash()
+    subm = k is None
+    kk = (3, 3, 3) if subm else k
+    wt = torch.randn(*kk, Ci, Co, generator=torch.Generator().manual_seed(3)) / 8
+    bias, res = torch.randn(Co), torch.randn(cap, Co)
+    oconv = osp.SpConv3d(Ci, Co, kk, 1 if subm else s, 1 if subm else p, subm=subm)
+    oconv.weight.data.copy_(wt)
+    with torch.no_grad():
+        ref = oconv(osp.SparseTensor(feat, idx, shape, B))
+    wpk = pack_taps(wt.reshape(-1, Ci, Co), "cuda")
+    if subm:
+        out = torch.zeros((cap, Co), device="cuda")
+        ops.sparse_conv(x.cuda(), lvl.subm_map(), lvl.n_dev, wpk, bias.cuda(), out, act=1, res=res.cuda())
+        got = _to_dense(out.cpu(), coors, n, shape, B)
+        r = torch.relu(ref.features + bias + res[:n])               # oracle rows are in input order for SubM
+        want = _to_dense(r, idx, n, shape, B)
+    else:
+        overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nl, nbr = lvl.downsample(k, s, p, 4 * cap, overflow)
+        out = torch.zeros((nl.cap, Co), device="cuda")
+        ops.sparse_conv(x.cuda(), nbr, nl.n_dev, wpk, bias.cuda(), out, act=0)
+        no = int(nl.n_dev.item())
+        assert int(overflow.item()) == 0 and no == ref.indices.shape[0]          # same output-site set size
+        assert nl.shape == tuple(ref.spatial_shape)
+        got = _to_dense(out.cpu(), nl.coors.cpu(), no, nl.shape, B)
+        want = _to_dense(ref.features + bias, ref.indices, no, ref.spatial_shape, B)
+        occ_g = _to_dense(torch.ones(nl.cap, 1), nl.coors.cpu(), no, nl.shape, B)
+        occ_w = _to_dense(torch.ones(no, 1), ref.indices, no, ref.spatial_shape, B)
+        assert torch.equal(occ_g, occ_w)                                         # identical active sites
+    assert (got - want).abs().max().item() < 2e-4
+
+
+def test_sparse_to_bev_scatter(ops):
+    B, shape, n, C = 2, (2, 6, 5), 40, 8
+    idx, feat = _rand_level(B, shape, n, C, 4)
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    lvl = ops.SparseLevel(idx.cuda(), n_dev, n, B, shape)
+    off = lvl.bev_offsets(shape[0] * C, C).cpu().long()
+    bev = torch.zeros(B * shape[1] * shape[2] * shape[0] * C)
+    for i in range(n):
+        bev[off[i]:off[i] + C] = feat[i]
+    bev = bev.view(B, shape[1], shape[2], shape[0], C)                            # [B,H,W,D,C]
+    dense = _to_dense(feat, idx, n, shape, B)                                     # [B,D,H,W,C]
+    assert torch.equal(bev.permute(0, 3, 1, 2, 4), dense)
+
+
+def test_down_build_overflow_flag(ops):
+    B, shape, n = 1, (5, 8, 8), 200
+    idx, _ = _rand_level(B, shape, n, 4, 8)
+    lvl = ops.SparseLevel(idx.cuda(), torch.tensor([n], dtype=torch.int32).cuda(), n, B, shape)
+    lvl.build_hash()
+    overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nl, _ = lvl.downsample((3, 3, 3), (2, 2, 2), (1, 1, 1), 16, overflow)
+    assert int(overflow.item()) == 1 and int(nl.n_dev.item()) == 16
+
+
+# ------------------------------------------------------------------------------------------------ HIP stage
+@pytest.mark.parametrize("dataset,C,exempt", [("nuScenes", 10, (8, 9)), ("Waymo", 3, (1, 2))])
+def test_hip_stage_matches_reference_logic(ops, dataset, C, exempt):
+    from oracle.head import canonical_topk
+    g = torch.Generator().manual_seed(7)
+    B, H, W, Cf, k = 2, 20, 18, 32, 30
+    logits = torch.randn(B, C, H, W, generator=g) * 2
+    acc = (torch.rand(B, C, H, W, generator=g) > 0.2).float()
+    feat = torch.randn(B, Cf, H, W, generator=g)
+    cls_w, cls_b = torch.randn(Cf, C, generator=g), torch.randn(Cf, generator=g)
+    # --- reference logic (focal_decoder.py:662-782)
+    heat = logits.sigmoid() * acc
+    lm = torch.zeros_like(heat)
+    lm[:, :, 1:-1, 1:-1] = F.max_pool2d(heat, 3, 1, 0)
+    for c in range(exempt[0], exempt[1] + 1):
+        lm[:, c] = heat[:, c]
+    nms = (heat * (heat == lm)).view(B, C, -1)
+    top = canonical_topk(nms.view(B, -1), k)
+    cls, pos = top // (H * W), top % (H * W)
+    qf = feat.view(B, Cf, -1).gather(2, pos[:, None].expand(-1, Cf, -1)) + (cls_w[:, cls].permute(1, 0, 2) + cls_b[None, :, None])
+    qs = nms.gather(2, pos[:, None].expand(-1, C, -1))
+    sel = torch.zeros(B, C * H * W).scatter_(1, top, 1.0).view(B, C, H, W)
+    selk = F.max_pool2d(sel, 3, 1, 1)
+    selk[:, exempt[0]:exempt[1] + 1] = sel[:, exempt[0]:exempt[1] + 1]
+    acc_ref = acc * (1 - selk)
+    # --- kernel
+    lg = torch.zeros(B, H, W, 12)
+    lg[..., :C] = logits.permute(0, 2, 3, 1)
+    accd, nmsd = acc.clone().cuda(), torch.empty(B, C, H, W, device="cuda")
+    nq = 2 * k
+    topd = torch.empty((B, k), dtype=torch.int32, device="cuda")
+    qfd, qpd = torch.zeros(B * nq, Cf, device="cuda"), torch.zeros(B * nq, 2, device="cuda")
+    qsd, qld = torch.zeros(B * nq, C, device="cuda"), torch.zeros(B * nq, dtype=torch.int32, device="cuda")
+    ops.hip_stage(lg.cuda(), accd, nmsd, feat.permute(0, 2, 3, 1).contiguous().cuda(), cls_w.t().contiguous().cuda(),
+                  cls_b.cuda(), k, 3, exempt, k, nq, topd, qfd, qpd, qsd, qld)
+    assert (nmsd.cpu().view(B, C, -1) - nms).abs().max().item() < 1e-6
+    assert torch.equal(topd.cpu().long(), top)                                    # bit-exact, canonical order
+    sl = slice(k, 2 * k)
+    assert torch.equal(qld.view(B, nq)[:, sl].cpu().long(), cls)
+    assert (qfd.view(B, nq, Cf)[:, sl].cpu() - qf.transpose(1, 2)).abs().max().item() < 1e-5
+    assert (qsd.view(B, nq, C)[:, sl].cpu() - qs.transpose(1, 2)).abs().max().item() < 1e-6
+    px = torch.stack([(pos % W).float() + 0.5, (pos // W).float() + 0.5], -1)
+    assert torch.equal(qpd.view(B, nq, 2)[:, sl].cpu(), px)
+    assert torch.equal(accd.cpu(), acc_ref)
+
+
+def test_hip_stage_degenerate_fewer_candidates_than_k(ops):
+    B, C, H, W, Cf, k = 1, 3, 6, 6, 8, 20
+    logits = torch.full((B, H, W, 4), -3.0)
+    acc = torch.zeros(B, C, H, W)
+    acc[0, 0, 2, 2] = acc[0, 2, 4, 1] = 1.0                                       # only two positive candidates
+    nmsd = torch.empty(B, C, H, W, device="cuda")
+    topd = torch.empty((B, k), dtype=torch.int32, device="cuda")
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device="cuda")
+    ops.hip_stage(logits.cuda(), acc.cuda(), nmsd, z(B, H, W, Cf), z(C, Cf), z(Cf), k, 3, (1, 2), 0, k, topd,
+                  z(B * k, Cf), z(B * k, 2), z(B * k, C), z(B * k, dt=torch.int32))
+    t = topd.cpu()[0].tolist()
+    assert set(t[:2]) == {0 * 36 + 14, 2 * 36 + 25} and len(set(t)) == k
+    zeros = [i for i in range(C * H * W) if i not in (14, 97)]
+    assert t[2:] == zeros[:k - 2]                                                 # ties at 0 -> lowest flat index
+
+
+# ------------------------------------------------------------------------------------------------ decoder pieces
+def test_sine_embed(ops):
+    from oracle.head import gen_sineembed_for_position
+    g = torch.Generator().manual_seed(0)
+    pos = torch.rand(2, 50, 2, generator=g) * 200 - 10
+    ref = gen_sineembed_for_position(pos / torch.tensor([180.0, 180.0]))
+    dim_t = 10000 ** (2 * (torch.arange(128, dtype=torch.float32) // 2) / 128)
+    out = ops.sine_embed(pos.view(-1, 2).cuda(), 180.0, 180.0, dim_t.cuda())
+    assert (out.cpu().view(2, 50, 256) - ref).abs().max().item() < 2e-5
+
+
+def test_mha_core(ops):
+    g = torch.Generator().manual_seed(0)
+    B, Nq, h, d = 2, 77, 8, 16
+    q, k, v = (torch.randn(B * Nq, h * d, generator=g) for _ in range(3))
+    qk = torch.cat([q, k], 1).cuda()
+    out = torch.empty(B * Nq, h * d, device="cuda")
+    ops.mha_core(qk[:, :h * d], qk[:, h * d:], v.cuda(), out, B, Nq, h, d)
+    sp = lambda t: t.view(B, Nq, h, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B * Nq, h * d)
+    assert (out.cpu() - ref).abs().max().item() < 1e-5
+
+
+def test_msda_matches_oracle(ops):
+    from oracle.transformer import ms_deform_attn_core
+    g = torch.Generator().manual_seed(3)
+    shapes = [(12, 10), (6, 5), (3, 2)]
+    B, Nq, h, d, P = 2, 40, 8, 16, 4
+    T = sum(a * b for a, b in shapes)
+    value = torch.randn(B, T, 3 * h * d, generator=g)                           # 3 layers' projected values side by side
+    pos = torch.rand(B, Nq, 2, generator=g) * torch.tensor([10.0, 12.0]) * 1.2 - 1.0
+    offs = torch.randn(B, Nq, h, 3, P, 2, generator=g) * 2
+    attw = torch.randn(B, Nq, h, 3 * P, generator=g)
+    ref_pts = pos / torch.tensor([10.0, 12.0])
+    norm = torch.tensor([[w, hh] for hh, w in shapes], dtype=torch.float32)
+    loc = ref_pts[:, :, None, None, None, :] + offs / norm[None, None, None, :, None, :]
+    col = h * d                                                                  # use the middle layer's columns
+    want = ms_deform_attn_core(value[:, :, col:2 * col].reshape(B, T, h, d), shapes, loc,
+                               attw.softmax(-1).view(B, Nq, h, 3, P))
+    geom = ops.LevelGeom(shapes)
+    oa = torch.cat([offs.reshape(B * Nq, -1), attw.reshape(B * Nq, -1)], 1).cuda()
+    n_off = h * 3 * P * 2
+    out = torch.empty(B * Nq, h * d, device="cuda")
+    ops.msda(value.cuda(), col, geom, P, pos.view(-1, 2).cuda(), 10.0, 12.0, oa[:, :n_off], oa[:, n_off:], out, B, Nq, h, d)
+    assert (out.cpu().view(B, Nq, -1) - want).abs().max().item() < 2e-5
+
+
+def test_roi_sample_matches_reference_logic(ops):
+    from oracle.head import FocalDecoder, TransFusionBBoxCoder, rotation_3d_in_axis_z
+    g = torch.Generator().manual_seed(5)
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    B, Nq, C, gs = 2, 9, 8, 7
+    T = sum(a * b for a, b in shapes)
+    ms = torch.randn(B, T, C, generator=g)
+    coder = TransFusionBBoxCoder(pc_range=[-54.0, -54.0], out_size_factor=8, voxel_size=[0.075, 0.075])
+    qb = torch.randn(B, 10, Nq, generator=g)
+    qb[:, :2] = torch.rand(B, 2, Nq, generator=g) * 180
+    qb[:, 3:6] = qb[:, 3:6] * 0.8 + 1.0
+    # reference logic, focal_decoder.py:890-919
+    std = coder.decode_box(qb[:, 6:8].clone(), qb[:, 3:6].clone() * 1.2, qb[:, 0:2].clone(), qb[:, 2:3].clone(), qb[:, 8:].clone())
+    std = std.reshape(B * Nq, -1)
+    gp = FocalDecoder.get_dense_grid_points(std, B * Nq, gs)
+    gp = rotation_3d_in_axis_z(gp, std[:, 6]) + std[:, None, :2]
+    gp = gp.view(B, Nq, gs * gs, 2)
+    pcr = torch.tensor([-54, -54, -5.0, 54, 54, 3.0])
+    gp = ((gp - pcr[:2]) / (pcr[3:5] - pcr[:2]) * 2 - 1).clip(-2, 2)
+    feats, s0 = [], 0
+    for hh, ww in shapes:
+        feats.append(ms[:, s0:s0 + hh * ww].view(B, hh, ww, C).permute(0, 3, 1, 2))
+        s0 += hh * ww
+    rf = torch.cat([F.grid_sample(f, gp, mode="bilinear", align_corners=False) for f in feats], 1)   # [B, 3C, Nq, 49]
+    want = rf.view(B, 3, C, Nq, gs * gs).permute(0, 3, 1, 4, 2).reshape(B * Nq, -1)                  # (lvl, pt, c)
+    out = torch.empty(B * Nq, 3 * gs * gs * C, device="cuda")
+    prev = qb.permute(0, 2, 1).reshape(B * Nq, 10).contiguous().cuda()
+    ops.roi_sample(prev, ms.cuda(), ops.LevelGeom(shapes), C, gs, 1.2, (0.6, 0.6), (-54.0, -54.0), (-54.0, -54.0, 54.0, 54.0),
+                   out, B, Nq)
+    assert (out.cpu() - want).abs().max().item() < 1e-4
+
+
+def test_head_update_and_box_decode(ops):
+    from oracle.head import TransFusionBBoxCoder
+    g = torch.Generator().manual_seed(1)
+    B, Nq, C = 2, 50, 10
+    pred = torch.randn(B * Nq, 20, generator=g)
+    qpos = torch.rand(B * Nq, 2, generator=g) * 180
+    prev = torch.randn(B * Nq, 20, generator=g)
+    p, qp = pred.clone().cuda(), qpos.clone().cuda()
+    ops.head_update(p, qp, prev.cuda())
+    want = pred.clone()
+    want[:, :2] += qpos
+    want[:, 3:5] += prev[:, 3:5]
+    want[:, 6:8] += prev[:, 6:8]
+    assert torch.allclose(p.cpu(), want) and torch.allclose(qp.cpu(), want[:, :2])
+    # decode (focal_decoder.py:1313-1321 + transfusion_bbox_coder.py:71-158)
+    coder = TransFusionBBoxCoder(pc_range=[-54.0, -54.0], out_size_factor=8, voxel_size=[0.075, 0.075],
+                                 post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.0, code_size=10)
+    qs = torch.rand(B * Nq, C, generator=g)
+    ql = torch.randint(0, C, (B * Nq,), generator=g)
+    qs[3, ql[3]] = 0.0                                                            # zero score -> label 0 by argmax
+    cm = lambda a, b: want[:, a:b].view(B, Nq, b - a).transpose(1, 2).clone()
+    score = cm(10, 20).sigmoid() * qs.view(B, Nq, C).transpose(1, 2) * F.one_hot(ql.view(B, Nq), C).permute(0, 2, 1)
+    ref = coder.decode(score, cm(6, 8), cm(3, 6), cm(0, 2), cm(2, 3), cm(8, 10), filter=False)
+    boxes = torch.empty(B * Nq, 9, device="cuda")
+    scores = torch.empty(B * Nq, device="cuda")
+    labels = torch.empty(B * Nq, dtype=torch.int32, device="cuda")
+    keep = torch.empty(B * Nq, dtype=torch.uint8, device="cuda")
+    ops.box_decode(p, 10, True, qs.cuda(), ql.int().cuda(), C, (0.6, 0.6), (-54.0, -54.0),
+                   [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], boxes, scores, labels, keep)
+    rb = torch.stack([r["bboxes"] for r in ref]).view(B * Nq, 9)
+    assert (boxes.cpu() - rb).abs().max().item() < 1e-4
+    assert (scores.cpu() - torch.stack([r["scores"] for r in ref]).view(-1)).abs().max().item() < 1e-6
+    assert torch.equal(labels.cpu().long(), torch.stack([r["labels"] for r in ref]).view(-1))
+    pr = torch.tensor([-61.2, -61.2, -10.0, 61.2, 61.2, 10.0])
+    assert torch.equal(keep.cpu().bool(), ((rb[:, :3] >= pr[:3]) & (rb[:, :3] <= pr[3:])).all(1))
