@@ -55,24 +55,28 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t k) {
   k ^= k >> 16; k *= 0x7feb352dU; k ^= k >> 15; k *= 0x846ca68bU; k ^= k >> 16;
   return k;
 }
-// returns slot of key (inserting if absent); *inserted tells whether this call created it
+// returns slot of key (inserting if absent); *inserted tells whether this call created it.
+// Probing is bounded by the table size: -1 means the table is full (capacity overflow), never a hang.
 __device__ __forceinline__ int hash_insert(uint32_t* keys, int mask, uint32_t key, bool* inserted) {
   uint32_t s = hash_u32(key) & mask;
-  while (true) {
+  *inserted = false;
+  for (int probe = 0; probe <= mask; ++probe) {
     uint32_t prev = atomicCAS(&keys[s], kEmptyKey, key);
     if (prev == kEmptyKey) { *inserted = true; return (int)s; }
-    if (prev == key) { *inserted = false; return (int)s; }
+    if (prev == key) return (int)s;
     s = (s + 1) & mask;
   }
+  return -1;
 }
 __device__ __forceinline__ int hash_find(const uint32_t* __restrict__ keys, int mask, uint32_t key) {
   uint32_t s = hash_u32(key) & mask;
-  while (true) {
+  for (int probe = 0; probe <= mask; ++probe) {
     uint32_t k = keys[s];
     if (k == key) return (int)s;
     if (k == kEmptyKey) return -1;
     s = (s + 1) & mask;
   }
+  return -1;
 }
 
 }  // namespace ff3d

@@ -20,7 +20,7 @@ __global__ void sp_hash_build_kernel(const int* __restrict__ coors, const int* _
     int4 c = reinterpret_cast<const int4*>(coors)[i];
     bool ins;
     int s = hash_insert(hkeys, hmask, lin_key(c.x, c.y, c.z, c.w, D, H, W), &ins);
-    hvals[s] = i;
+    if (s >= 0) hvals[s] = i;
   }
 }
 
@@ -54,7 +54,7 @@ struct Down {
 // every (input site, tap) proposes an output site; first proposer allocates the row
 __global__ void sp_down_sites_kernel(const int* __restrict__ coors_in, const int* __restrict__ n_in_dev, int cap_in,
                                      Down g, int* coors_out, int* n_out_dev, int cap_out, uint32_t* hkeys_out,
-                                     int* hvals_out, int hmask_out, int* overflow) {
+                                     int* hvals_out, int hmask_out, volatile int* overflow) {
   int n = min(*n_in_dev, cap_in);
   int kvol = g.k[0] * g.k[1] * g.k[2];
   long long total = (long long)n * kvol;
@@ -69,7 +69,9 @@ __global__ void sp_down_sites_kernel(const int* __restrict__ coors_in, const int
     int oz = vz / g.s[0], oy = vy / g.s[1], ox = vx / g.s[2];
     if (oz >= g.Do || oy >= g.Ho || ox >= g.Wo) continue;
     bool ins;
+    if (*overflow) continue;   // capacity already exceeded: stop filling the table (keeps probing short)
     int s = hash_insert(hkeys_out, hmask_out, lin_key(c.x, oz, oy, ox, g.Do, g.Ho, g.Wo), &ins);
+    if (s < 0) { *overflow = 1; continue; }
     if (ins) {
       int row = atomicAdd(n_out_dev, 1);
       if (row < cap_out) {

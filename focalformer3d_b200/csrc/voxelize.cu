@@ -47,8 +47,8 @@ __global__ void vox_hash_kernel(const float* __restrict__ pts, VoxP p, uint32_t*
     int b = sample_of(p, i);
     uint32_t key = (uint32_t)(((b * p.g[2] + cz) * p.g[1] + cy) * p.g[0] + cx);
     bool ins;
-    slot = hash_insert(hkeys, hmask, key, &ins);
-    atomicMin(&hfirst[slot], i);
+    slot = hash_insert(hkeys, hmask, key, &ins);   // table holds 2x the point count: never full
+    if (slot >= 0) atomicMin(&hfirst[slot], i);
   }
   pt_slot[i] = slot;
 }
