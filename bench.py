@@ -91,6 +91,19 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def cpu_threads():
+    """Threads for the CPU arm: all host cores, capped at 32 (ATen's intra-op pool degrades badly on the small
+    index ops of the rulebook build when hundreds of threads are used); the JSON reports the count actually used."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def make_scenes(cfg, n_scenes, n_points, seed0):
     import torch
     from focalformer3d_b200.synth import synth_points
@@ -102,7 +115,7 @@ def time_oracle(cfg, sd, scenes, warmup, steps):
     """The reference algorithm (oracle port) on the host CPUs, all threads; one scene per step."""
     import torch
     from oracle.detector import build_oracle
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(cpu_threads())
     o = build_oracle(cfg)
     o.load_state_dict(sd, strict=True)
     for i in range(warmup):
@@ -130,7 +143,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_step": 1, "points_per_scene": args.points},
-        "cpu_baseline": {"value": sps, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": sps, "unit": "scenes/s", "cores": cpu_threads(), "kind": "port",
                          "sample": f"1 full-size scene per step x {args.steps} steps (oracle port of the reference algorithm: "
                                    "rulebook gather+mm+scatter sparse conv, ATen conv2d, nn.MultiheadAttention, grid_sample MSDA; "
                                    "the reference itself needs mmcv/mmdet3d/spconv which are not installable offline)"},
@@ -205,8 +218,11 @@ def run_ours(args):
         d2h_bytes[0] = sum(o["pts_bbox"]["boxes_3d"].numel() * 4 + o["pts_bbox"]["scores_3d"].numel() * 4
                            + o["pts_bbox"]["labels_3d"].numel() * 4 for o in out)
 
+    log("model ready; warm-up")
     for _ in range(max(args.warmup, 3)):
         step_dev()
+    torch.cuda.synchronize()
+    log("timed region (device-resident inputs)")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -214,6 +230,7 @@ def run_ours(args):
     ms = timed(step_dev, args.steps)
     launches = ops.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
+    log(f"device-resident: {ms / args.steps:.2f} ms/step; e2e region")
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -223,6 +240,7 @@ def run_ours(args):
 
     # ---- instrumented passes (outside the timed region): per-stage ms and per-kernel roofline
     stage_ms, roof = {}, None
+    log(f"e2e: {ms_e2e / args.steps:.2f} ms/step; instrumented passes")
     if rank == 0:
         reps = 3
         agg = {}
@@ -264,8 +282,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
+        log(f"cpu baseline on {cpu_threads()} threads")
         sps, sec = time_oracle(cfg, sd, [h.clone() for h in host[:1]], 0, args.cpu_baseline_scenes)
-        cpu = {"value": sps, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": sps, "unit": "scenes/s", "cores": cpu_threads(), "kind": "port",
                "sample": f"{args.cpu_baseline_scenes} full-size scene(s), no warm-up (oracle port; {sec:.1f} s/scene)"}
     if rank == 0:
         line = {
