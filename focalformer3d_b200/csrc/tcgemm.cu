@@ -1,0 +1,404 @@
+// tcgen05 implicit-GEMM with 3xTF32 split accumulation (fp32-grade accuracy on the 5th-gen tensor cores).
+//
+//   y[row(m), n] = act( sum_{t,c} x[src(m,t), c] * w[t,c,n] + bias[n] + res[m,n] )        (same contract as igemm.cu)
+//
+// B200 has no fp32 tensor-core MMA; kind::tf32 keeps 10 mantissa bits.  The parity bar of this path (heatmaps and box
+// regressions within 1e-3 of an fp32 oracle, bit-exact top-k) does not survive ~40 stacked TF32 layers, so each operand
+// is split a = a_hi + a_lo (a_hi = a with the low 13 mantissa bits cleared, a_lo = a - a_hi, both exact TF32 values up
+// to 2^-22 relative) and D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulates in fp32 in TMEM.
+//
+// CTA = one 128 x BN output tile, 192 threads:
+//   warps 0-3  A producers: each thread owns one of the 128 tile rows; per pipeline stage it gathers the row's 32
+//              fp32 (128 B: one conv tap x 32 channels, or 32/cin taps when cin < 32) with 8 LDG.128, splits hi/lo in
+//              registers and stores both into the 128B-swizzled K-major smem tiles (generic proxy) ->
+//              fence.proxy.async -> mbarrier arrive.  After the main loop the same warps run the epilogue
+//              (tcgen05.ld 32x32b: thread <-> TMEM lane <-> tile row).
+//   warp 4     B producer: one cp.async.bulk (UBLKCP) per stage of the host-pre-swizzled [hi | lo] weight image.
+//   warp 5     TMEM alloc/dealloc + single-thread tcgen05.mma issue (12 MMAs of 128 x BN x 8 per stage),
+//              tcgen05.commit releases smem stages / signals the epilogue.
+#include "common.cuh"
+
+namespace ff3d {
+
+struct TcP {
+  int mode, M;
+  const int* m_dev;
+  int cin, cout, taps;
+  const float* x; int ldx;
+  const float* x2;
+  const float* wimg;        // [n_tiles][n_stages][2][BN*32] pre-swizzled hi/lo images
+  const float* bias;
+  const float* res; int ldres;
+  float* y; int ldy;
+  int act, res_after_act;
+  int B, H, W, Ho, Wo, kh, kw, stride, pad;
+  long long x_bstride, y_bstride, y_row0;
+  int ux, uy, dx, dy;
+  const int* nbr; int nbr_stride;
+  const int* y_off;
+  int n_stages, tps, cpt;   // pipeline K-steps; taps per stage (cin < 32); 32-channel chunks per tap (cin >= 32)
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
+// SBO(1024B>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major A and B,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of (row r, 16-byte chunk j) inside a 128B-swizzled K-major tile whose base is 1024B aligned
+__device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int n_slots) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], then barriers
+  constexpr uint32_t A_BYTES = TC_BM * 128;
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t SLOT_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_slots * SLOT_BYTES);
+  uint64_t* empty_bar = full_bar + n_slots;
+  uint64_t* tmem_full = empty_bar + n_slots;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int ntile = blockIdx.y;
+  int Mv = p.M;
+  if (p.m_dev) { int md = *p.m_dev; Mv = md < Mv ? md : Mv; }
+  if (m0 >= Mv) return;   // uniform for the whole CTA, before any barrier / TMEM use
+
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  if (tid == 0) {
+    for (int s = 0; s < n_slots; ++s) { mbar_init(&full_bar[s], TC_BM + 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n_stages = p.n_stages;
+
+  if (warp < 4) {
+    // =========================== A producers: thread <-> tile row ===========================
+    const int r = tid;
+    const int m = m0 + r;
+    const bool rvalid = m < Mv;
+    int cb = 0, coy = 0, cox = 0;
+    if (MODE == FF3D_GEMM_CONV2D && rvalid) {
+      int hw = p.Ho * p.Wo;
+      cb = m / hw;
+      int rr = m - cb * hw;
+      coy = rr / p.Wo;
+      cox = rr - coy * p.Wo;
+    }
+    auto src_row = [&](int t) -> long long {
+      if (!rvalid || t >= p.taps) return -1;
+      if (MODE == FF3D_GEMM_ROWS) return m;
+      if (MODE == FF3D_GEMM_CONV2D) {
+        int ky = t / p.kw, kx = t - ky * p.kw;
+        int iy = coy * p.stride - p.pad + ky, ix = cox * p.stride - p.pad + kx;
+        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
+        return cb * p.x_bstride + (long long)iy * p.W + ix;
+      }
+      return (long long)__ldg(p.nbr + (size_t)t * p.nbr_stride + m);
+    };
+    for (int s = 0; s < n_stages; ++s) {
+      const int slot = s % n_slots;
+      const uint32_t ph = (uint32_t)((s / n_slots) & 1);
+      float4 v[8];
+      if (p.cin >= 32) {
+        int t = s / p.cpt, c0 = (s - t * p.cpt) * 32;
+        long long sr = src_row(t);
+        if (sr >= 0) {
+          const float4* g = reinterpret_cast<const float4*>(p.x + sr * p.ldx + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldg(g + j);
+          if (MODE == FF3D_GEMM_ROWS && p.x2) {
+            const float4* g2 = reinterpret_cast<const float4*>(p.x2 + sr * p.ldx + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 u = __ldg(g2 + j);
+              v[j].x += u.x; v[j].y += u.y; v[j].z += u.z; v[j].w += u.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        // cin in {8, 16}: 32/cin taps share one 128-byte K-step (static register indexing only)
+        const int qshift = p.cin == 16 ? 2 : 1;      // float4 per tap = 1 << qshift
+        long long srs[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) srs[q] = q < p.tps ? src_row(s * p.tps + q) : -1;
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+          int q = idx >> qshift, j = idx & ((1 << qshift) - 1);
+          long long sr = q == 0 ? srs[0] : q == 1 ? srs[1] : q == 2 ? srs[2] : srs[3];
+          v[idx] = sr >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + sr * p.ldx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      mbar_wait(&empty_bar[slot], ph ^ 1u);
+      uint8_t* a_hi = smem + (size_t)slot * SLOT_BYTES;
+      uint8_t* a_lo = a_hi + A_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u); l.x = v[j].x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u); l.y = v[j].y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u); l.z = v[j].z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u); l.w = v[j].w - h.w;
+        uint32_t o = swz(r, j);
+        *reinterpret_cast<float4*>(a_hi + o) = h;
+        *reinterpret_cast<float4*>(a_lo + o) = l;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full_bar[slot]);
+    }
+    // =========================== epilogue: TMEM -> registers -> global ===========================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* yp = nullptr;
+    if (rvalid) {
+      if (MODE == FF3D_GEMM_CONV2D) {
+        long long row = cb * p.y_bstride + p.y_row0 + (long long)(coy * p.uy + p.dy) * (p.Wo * p.ux) + cox * p.ux + p.dx;
+        yp = p.y + row * p.ldy;
+      } else if (MODE == FF3D_GEMM_SPARSE && p.y_off) {
+        yp = p.y + __ldg(p.y_off + m);
+      } else {
+        yp = p.y + (long long)m * p.ldy;
+      }
+    }
+    const int n0 = ntile * BN;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);   // warp-collective: all lanes execute
+      if (rvalid) {
+        const int n = n0 + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = v[i];
+          if (p.bias) a += __ldg(p.bias + n + i);
+          if (p.res_after_act) a = apply_act(a, p.act);
+          if (p.res) a += __ldg(p.res + (long long)m * p.ldres + n + i);
+          if (!p.res_after_act) a = apply_act(a, p.act);
+          v[i] = a;
+        }
+        if ((reinterpret_cast<uintptr_t>(yp + n) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yp + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) yp[n + i] = v[i];
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================== B producer ===========================
+    if (lane == 0) {
+      const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
+      for (int s = 0; s < n_stages; ++s) {
+        const int slot = s % n_slots;
+        const uint32_t ph = (uint32_t)((s / n_slots) & 1);
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        uint8_t* b_hi = smem + (size_t)slot * SLOT_BYTES + 2 * A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[slot], 2 * B_BYTES);
+        bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, &full_bar[slot]);
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      for (int s = 0; s < n_stages; ++s) {
+        const int slot = s % n_slots;
+        const uint32_t ph = (uint32_t)((s / n_slots) & 1);
+        mbar_wait(&full_bar[slot], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + (size_t)slot * SLOT_BYTES);
+        const uint32_t a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_lo + A_BYTES;
+        const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
+          const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
+          const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
+          umma_tf32(tmem_base, dal, dbh, idesc, (s | k) ? 1u : 0u);   // small terms first
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[slot]);   // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);            // all MMAs done -> accumulator readable
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int MODE, int BN>
+static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
+  constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
+  int n_slots = (int)((200 * 1024) / SLOT_BYTES);
+  if (n_slots > 6) n_slots = 6;
+  if (n_slots > p.n_stages) n_slots = p.n_stages;
+  if (n_slots < 1) n_slots = 1;
+  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 2) * sizeof(uint64_t) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tcgemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(cdiv(p.M, TC_BM), n_tiles_n);
+  tcgemm_kernel<MODE, BN><<<grid, TC_THREADS, smem, st>>>(p, n_slots);
+  return check_launch("ff3d_tcgemm");
+}
+
+template <int MODE>
+static int launch_tc_mode(const TcP& p, int bn, int n_tiles_n, cudaStream_t st) {
+  switch (bn) {
+    case 16: return launch_tc<MODE, 16>(p, n_tiles_n, st);
+    case 32: return launch_tc<MODE, 32>(p, n_tiles_n, st);
+    case 64: return launch_tc<MODE, 64>(p, n_tiles_n, st);
+    case 128: return launch_tc<MODE, 128>(p, n_tiles_n, st);
+  }
+  set_error("ff3d_tcgemm: unsupported N tile %d", bn);
+  return FF3D_EINVAL;
+}
+
+}  // namespace ff3d
+
+// N tile used for a given cout (0 = shape not supported by the tensor-core path)
+extern "C" int ff3d_tcgemm_ntile(int cin, int cout) {
+  if (!(cin == 8 || cin == 16 || (cin >= 32 && cin % 32 == 0))) return 0;
+  if (cout % 128 == 0) return 128;
+  if (cout == 64 || cout == 32 || cout == 16) return cout;
+  return 0;
+}
+extern "C" int ff3d_tcgemm_stages(int cin, int taps) {
+  if (cin >= 32) return taps * (cin / 32);
+  int tps = 32 / cin;
+  return (taps + tps - 1) / tps;
+}
+
+extern "C" int ff3d_tcgemm(const ff3d_gemm_desc* d, const float* wimg, ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(d != nullptr && wimg != nullptr, "ff3d_tcgemm: null argument");
+  int bn = ff3d_tcgemm_ntile(d->cin, d->cout);
+  FF3D_REQUIRE(bn > 0, "ff3d_tcgemm: shape cin=%d cout=%d is not tensor-core tileable", d->cin, d->cout);
+  FF3D_REQUIRE(d->ldx % 4 == 0 && d->x && d->y && d->taps > 0, "ff3d_tcgemm: bad operands");
+  FF3D_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wimg) & 15) == 0,
+               "ff3d_tcgemm: x and wimg must be 16-byte aligned");
+  if (d->M <= 0) return FF3D_OK;
+  TcP p;
+  p.mode = d->mode; p.M = d->M; p.m_dev = d->m_dev;
+  p.cin = d->cin; p.cout = d->cout; p.taps = d->taps;
+  p.x = d->x; p.ldx = d->ldx; p.x2 = d->x2; p.wimg = wimg; p.bias = d->bias;
+  p.res = d->res; p.ldres = d->ldres; p.y = d->y; p.ldy = d->ldy; p.act = d->act; p.res_after_act = d->res_after_act;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo; p.kh = d->kh; p.kw = d->kw;
+  p.stride = d->stride; p.pad = d->pad;
+  p.ux = d->ux > 0 ? d->ux : 1; p.uy = d->uy > 0 ? d->uy : 1; p.dx = d->dx; p.dy = d->dy;
+  p.x_bstride = d->x_bstride; p.y_bstride = d->y_bstride; p.y_row0 = d->y_row0;
+  p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.y_off = d->y_off;
+  p.n_stages = ff3d_tcgemm_stages(d->cin, d->taps);
+  p.tps = d->cin >= 32 ? 1 : 32 / d->cin;
+  p.cpt = d->cin >= 32 ? d->cin / 32 : 1;
+  if (d->mode == FF3D_GEMM_CONV2D) {
+    FF3D_REQUIRE(d->taps == d->kh * d->kw && (long long)d->B * d->Ho * d->Wo == d->M, "ff3d_tcgemm: bad conv geometry");
+    if (p.x_bstride == 0) p.x_bstride = (long long)d->H * d->W;
+    if (p.y_bstride == 0) p.y_bstride = (long long)d->Ho * p.uy * d->Wo * p.ux;
+  } else if (d->mode == FF3D_GEMM_SPARSE) {
+    FF3D_REQUIRE(d->nbr != nullptr && d->nbr_stride >= d->M, "ff3d_tcgemm: sparse mode needs nbr [taps, >=M]");
+  } else {
+    FF3D_REQUIRE(d->mode == FF3D_GEMM_ROWS && d->taps == 1, "ff3d_tcgemm: bad mode");
+  }
+  int n_tiles_n = d->cout / bn;
+  cudaStream_t st = as_stream(stream);
+  if (d->mode == FF3D_GEMM_ROWS) return launch_tc_mode<FF3D_GEMM_ROWS>(p, bn, n_tiles_n, st);
+  if (d->mode == FF3D_GEMM_CONV2D) return launch_tc_mode<FF3D_GEMM_CONV2D>(p, bn, n_tiles_n, st);
+  return launch_tc_mode<FF3D_GEMM_SPARSE>(p, bn, n_tiles_n, st);
+}

@@ -59,11 +59,12 @@ def bn_scale_shift(sd, name, eps):
 
 
 def pack_taps(w_tco, dev):
-    """[taps, cin, cout] (float64/32) -> device fp32 [taps, pad4(cin), pad4(cout)]"""
+    """[taps, cin, cout] (float64/32) -> ops.PackedW: fp32 [taps, pad4(cin), pad4(cout)] for the SIMT kernel plus,
+    when the shape is tensor-core tileable, the pre-swizzled hi/lo TF32 images for the tcgen05 kernel."""
     t, ci, co = w_tco.shape
     out = torch.zeros((t, _pad4(ci), _pad4(co)), dtype=torch.float32)
     out[:, :ci, :co] = w_tco.float()
-    return out.contiguous().to(dev)
+    return ops.PackedW(out.contiguous(), dev)
 
 
 def pack_conv2d(w, scale=None, dev="cuda"):

@@ -77,6 +77,62 @@ class Profiler:
 prof = Profiler()
 mark = prof.mark
 
+# FF3D_TC=0 forces the fp32 SIMT kernel everywhere (debugging aid; both are our own sm_100a kernels)
+import os as _os
+USE_TC = _os.environ.get("FF3D_TC", "1") != "0"
+
+
+def tc_weight_images(w):
+    """[taps, cin, cout] fp32 (cin in {8,16} or a multiple of 32) -> [n_tiles, n_stages, 2, bn, 32] fp32: per
+    (N tile, pipeline K-step) the hi and lo TF32 parts of the weights as 128B-swizzled K-major smem images
+    (row n = output channel, 16-byte chunk j stored at chunk j ^ (n % 8)): one cp.async.bulk per stage."""
+    taps, cin, cout = w.shape
+    bn = lib.ff3d_tcgemm_ntile(cin, cout)
+    if bn <= 0:
+        return None, 0
+    n_stages = lib.ff3d_tcgemm_stages(cin, taps)
+    if cin >= 32:
+        kmat = w.reshape(taps * cin, cout)                                    # stage s = rows [32 s, 32 s + 32)
+    else:
+        tps = 32 // cin
+        kmat = torch.zeros((n_stages * tps, cin, cout), dtype=torch.float32)
+        kmat[:taps] = w
+        kmat = kmat.reshape(n_stages * 32, cout)
+    hi = (kmat.contiguous().view(torch.int32) & -8192).view(torch.float32)   # clear the low 13 mantissa bits
+    lo = kmat - hi
+    n_tiles = cout // bn
+    n_idx = torch.arange(bn)
+    j_idx = torch.arange(8)
+    dst_chunk = (j_idx[None, :] ^ (n_idx[:, None] & 7))                       # [bn, 8]
+    imgs = torch.empty((n_tiles, n_stages, 2, bn, 32), dtype=torch.float32)
+    for part, src in enumerate((hi, lo)):
+        blk = src.view(n_stages, 8, 4, n_tiles, bn).permute(3, 0, 4, 1, 2)    # [tile, stage, n, j, e]
+        out = torch.empty((n_tiles, n_stages, bn, 8, 4), dtype=torch.float32)
+        out.scatter_(3, dst_chunk[None, None, :, :, None].expand(n_tiles, n_stages, bn, 8, 4), blk)
+        imgs[:, :, part] = out.view(n_tiles, n_stages, bn, 32)
+    return imgs.contiguous(), bn
+
+
+class PackedW:
+    """Device weights of one GEMM-like layer: ``w`` [taps, cin, ldw] (SIMT kernel) and ``img`` (tcgen05 kernel)."""
+
+    def __init__(self, w_cpu, dev):
+        self.w = w_cpu.to(dev)
+        img, self.bn = tc_weight_images(w_cpu)
+        self.img = img.to(dev) if img is not None else None
+
+    @property
+    def shape(self):
+        return self.w.shape
+
+
+def _gemm(d, w, what):
+    """Dispatch one implicit-GEMM launch: tcgen05 3xTF32 kernel when the layer is tensor-core tileable."""
+    if USE_TC and w.img is not None:
+        check(lib.ff3d_tcgemm(C.byref(d), _ptr(w.img), _stream()), f"ff3d_tcgemm({what})")
+    else:
+        check(lib.ff3d_igemm(C.byref(d), _stream()), f"ff3d_igemm({what})")
+
 
 # --------------------------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, out=None, act=ACT_NONE, res=None, x2=None, cout=None, res_after_act=False):
@@ -92,12 +148,12 @@ def linear(x, w, bias=None, out=None, act=ACT_NONE, res=None, x2=None, cout=None
     d.x, d.ldx, d.x2 = x.data_ptr(), x.stride(0), (x2.data_ptr() if x2 is not None else None)
     if x2 is not None and x2.stride(0) != x.stride(0):
         raise L.Ff3dError("linear: x2 must share x's row stride")
-    d.w, d.ldw, d.bias = w.data_ptr(), ldw, (bias.data_ptr() if bias is not None else None)
+    d.w, d.ldw, d.bias = w.w.data_ptr(), ldw, (bias.data_ptr() if bias is not None else None)
     d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
     d.y, d.ldy, d.act = out.data_ptr(), out.stride(0), act
     d.res_after_act = 1 if res_after_act else 0
     t0 = prof.begin()
-    check(lib.ff3d_igemm(C.byref(d), _stream()), "ff3d_igemm(rows)")
+    _gemm(d, w, "rows")
     prof.end(t0, f"linear[{cin}x{cout}]", 2.0 * M * cin * cout, 4.0 * (M * cin + cin * cout + M * cout))
     _count()
     return out
@@ -126,7 +182,7 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     d = GemmDesc()
     d.mode, d.M, d.cin, d.cout, d.taps = GEMM_CONV2D, B * Ho * Wo, cin, cout, k * k
     d.x, d.ldx = x.data_ptr(), ldx
-    d.w, d.ldw, d.bias = w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
+    d.w, d.ldw, d.bias = w.w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
     if res is not None:
         rB, rH, rW, rC, ldr, rbs = _nhwc_geom(res, "conv2d.res")
         if rbs != rH * rW or (rB, rH, rW) != (B, Ho, Wo) or u != 1:
@@ -137,7 +193,7 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     d.x_bstride, d.y_bstride, d.y_row0 = xbs, ybs, 0
     d.ux, d.uy, d.dx, d.dy = u, u, dx, dy
     t0 = prof.begin()
-    check(lib.ff3d_igemm(C.byref(d), _stream()), "ff3d_igemm(conv2d)")
+    _gemm(d, w, "conv2d")
     Mo = B * Ho * Wo
     prof.end(t0, f"conv{k}x{k}s{stride}[{cin}->{cout}@{Ho}]", 2.0 * Mo * k * k * cin * cout,
              4.0 * (B * H * W * cin + k * k * cin * cout + Mo * cout))
@@ -155,13 +211,13 @@ def sparse_conv(x, nbr, n_dev, w, bias, out, act=ACT_RELU, res=None, y_off=None,
     d = GemmDesc()
     d.mode, d.M, d.m_dev, d.cin, d.cout, d.taps = GEMM_SPARSE, cap, n_dev.data_ptr(), cin, cout, taps
     d.x, d.ldx = x.data_ptr(), x.stride(0)
-    d.w, d.ldw, d.bias = w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
+    d.w, d.ldw, d.bias = w.w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
     d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
     d.y, d.ldy, d.act = out.data_ptr(), (out.stride(0) if y_off is None else 0), act
     d.nbr, d.nbr_stride = nbr.data_ptr(), nbr.stride(0)
     d.y_off = y_off.data_ptr() if y_off is not None else None
     t0 = prof.begin()
-    check(lib.ff3d_igemm(C.byref(d), _stream()), "ff3d_igemm(sparse)")
+    _gemm(d, w, "sparse")
     prof.end(t0, f"spconv[{taps}t {cin}->{cout}]", None, None, n_dev, dict(nbr=nbr, cin=cin, cout=cout, taps=taps,
                                                                             x_rows=x.shape[0]))
     _count()

@@ -124,6 +124,16 @@ typedef struct ff3d_gemm_desc {
 
 int ff3d_igemm(const ff3d_gemm_desc* desc, ff3d_stream_t stream);
 
+/* Same contract on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, weights staged by
+ * cp.async.bulk) with 3xTF32 split accumulation, i.e. fp32-grade accuracy: D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.
+ * Supported when ff3d_tcgemm_ntile(cin, cout) > 0 (cin in {8,16} or a multiple of 32; cout in {16,32,64} or a
+ * multiple of 128).  `wimg` = [cout/ntile][ff3d_tcgemm_stages(cin,taps)][2][ntile*32] floats: per (N tile, K step)
+ * the hi and lo TF32 parts of w as 128B-swizzled K-major shared-memory images (focalformer3d_b200/ops.py
+ * tc_weight_images).  desc->w / ldw are ignored. */
+int ff3d_tcgemm(const ff3d_gemm_desc* desc, const float* wimg, ff3d_stream_t stream);
+int ff3d_tcgemm_ntile(int cin, int cout);
+int ff3d_tcgemm_stages(int cin, int taps);
+
 /* Depthwise 3x3 stride 1 pad 1, NHWC, folded BN + activation (torchvision InvertedResidual dw conv,
  * focal_encoder.py:36-38). x [B,H,W,C] (ldx), w [9, C], bias [C]. */
 int ff3d_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy, int B, int H, int W,

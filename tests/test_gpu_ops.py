@@ -400,3 +400,43 @@ def test_head_update_and_box_decode(ops):
     assert torch.equal(labels.cpu().long(), torch.stack([r["labels"] for r in ref]).view(-1))
     pr = torch.tensor([-61.2, -61.2, -10.0, 61.2, 61.2, 10.0])
     assert torch.equal(keep.cpu().bool(), ((rb[:, :3] >= pr[:3]) & (rb[:, :3] <= pr[3:])).all(1))
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 path
+@pytest.mark.parametrize("M,K,N", [(128, 32, 16), (1000, 128, 128), (300, 1024, 128), (2400, 128, 384), (129, 64, 64),
+                                   (4096, 512, 256)])
+def test_tcgemm_3xtf32_accuracy_vs_fp64(ops, M, K, N):
+    """The tensor-core kernel must be fp32-grade (3xTF32), not TF32-grade: error vs fp64 ~1e-6 of the row norm,
+    and indistinguishable from the SIMT fp32 kernel."""
+    g = torch.Generator().manual_seed(M + K + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    pw = _pack_lin(w)
+    assert pw.img is not None
+    old = ops.USE_TC
+    try:
+        ops.USE_TC = True
+        y_tc = ops.linear(x.cuda(), pw, b.cuda()).cpu()
+        ops.USE_TC = False
+        y_simt = ops.linear(x.cuda(), pw, b.cuda()).cpu()
+    finally:
+        ops.USE_TC = old
+    e_tc = (y_tc.double() - ref).abs().max().item()
+    e_simt = (y_simt.double() - ref).abs().max().item()
+    assert e_tc < 2e-5, f"tcgen05 3xTF32 max abs err {e_tc} (SIMT fp32: {e_simt})"
+    assert e_simt < 2e-5
+
+
+def test_tcgemm_conv_small_cin_taps_share_a_kstep(ops):
+    """cin=16 (two taps per 128-byte K-step) and cin=8 (four) against fp64 conv."""
+    for cin, cout in ((16, 16), (8, 32), (16, 64)):
+        g = torch.Generator().manual_seed(cin * cout)
+        B, H, W = 2, 11, 9
+        x = torch.randn(B, cin, H, W, generator=g)
+        w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+        ref = F.conv2d(x.double(), w.double(), padding=1).float()
+        out = torch.empty((B, H, W, cout), device="cuda")
+        pw = _pack_conv(w)
+        assert pw.img is not None
+        ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), pw, None, out, 3)
+        assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-5
