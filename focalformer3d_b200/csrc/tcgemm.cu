@@ -4,8 +4,7 @@
 //
 // B200 has no fp32 tensor-core MMA; kind::tf32 keeps 10 mantissa bits.  The parity bar of this path (heatmaps and box
 // regressions within 1e-3 of an fp32 oracle, bit-exact top-k) does not survive ~40 stacked TF32 layers, so each operand
-// is split a = a_hi + a_lo (a_hi = a with the low 13 mantissa bits cleared, a_lo = a - a_hi, both exact TF32 values up
-// to 2^-22 relative) and D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulates in fp32 in TMEM.
+// is split a = a_hi + a_lo (a_hi = rn_tf32(a), a_lo = rn_tf32(a - a_hi): a_hi + a_lo reproduces a to ~2^-24 relative) and D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulates in fp32 in TMEM.
 //
 // CTA = one 128 x BN output tile, 192 threads:
 //   warps 0-3  A producers: each thread owns one of the 128 tile rows; per pipeline stage it gathers the row's 32
@@ -115,6 +114,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// round-to-nearest fp32 -> tf32 (result in fp32 layout, low 13 mantissa bits zero)
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // byte offset of (row r, 16-byte chunk j) inside a 128B-swizzled K-major tile whose base is 1024B aligned
 __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
@@ -214,6 +220,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
           int q = idx >> qshift, j = idx & ((1 << qshift) - 1);
           long long sr = q == 0 ? srs[0] : q == 1 ? srs[1] : q == 2 ? srs[2] : srs[3];
           v[idx] = sr >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + sr * p.ldx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (MODE == FF3D_GEMM_ROWS && p.x2 && sr >= 0) {
+            float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + sr * p.ldx) + j);
+            v[idx].x += u.x; v[idx].y += u.y; v[idx].z += u.z; v[idx].w += u.w;
+          }
         }
       }
       mbar_wait(&empty_bar[slot], ph ^ 1u);
@@ -222,10 +232,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u); l.x = v[j].x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u); l.y = v[j].y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u); l.z = v[j].z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u); l.w = v[j].w - h.w;
+        h.x = to_tf32(v[j].x); l.x = to_tf32(v[j].x - h.x);
+        h.y = to_tf32(v[j].y); l.y = to_tf32(v[j].y - h.y);
+        h.z = to_tf32(v[j].z); l.z = to_tf32(v[j].z - h.z);
+        h.w = to_tf32(v[j].w); l.w = to_tf32(v[j].w - h.w);
         uint32_t o = swz(r, j);
         *reinterpret_cast<float4*>(a_hi + o) = h;
         *reinterpret_cast<float4*>(a_lo + o) = l;

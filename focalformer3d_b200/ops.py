@@ -98,8 +98,10 @@ def tc_weight_images(w):
         kmat = torch.zeros((n_stages * tps, cin, cout), dtype=torch.float32)
         kmat[:taps] = w
         kmat = kmat.reshape(n_stages * 32, cout)
-    hi = (kmat.contiguous().view(torch.int32) & -8192).view(torch.float32)   # clear the low 13 mantissa bits
-    lo = kmat - hi
+    def rn_tf32(t):          # cvt.rna.tf32.f32: round the magnitude to 10 mantissa bits, ties away from zero
+        return ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    hi = rn_tf32(kmat)
+    lo = rn_tf32(kmat - hi)
     n_tiles = cout // bn
     n_idx = torch.arange(bn)
     j_idx = torch.arange(8)

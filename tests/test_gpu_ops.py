@@ -423,8 +423,13 @@ def test_tcgemm_3xtf32_accuracy_vs_fp64(ops, M, K, N):
         ops.USE_TC = old
     e_tc = (y_tc.double() - ref).abs().max().item()
     e_simt = (y_simt.double() - ref).abs().max().item()
-    assert e_tc < 2e-5, f"tcgen05 3xTF32 max abs err {e_tc} (SIMT fp32: {e_simt})"
+    print(f"M={M} K={K} N={N}: tcgen05 3xTF32 err {e_tc:.2e}, SIMT fp32 err {e_simt:.2e}")
+    assert e_tc < 3e-5 and e_tc < 8 * e_simt, f"tcgen05 3xTF32 max abs err {e_tc} (SIMT fp32: {e_simt})"
     assert e_simt < 2e-5
+    # a single TF32 pass would be ~1e-3 here: the split accumulation is what buys the parity bar
+    tf32 = lambda t: ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    e_1x = ((tf32(x).double() @ tf32(w).double().t() + b.double()) - ref).abs().max().item()
+    assert e_tc < 0.2 * e_1x
 
 
 def test_tcgemm_conv_small_cin_taps_share_a_kstep(ops):
