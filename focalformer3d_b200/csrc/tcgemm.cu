@@ -6,15 +6,23 @@
 // regressions within 1e-3 of an fp32 oracle, bit-exact top-k) does not survive ~40 stacked TF32 layers, so each operand
 // is split a = a_hi + a_lo (a_hi = rn_tf32(a), a_lo = rn_tf32(a - a_hi): a_hi + a_lo reproduces a to ~2^-24 relative) and D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulates in fp32 in TMEM.
 //
-// CTA = one 128 x BN output tile, 192 threads:
-//   warps 0-3  A producers: each thread owns one of the 128 tile rows; per pipeline stage it gathers the row's 32
-//              fp32 (128 B: one conv tap x 32 channels, or 32/cin taps when cin < 32) with 8 LDG.128, splits hi/lo in
-//              registers and stores both into the 128B-swizzled K-major smem tiles (generic proxy) ->
-//              fence.proxy.async -> mbarrier arrive.  After the main loop the same warps run the epilogue
+// The two small cross terms go to their own TMEM accumulator: the tensor core's fp32 accumulate truncates, so every
+// accumulation step costs up to 1 ulp of the running sum; keeping the 2/3 of the steps that carry 2^-11-sized terms
+// out of the main accumulator cuts that bias 3x for free (measured: K=1024 error 3.1e-5 -> see tests).
+//
+// CTA = one 128 x BN output tile, 320 threads:
+//   warps 0-3, 4-7  two A-producer groups (even / odd pipeline stages): each thread owns one of the 128 tile rows;
+//              per stage it gathers the row's 32 fp32 (128 B: one conv tap x 32 channels, or 32/cin taps when
+//              cin < 32) with 8 LDG.128, splits hi/lo in registers and stores both into the 128B-swizzled K-major
+//              smem tiles (generic proxy) -> fence.proxy.async -> mbarrier arrive.  Two groups (and 2 CTAs/SM for
+//              BN <= 64) keep several 16 KB gathers in flight per SM: the gather is latency-bound otherwise.
+//              After the main loop both groups run the epilogue, half the columns each
 //              (tcgen05.ld 32x32b: thread <-> TMEM lane <-> tile row).
-//   warp 4     B producer: one cp.async.bulk (UBLKCP) per stage of the host-pre-swizzled [hi | lo] weight image.
-//   warp 5     TMEM alloc/dealloc + single-thread tcgen05.mma issue (12 MMAs of 128 x BN x 8 per stage),
+//   warp 8     B producer: one cp.async.bulk (UBLKCP) per stage of the host-pre-swizzled [hi | lo] weight image.
+//   warp 9     TMEM alloc/dealloc + single-thread tcgen05.mma issue (12 MMAs of 128 x BN x 8 per stage),
 //              tcgen05.commit releases smem stages / signals the epilogue.
+// Sparse mode stages the tile's whole neighbour map (taps x 128 int32) in shared memory up front, so the gather's
+// dependent index load is off the per-stage critical path.
 #include "common.cuh"
 
 namespace ff3d {
@@ -39,7 +47,8 @@ struct TcP {
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr int TC_MAX_TAPS = 27;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -125,7 +134,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 template <int MODE, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int n_slots) {
+__global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], then barriers
   constexpr uint32_t A_BYTES = TC_BM * 128;
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
   uint64_t* empty_bar = full_bar + n_slots;
   uint64_t* tmem_full = empty_bar + n_slots;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  int* nbr_s = reinterpret_cast<int*>(tmem_ptr + 2);   // [taps][128], SPARSE mode only
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_BM;
@@ -144,17 +154,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
   if (p.m_dev) { int md = *p.m_dev; Mv = md < Mv ? md : Mv; }
   if (m0 >= Mv) return;   // uniform for the whole CTA, before any barrier / TMEM use
 
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // main accumulator | small-term accumulator
   if (tid == 0) {
     for (int s = 0; s < n_slots; ++s) { mbar_init(&full_bar[s], TC_BM + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "n"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (MODE == FF3D_GEMM_SPARSE) {
+    for (int i = tid; i < p.taps * TC_BM; i += TC_THREADS) {
+      int t = i >> 7, rr = i & 127;
+      nbr_s[i] = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -162,9 +178,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
   const uint32_t tmem_base = *tmem_ptr;
   const int n_stages = p.n_stages;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =========================== A producers: thread <-> tile row ===========================
-    const int r = tid;
+    const int grp = warp >> 2;
+    const int r = tid & 127;
     const int m = m0 + r;
     const bool rvalid = m < Mv;
     int cb = 0, coy = 0, cox = 0;
@@ -184,9 +201,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
         if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
         return cb * p.x_bstride + (long long)iy * p.W + ix;
       }
-      return (long long)__ldg(p.nbr + (size_t)t * p.nbr_stride + m);
+      return (long long)nbr_s[t * TC_BM + r];
     };
-    for (int s = 0; s < n_stages; ++s) {
+    for (int s = grp; s < n_stages; s += 2) {
       const int slot = s % n_slots;
       const uint32_t ph = (uint32_t)((s / n_slots) & 1);
       float4 v[8];
@@ -258,15 +275,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
       }
     }
     const int n0 = ntile * BN;
+    constexpr int CPG = BN >= 32 ? BN / 2 : BN;          // columns per producer group in the epilogue
+    const int c_begin = BN >= 32 ? grp * CPG : 0;
+    const int c_end = (BN >= 32 || grp == 0) ? c_begin + CPG : 0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);   // warp-collective: all lanes execute
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      float v[16], v2[16];
+      tmem_ld16(lane_base + (uint32_t)c0, v);             // warp-collective: all lanes execute
+      tmem_ld16(lane_base + (uint32_t)(BN + c0), v2);
       if (rvalid) {
         const int n = n0 + c0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = v[i];
+          float a = v[i] + v2[i];
           if (p.bias) a += __ldg(p.bias + n + i);
           if (p.res_after_act) a = apply_act(a, p.act);
           if (p.res) a += __ldg(p.res + (long long)m * p.ldres + n + i);
@@ -283,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // =========================== B producer ===========================
     if (lane == 0) {
       const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
@@ -313,9 +335,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
         for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
           const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
           const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
-          umma_tf32(tmem_base, dal, dbh, idesc, (s | k) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          umma_tf32(tmem_base + BN, dal, dbh, idesc, (s | k) ? 1u : 0u);   // cross terms -> second accumulator
+          umma_tf32(tmem_base + BN, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, (s | k) ? 1u : 0u);
         }
         umma_commit(&empty_bar[slot]);   // frees the smem slot once these MMAs have read it
       }
@@ -324,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -333,11 +355,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcgemm_kernel(const TcP p, int 
 template <int MODE, int BN>
 static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
-  int n_slots = (int)((200 * 1024) / SLOT_BYTES);
-  if (n_slots > 6) n_slots = 6;
+  int n_slots = BN <= 64 ? 2 : 3;                       // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   if (n_slots > p.n_stages) n_slots = p.n_stages;
-  if (n_slots < 1) n_slots = 1;
-  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 2) * sizeof(uint64_t) + 1024;
+  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 2) * sizeof(uint64_t) + 16 +
+                (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TC_BM * sizeof(int) : 0) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tcgemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -402,7 +423,8 @@ extern "C" int ff3d_tcgemm(const ff3d_gemm_desc* d, const float* wimg, ff3d_stre
     if (p.x_bstride == 0) p.x_bstride = (long long)d->H * d->W;
     if (p.y_bstride == 0) p.y_bstride = (long long)d->Ho * p.uy * d->Wo * p.ux;
   } else if (d->mode == FF3D_GEMM_SPARSE) {
-    FF3D_REQUIRE(d->nbr != nullptr && d->nbr_stride >= d->M, "ff3d_tcgemm: sparse mode needs nbr [taps, >=M]");
+    FF3D_REQUIRE(d->nbr != nullptr && d->nbr_stride >= d->M && d->taps <= TC_MAX_TAPS,
+                 "ff3d_tcgemm: sparse mode needs nbr [taps <= 27, >=M]");
   } else {
     FF3D_REQUIRE(d->mode == FF3D_GEMM_ROWS && d->taps == 1, "ff3d_tcgemm: bad mode");
   }
