@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
   uint64_t* empty_bar = full_bar + n_slots;
   uint64_t* tmem_full = empty_bar + n_slots;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  int* nbr_s = reinterpret_cast<int*>(tmem_ptr + 2);   // [taps][128], SPARSE mode only
+  // SPARSE: nbr [taps][128]; CONV2D: int4 row info [128] (16-byte aligned)
+  int* aux_s = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TC_BM;
@@ -169,7 +170,20 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
   if (MODE == FF3D_GEMM_SPARSE) {
     for (int i = tid; i < p.taps * TC_BM; i += TC_THREADS) {
       int t = i >> 7, rr = i & 127;
-      nbr_s[i] = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
+      aux_s[i] = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
+    }
+  } else if (MODE == FF3D_GEMM_CONV2D) {
+    if (tid < TC_BM) {
+      int mm = m0 + tid;
+      int4 info = make_int4(0, 0, 0, 0);
+      if (mm < Mv) {
+        int hw = p.Ho * p.Wo;
+        int b = mm / hw;
+        int rr = mm - b * hw;
+        int oy = rr / p.Wo, ox = rr - (rr / p.Wo) * p.Wo;
+        info = make_int4((int)(b * p.x_bstride), oy * p.stride - p.pad, ox * p.stride - p.pad, 1);
+      }
+      reinterpret_cast<int4*>(aux_s)[tid] = info;
     }
   }
   tc_fence_before();
@@ -179,8 +193,68 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
   const int n_stages = p.n_stages;
 
   if (warp < 8) {
-    // =========================== A producers: thread <-> tile row ===========================
+    // =========================== A producers ===========================
+    // 8 consecutive lanes read the 8 16-byte chunks of ONE row (a full 128-byte line per quarter-warp request:
+    // 4 L1 wavefronts per LDG.128 instead of 32), 4 rows per warp instruction, 8 instructions per stage.
     const int grp = warp >> 2;
+    const int pw = warp & 3;
+    const int j = lane & 7;
+    const int q = lane >> 3;
+    const int qshift = p.cin == 16 ? 2 : 1;
+    const int lane_tap = p.cin >= 32 ? 0 : (j >> qshift);                 // tap within the stage (cin < 32)
+    const int lane_coff = p.cin >= 32 ? j * 4 : (j & ((1 << qshift) - 1)) * 4;
+    auto src_row = [&](int row, int t) -> long long {
+      if (t >= p.taps) return -1;
+      if (MODE == FF3D_GEMM_ROWS) return (m0 + row < Mv) ? (long long)(m0 + row) : -1;
+      if (MODE == FF3D_GEMM_CONV2D) {
+        const int4 info = reinterpret_cast<const int4*>(aux_s)[row];
+        if (!info.w) return -1;
+        int ky = t / p.kw, kx = t - ky * p.kw;
+        int iy = info.y + ky, ix = info.z + kx;
+        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
+        return (long long)info.x + (long long)iy * p.W + ix;
+      }
+      return (long long)aux_s[t * TC_BM + row];
+    };
+    for (int s = grp; s < n_stages; s += 2) {
+      const int slot = s % n_slots;
+      const uint32_t ph = (uint32_t)((s / n_slots) & 1);
+      int t, coff;
+      if (p.cin >= 32) { t = s / p.cpt; coff = (s - t * p.cpt) * 32 + lane_coff; }
+      else { t = s * p.tps + lane_tap; coff = lane_coff; }
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = pw * 32 + i * 4 + q;
+        const long long sr = src_row(row, t);
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sr >= 0) {
+          v[i] = __ldg(reinterpret_cast<const float4*>(p.x + sr * p.ldx + coff));
+          if (MODE == FF3D_GEMM_ROWS && p.x2) {
+            float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + sr * p.ldx + coff));
+            v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+          }
+        }
+      }
+      mbar_wait(&empty_bar[slot], ph ^ 1u);
+      uint8_t* a_hi = smem + (size_t)slot * SLOT_BYTES;
+      uint8_t* a_lo = a_hi + A_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = pw * 32 + i * 4 + q;
+        float4 h, l;
+        h.x = to_tf32(v[i].x); l.x = to_tf32(v[i].x - h.x);
+        h.y = to_tf32(v[i].y); l.y = to_tf32(v[i].y - h.y);
+        h.z = to_tf32(v[i].z); l.z = to_tf32(v[i].z - h.z);
+        h.w = to_tf32(v[i].w); l.w = to_tf32(v[i].w - h.w);
+        const uint32_t o = swz(row, j);
+        *reinterpret_cast<float4*>(a_hi + o) = h;
+        *reinterpret_cast<float4*>(a_lo + o) = l;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full_bar[slot]);
+    }
+    // epilogue mapping: thread <-> tile row (TMEM lane)
     const int r = tid & 127;
     const int m = m0 + r;
     const bool rvalid = m < Mv;
@@ -191,74 +265,6 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
       int rr = m - cb * hw;
       coy = rr / p.Wo;
       cox = rr - coy * p.Wo;
-    }
-    auto src_row = [&](int t) -> long long {
-      if (!rvalid || t >= p.taps) return -1;
-      if (MODE == FF3D_GEMM_ROWS) return m;
-      if (MODE == FF3D_GEMM_CONV2D) {
-        int ky = t / p.kw, kx = t - ky * p.kw;
-        int iy = coy * p.stride - p.pad + ky, ix = cox * p.stride - p.pad + kx;
-        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
-        return cb * p.x_bstride + (long long)iy * p.W + ix;
-      }
-      return (long long)nbr_s[t * TC_BM + r];
-    };
-    for (int s = grp; s < n_stages; s += 2) {
-      const int slot = s % n_slots;
-      const uint32_t ph = (uint32_t)((s / n_slots) & 1);
-      float4 v[8];
-      if (p.cin >= 32) {
-        int t = s / p.cpt, c0 = (s - t * p.cpt) * 32;
-        long long sr = src_row(t);
-        if (sr >= 0) {
-          const float4* g = reinterpret_cast<const float4*>(p.x + sr * p.ldx + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __ldg(g + j);
-          if (MODE == FF3D_GEMM_ROWS && p.x2) {
-            const float4* g2 = reinterpret_cast<const float4*>(p.x2 + sr * p.ldx + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 u = __ldg(g2 + j);
-              v[j].x += u.x; v[j].y += u.y; v[j].z += u.z; v[j].w += u.w;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-        // cin in {8, 16}: 32/cin taps share one 128-byte K-step (static register indexing only)
-        const int qshift = p.cin == 16 ? 2 : 1;      // float4 per tap = 1 << qshift
-        long long srs[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) srs[q] = q < p.tps ? src_row(s * p.tps + q) : -1;
-#pragma unroll
-        for (int idx = 0; idx < 8; ++idx) {
-          int q = idx >> qshift, j = idx & ((1 << qshift) - 1);
-          long long sr = q == 0 ? srs[0] : q == 1 ? srs[1] : q == 2 ? srs[2] : srs[3];
-          v[idx] = sr >= 0 ? __ldg(reinterpret_cast<const float4*>(p.x + sr * p.ldx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (MODE == FF3D_GEMM_ROWS && p.x2 && sr >= 0) {
-            float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + sr * p.ldx) + j);
-            v[idx].x += u.x; v[idx].y += u.y; v[idx].z += u.z; v[idx].w += u.w;
-          }
-        }
-      }
-      mbar_wait(&empty_bar[slot], ph ^ 1u);
-      uint8_t* a_hi = smem + (size_t)slot * SLOT_BYTES;
-      uint8_t* a_lo = a_hi + A_BYTES;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 h, l;
-        h.x = to_tf32(v[j].x); l.x = to_tf32(v[j].x - h.x);
-        h.y = to_tf32(v[j].y); l.y = to_tf32(v[j].y - h.y);
-        h.z = to_tf32(v[j].z); l.z = to_tf32(v[j].z - h.z);
-        h.w = to_tf32(v[j].w); l.w = to_tf32(v[j].w - h.w);
-        uint32_t o = swz(r, j);
-        *reinterpret_cast<float4*>(a_hi + o) = h;
-        *reinterpret_cast<float4*>(a_lo + o) = l;
-      }
-      fence_proxy_async();
-      mbar_arrive(&full_bar[slot]);
     }
     // =========================== epilogue: TMEM -> registers -> global ===========================
     mbar_wait(tmem_full, 0);
@@ -357,8 +363,9 @@ static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
   int n_slots = BN <= 64 ? 2 : 3;                       // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   if (n_slots > p.n_stages) n_slots = p.n_stages;
-  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 2) * sizeof(uint64_t) + 16 +
-                (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TC_BM * sizeof(int) : 0) + 1024;
+  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 2) * sizeof(uint64_t) + 32 +
+                (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TC_BM * sizeof(int)
+                                          : (MODE == FF3D_GEMM_CONV2D ? (size_t)TC_BM * 16 : 0)) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tcgemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
