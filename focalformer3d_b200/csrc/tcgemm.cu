@@ -133,32 +133,52 @@ __device__ __forceinline__ float to_tf32(float x) {
 // byte offset of (row r, 16-byte chunk j) inside a 128B-swizzled K-major tile whose base is 1024B aligned
 __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
+// cheap round-to-nearest split: hi = rn_tf32(v) by integer add + mask (2 ALU ops), lo = v - hi (exact; the tensor core
+// drops lo's bits below its own 2^-11, i.e. ~2^-23 of v)
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = v - hi;
+}
+
+struct Ring {
+  int slot;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int k, int n) {
+    slot += k;
+    while (slot >= n) { slot -= n; phase ^= 1u; }
+  }
+};
+
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int MODE, int BN>
 __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], then barriers
+  // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
   constexpr uint32_t A_BYTES = TC_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t SLOT_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int ACC_COLS = 2 * BN;                               // main | cross-term accumulator
+  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // double buffered across tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_slots * SLOT_BYTES);
   uint64_t* empty_bar = full_bar + n_slots;
-  uint64_t* tmem_full = empty_bar + n_slots;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  // SPARSE: nbr [taps][128]; CONV2D: int4 row info [128] (16-byte aligned)
+  uint64_t* tfull_bar = empty_bar + n_slots;    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // SPARSE: nbr element offsets [taps][128]; CONV2D: int4 row info [128] (16-byte aligned)
   int* aux_s = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM;
-  const int ntile = blockIdx.y;
   int Mv = p.M;
   if (p.m_dev) { int md = *p.m_dev; Mv = md < Mv ? md : Mv; }
-  if (m0 >= Mv) return;   // uniform for the whole CTA, before any barrier / TMEM use
+  const int n_tiles_n = p.cout / BN;
+  const int total_tiles = ((Mv + TC_BM - 1) / TC_BM) * n_tiles_n;
+  if ((int)blockIdx.x >= total_tiles) return;   // uniform for the whole CTA, before any barrier / TMEM use
 
-  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // main accumulator | small-term accumulator
   if (tid == 0) {
     for (int s = 0; s < n_slots; ++s) { mbar_init(&full_bar[s], TC_BM + 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -167,25 +187,6 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (MODE == FF3D_GEMM_SPARSE) {
-    for (int i = tid; i < p.taps * TC_BM; i += TC_THREADS) {
-      int t = i >> 7, rr = i & 127;
-      aux_s[i] = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
-    }
-  } else if (MODE == FF3D_GEMM_CONV2D) {
-    if (tid < TC_BM) {
-      int mm = m0 + tid;
-      int4 info = make_int4(0, 0, 0, 0);
-      if (mm < Mv) {
-        int hw = p.Ho * p.Wo;
-        int b = mm / hw;
-        int rr = mm - b * hw;
-        int oy = rr / p.Wo, ox = rr - (rr / p.Wo) * p.Wo;
-        info = make_int4((int)(b * p.x_bstride), oy * p.stride - p.pad, ox * p.stride - p.pad, 1);
-      }
-      reinterpret_cast<int4*>(aux_s)[tid] = info;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -193,161 +194,213 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
   const int n_stages = p.n_stages;
 
   if (warp < 8) {
-    // =========================== A producers ===========================
-    // 8 consecutive lanes read the 8 16-byte chunks of ONE row (a full 128-byte line per quarter-warp request:
-    // 4 L1 wavefronts per LDG.128 instead of 32), 4 rows per warp instruction, 8 instructions per stage.
+    // =========================== A producers (+ deferred epilogue) ===========================
+    // 8 consecutive lanes read the 8 16-byte chunks of ONE row (a full 128-byte line per quarter-warp request),
+    // 4 rows per warp instruction, 8 instructions per stage.
     const int grp = warp >> 2;
     const int pw = warp & 3;
     const int j = lane & 7;
     const int q = lane >> 3;
+    const int ptid = tid & 255;
     const int qshift = p.cin == 16 ? 2 : 1;
-    const int lane_tap = p.cin >= 32 ? 0 : (j >> qshift);                 // tap within the stage (cin < 32)
+    const int lane_tap = p.cin >= 32 ? 0 : (j >> qshift);
     const int lane_coff = p.cin >= 32 ? j * 4 : (j & ((1 << qshift) - 1)) * 4;
-    auto src_row = [&](int row, int t) -> long long {
-      if (t >= p.taps) return -1;
-      if (MODE == FF3D_GEMM_ROWS) return (m0 + row < Mv) ? (long long)(m0 + row) : -1;
-      if (MODE == FF3D_GEMM_CONV2D) {
-        const int4 info = reinterpret_cast<const int4*>(aux_s)[row];
-        if (!info.w) return -1;
-        int ky = t / p.kw, kx = t - ky * p.kw;
-        int iy = info.y + ky, ix = info.z + kx;
-        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
-        return (long long)info.x + (long long)iy * p.W + ix;
+    const int r = tid & 127;                                  // epilogue: thread <-> tile row (TMEM lane)
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    Ring ring{grp % n_slots, (uint32_t)((grp / n_slots) & 1)};
+    constexpr int CPG = BN >= 32 ? BN / 2 : BN;               // epilogue columns per producer group
+    const int c_begin = BN >= 32 ? grp * CPG : 0;
+    const int c_end = (BN >= 32 || grp == 0) ? c_begin + CPG : 0;
+
+    auto epilogue = [&](int tile, int it) {
+      const int m0 = (tile / n_tiles_n) * TC_BM;
+      const int n0 = (tile - (tile / n_tiles_n) * n_tiles_n) * BN;
+      const int ab = it & 1;
+      mbar_wait(&tfull_bar[ab], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int m = m0 + r;
+      const bool rvalid = m < Mv;
+      float* yp = nullptr;
+      if (rvalid) {
+        if (MODE == FF3D_GEMM_CONV2D) {
+          int hw = p.Ho * p.Wo;
+          int cb = m / hw;
+          int rr = m - cb * hw;
+          int coy = rr / p.Wo, cox = rr - (rr / p.Wo) * p.Wo;
+          long long row = cb * p.y_bstride + p.y_row0 + (long long)(coy * p.uy + p.dy) * (p.Wo * p.ux) + cox * p.ux + p.dx;
+          yp = p.y + row * p.ldy;
+        } else if (MODE == FF3D_GEMM_SPARSE && p.y_off) {
+          yp = p.y + __ldg(p.y_off + m);
+        } else {
+          yp = p.y + (long long)m * p.ldy;
+        }
       }
-      return (long long)aux_s[t * TC_BM + row];
-    };
-    for (int s = grp; s < n_stages; s += 2) {
-      const int slot = s % n_slots;
-      const uint32_t ph = (uint32_t)((s / n_slots) & 1);
-      int t, coff;
-      if (p.cin >= 32) { t = s / p.cpt; coff = (s - t * p.cpt) * 32 + lane_coff; }
-      else { t = s * p.tps + lane_tap; coff = lane_coff; }
-      float4 v[8];
+      const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS);
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        float v[16], v2[16];
+        tmem_ld16(acc + (uint32_t)c0, v);                   // warp-collective: all lanes execute
+        tmem_ld16(acc + (uint32_t)(BN + c0), v2);
+        if (rvalid) {
+          const int n = n0 + c0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = pw * 32 + i * 4 + q;
-        const long long sr = src_row(row, t);
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sr >= 0) {
-          v[i] = __ldg(reinterpret_cast<const float4*>(p.x + sr * p.ldx + coff));
-          if (MODE == FF3D_GEMM_ROWS && p.x2) {
-            float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + sr * p.ldx + coff));
-            v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+          for (int i = 0; i < 16; ++i) {
+            float a = v[i] + v2[i];
+            if (p.bias) a += __ldg(p.bias + n + i);
+            if (p.res_after_act) a = apply_act(a, p.act);
+            if (p.res) a += __ldg(p.res + (long long)m * p.ldres + n + i);
+            if (!p.res_after_act) a = apply_act(a, p.act);
+            v[i] = a;
+          }
+          if ((reinterpret_cast<uintptr_t>(yp + n) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yp + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yp[n + i] = v[i];
           }
         }
       }
-      mbar_wait(&empty_bar[slot], ph ^ 1u);
-      uint8_t* a_hi = smem + (size_t)slot * SLOT_BYTES;
-      uint8_t* a_lo = a_hi + A_BYTES;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = pw * 32 + i * 4 + q;
-        float4 h, l;
-        h.x = to_tf32(v[i].x); l.x = to_tf32(v[i].x - h.x);
-        h.y = to_tf32(v[i].y); l.y = to_tf32(v[i].y - h.y);
-        h.z = to_tf32(v[i].z); l.z = to_tf32(v[i].z - h.z);
-        h.w = to_tf32(v[i].w); l.w = to_tf32(v[i].w - h.w);
-        const uint32_t o = swz(row, j);
-        *reinterpret_cast<float4*>(a_hi + o) = h;
-        *reinterpret_cast<float4*>(a_lo + o) = l;
-      }
-      fence_proxy_async();
-      mbar_arrive(&full_bar[slot]);
-    }
-    // epilogue mapping: thread <-> tile row (TMEM lane)
-    const int r = tid & 127;
-    const int m = m0 + r;
-    const bool rvalid = m < Mv;
-    int cb = 0, coy = 0, cox = 0;
-    if (MODE == FF3D_GEMM_CONV2D && rvalid) {
-      int hw = p.Ho * p.Wo;
-      cb = m / hw;
-      int rr = m - cb * hw;
-      coy = rr / p.Wo;
-      cox = rr - coy * p.Wo;
-    }
-    // =========================== epilogue: TMEM -> registers -> global ===========================
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    float* yp = nullptr;
-    if (rvalid) {
-      if (MODE == FF3D_GEMM_CONV2D) {
-        long long row = cb * p.y_bstride + p.y_row0 + (long long)(coy * p.uy + p.dy) * (p.Wo * p.ux) + cox * p.ux + p.dx;
-        yp = p.y + row * p.ldy;
-      } else if (MODE == FF3D_GEMM_SPARSE && p.y_off) {
-        yp = p.y + __ldg(p.y_off + m);
-      } else {
-        yp = p.y + (long long)m * p.ldy;
-      }
-    }
-    const int n0 = ntile * BN;
-    constexpr int CPG = BN >= 32 ? BN / 2 : BN;          // columns per producer group in the epilogue
-    const int c_begin = BN >= 32 ? grp * CPG : 0;
-    const int c_end = (BN >= 32 || grp == 0) ? c_begin + CPG : 0;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-#pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-      float v[16], v2[16];
-      tmem_ld16(lane_base + (uint32_t)c0, v);             // warp-collective: all lanes execute
-      tmem_ld16(lane_base + (uint32_t)(BN + c0), v2);
-      if (rvalid) {
-        const int n = n0 + c0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a = v[i] + v2[i];
-          if (p.bias) a += __ldg(p.bias + n + i);
-          if (p.res_after_act) a = apply_act(a, p.act);
-          if (p.res) a += __ldg(p.res + (long long)m * p.ldres + n + i);
-          if (!p.res_after_act) a = apply_act(a, p.act);
-          v[i] = a;
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[ab]);                          // 256 arrivals free the accumulator buffer
+    };
+
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles_n) * TC_BM;
+      // ---- per-tile gather metadata (both groups are past the previous tile's stages after the first barrier)
+      producer_bar();
+      if (MODE == FF3D_GEMM_SPARSE) {
+        for (int i = ptid; i < p.taps * TC_BM; i += 256) {
+          int t = i >> 7, rr = i & 127;
+          int v = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
+          aux_s[i] = v < 0 ? -1 : v * p.ldx;                 // element offset of the source row
         }
-        if ((reinterpret_cast<uintptr_t>(yp + n) & 15) == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yp + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) yp[n + i] = v[i];
+      } else if (MODE == FF3D_GEMM_CONV2D) {
+        if (ptid < TC_BM) {
+          int mm = m0 + ptid;
+          int4 info = make_int4(0, 0, 0, 0);
+          if (mm < Mv) {
+            int hw = p.Ho * p.Wo;
+            int b = mm / hw;
+            int rr = mm - b * hw;
+            int oy = rr / p.Wo, ox = rr - (rr / p.Wo) * p.Wo;
+            info = make_int4((int)(b * p.x_bstride), oy * p.stride - p.pad, ox * p.stride - p.pad, 1);
+          }
+          reinterpret_cast<int4*>(aux_s)[ptid] = info;
         }
       }
+      producer_bar();
+      // element offset of the source row feeding (row, tap t), or -1
+      auto src_off = [&](int row, int t, int ky, int kx) -> long long {
+        if (t >= p.taps) return -1;
+        if (MODE == FF3D_GEMM_ROWS) return (m0 + row < Mv) ? (long long)(m0 + row) * p.ldx : -1;
+        if (MODE == FF3D_GEMM_CONV2D) {
+          const int4 info = reinterpret_cast<const int4*>(aux_s)[row];
+          int iy = info.y + ky, ix = info.z + kx;
+          if (!info.w || iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
+          return ((long long)info.x + (long long)iy * p.W + ix) * p.ldx;
+        }
+        return (long long)aux_s[t * TC_BM + row];
+      };
+      // my stages of this tile: global stage index (it * n_stages + s) has my parity
+      int s = (grp + it * n_stages) & 1;
+      int t, cidx;                                           // tap and 32-channel chunk of stage s (cin >= 32)
+      if (p.cpt == 1) { t = s; cidx = 0; } else { t = 0; cidx = s; }
+      for (; s < n_stages; s += 2) {
+        int tap, coff, ky = 0, kx = 0;
+        if (p.cin >= 32) { tap = t; coff = cidx * 32 + lane_coff; }
+        else { tap = s * p.tps + lane_tap; coff = lane_coff; }
+        if (MODE == FF3D_GEMM_CONV2D) { ky = tap / p.kw; kx = tap - ky * p.kw; }
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = pw * 32 + i * 4 + q;
+          const long long so = src_off(row, tap, ky, kx);
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (so >= 0) {
+            v[i] = __ldg(reinterpret_cast<const float4*>(p.x + so + coff));
+            if (MODE == FF3D_GEMM_ROWS && p.x2) {
+              float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + so + coff));
+              v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+            }
+          }
+        }
+        mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
+        uint8_t* a_hi = smem + (size_t)ring.slot * SLOT_BYTES;
+        uint8_t* a_lo = a_hi + A_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = pw * 32 + i * 4 + q;
+          float4 h, l;
+          split_tf32(v[i].x, h.x, l.x);
+          split_tf32(v[i].y, h.y, l.y);
+          split_tf32(v[i].z, h.z, l.z);
+          split_tf32(v[i].w, h.w, l.w);
+          const uint32_t o = swz(row, j);
+          *reinterpret_cast<float4*>(a_hi + o) = h;
+          *reinterpret_cast<float4*>(a_lo + o) = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[ring.slot]);
+        ring.advance(2, n_slots);
+        if (p.cin >= 32) { cidx += 2; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
+      }
+      // epilogue of the PREVIOUS tile: its MMAs have had a whole tile's worth of gathers to finish, and the
+      // tensor core keeps working on this tile out of the other TMEM accumulator buffer meanwhile
+      if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+      prev_tile = tile;
     }
-    tc_fence_before();
+    if (prev_tile >= 0) epilogue(prev_tile, it - 1);
   } else if (warp == 8) {
     // =========================== B producer ===========================
     if (lane == 0) {
-      const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
-      for (int s = 0; s < n_stages; ++s) {
-        const int slot = s % n_slots;
-        const uint32_t ph = (uint32_t)((s / n_slots) & 1);
-        mbar_wait(&empty_bar[slot], ph ^ 1u);
-        uint8_t* b_hi = smem + (size_t)slot * SLOT_BYTES + 2 * A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[slot], 2 * B_BYTES);
-        bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, &full_bar[slot]);
+      Ring ring{0, 0u};
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ntile = tile - (tile / n_tiles_n) * n_tiles_n;
+        const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
+        for (int s = 0; s < n_stages; ++s) {
+          mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
+          uint8_t* b_hi = smem + (size_t)ring.slot * SLOT_BYTES + 2 * A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[ring.slot], 2 * B_BYTES);
+          bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, &full_bar[ring.slot]);
+          ring.advance(1, n_slots);
+        }
       }
     }
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BN);
-      for (int s = 0; s < n_stages; ++s) {
-        const int slot = s % n_slots;
-        const uint32_t ph = (uint32_t)((s / n_slots) & 1);
-        mbar_wait(&full_bar[slot], ph);
+      Ring ring{0, 0u};
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(&tempty_bar[ab], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue of tile it-2 drained this buffer
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + (size_t)slot * SLOT_BYTES);
-        const uint32_t a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_lo + A_BYTES;
-        const uint32_t b_lo = b_hi + B_BYTES;
+        const uint32_t d_main = tmem_base + (uint32_t)(ab * ACC_COLS);
+        const uint32_t d_cross = d_main + BN;
+        for (int s = 0; s < n_stages; ++s) {
+          mbar_wait(&full_bar[ring.slot], ring.phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + (size_t)ring.slot * SLOT_BYTES);
+          const uint32_t a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_lo + A_BYTES;
+          const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
-          const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
-          const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
-          umma_tf32(tmem_base + BN, dal, dbh, idesc, (s | k) ? 1u : 0u);   // cross terms -> second accumulator
-          umma_tf32(tmem_base + BN, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, (s | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
+            const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
+            const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
+            const uint32_t acc = (s | k) ? 1u : 0u;
+            umma_tf32(d_cross, dal, dbh, idesc, acc);
+            umma_tf32(d_cross, dah, dbl, idesc, 1u);
+            umma_tf32(d_main, dah, dbh, idesc, acc);
+          }
+          umma_commit(&empty_bar[ring.slot]);   // frees the smem slot once these MMAs have read it
+          ring.advance(1, n_slots);
         }
-        umma_commit(&empty_bar[slot]);   // frees the smem slot once these MMAs have read it
+        umma_commit(&tfull_bar[ab]);            // accumulator of this tile complete
       }
-      umma_commit(tmem_full);            // all MMAs done -> accumulator readable
     }
     __syncwarp();
   }
@@ -363,7 +416,7 @@ static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
   int n_slots = BN <= 64 ? 2 : 3;                       // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   if (n_slots > p.n_stages) n_slots = p.n_stages;
-  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 2) * sizeof(uint64_t) + 32 +
+  size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 4) * sizeof(uint64_t) + 32 +
                 (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TC_BM * sizeof(int)
                                           : (MODE == FF3D_GEMM_CONV2D ? (size_t)TC_BM * 16 : 0)) + 1024;
   static bool attr_set = false;
@@ -371,7 +424,10 @@ static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
     cudaFuncSetAttribute(tcgemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  dim3 grid(cdiv(p.M, TC_BM), n_tiles_n);
+  // persistent CTAs: one (BN = 128) or two (BN <= 64) per SM, each looping over output tiles
+  long long tiles = (long long)cdiv(p.M, TC_BM) * n_tiles_n;
+  long long resident = (long long)num_sms() * (BN <= 64 ? 2 : 1);
+  dim3 grid((unsigned)(tiles < resident ? tiles : resident));
   tcgemm_kernel<MODE, BN><<<grid, TC_THREADS, smem, st>>>(p, n_slots);
   return check_launch("ff3d_tcgemm");
 }
