@@ -258,6 +258,8 @@ def run_ours(args):
                     by, fl, _, _ = spconv_traffic(rec)
                 a = agg.setdefault(label, [0.0, 0.0, 0.0, 0])
                 a[0] += t / reps; a[1] += fl / reps; a[2] += by / reps; a[3] += 1
+        for label, (t, fl, by, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:28]:
+            log(f"  {t:7.3f} ms  x{cnt // reps:<3d} {fl / max(t, 1e-9) / 1e9:8.1f} TFLOP/s {by / max(t, 1e-9) / 1e6:8.1f} GB/s  {label}")
         pk = peaks()
         kinds = {"spconv": [0.0, 0.0, 0.0], "conv": [0.0, 0.0, 0.0], "linear": [0.0, 0.0, 0.0]}
         for label, (t, fl, by, _) in agg.items():

@@ -47,7 +47,6 @@ struct TcP {
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 320;
 constexpr int TC_MAX_TAPS = 27;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,10 +148,15 @@ struct Ring {
   }
 };
 
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-template <int MODE, int BN>
-__global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
+// G = number of 128-thread A-producer groups: 2 (and two CTAs per SM) for BN <= 64, 4 for BN = 128 (one CTA per SM):
+// either way four 16 KB gathers are in flight per SM
+template <int MODE, int BN, int G>
+__global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
+  constexpr int NT = 128 * G + 64;
+  constexpr int NPROD = 128 * G;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
   constexpr uint32_t A_BYTES = TC_BM * 128;
@@ -178,10 +182,10 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
 
   if (tid == 0) {
     for (int s = 0; s < n_slots; ++s) { mbar_init(&full_bar[s], TC_BM + 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NPROD); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == 4 * G + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
   const uint32_t tmem_base = *tmem_ptr;
   const int n_stages = p.n_stages;
 
-  if (warp < 8) {
+  if (warp < 4 * G) {
     // =========================== A producers (+ deferred epilogue) ===========================
     // 8 consecutive lanes read the 8 16-byte chunks of ONE row (a full 128-byte line per quarter-warp request),
     // 4 rows per warp instruction, 8 instructions per stage.
@@ -201,16 +205,17 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
     const int pw = warp & 3;
     const int j = lane & 7;
     const int q = lane >> 3;
-    const int ptid = tid & 255;
+    const int ptid = tid;                                     // producers are threads [0, NPROD)
     const int qshift = p.cin == 16 ? 2 : 1;
     const int lane_tap = p.cin >= 32 ? 0 : (j >> qshift);
     const int lane_coff = p.cin >= 32 ? j * 4 : (j & ((1 << qshift) - 1)) * 4;
     const int r = tid & 127;                                  // epilogue: thread <-> tile row (TMEM lane)
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     Ring ring{grp % n_slots, (uint32_t)((grp / n_slots) & 1)};
-    constexpr int CPG = BN >= 32 ? BN / 2 : BN;               // epilogue columns per producer group
-    const int c_begin = BN >= 32 ? grp * CPG : 0;
-    const int c_end = (BN >= 32 || grp == 0) ? c_begin + CPG : 0;
+    constexpr int EG = (BN / 16) < G ? (BN / 16) : G;          // groups taking part in the epilogue column split
+    constexpr int CPG = BN / EG;                               // columns per participating group (multiple of 16)
+    const int c_begin = grp < EG ? grp * CPG : 0;
+    const int c_end = grp < EG ? c_begin + CPG : 0;
 
     auto epilogue = [&](int tile, int it) {
       const int m0 = (tile / n_tiles_n) * TC_BM;
@@ -262,16 +267,16 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[ab]);                          // 256 arrivals free the accumulator buffer
+      mbar_arrive(&tempty_bar[ab]);                          // NPROD arrivals free the accumulator buffer
     };
 
     int it = 0, prev_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_tiles_n) * TC_BM;
       // ---- per-tile gather metadata (both groups are past the previous tile's stages after the first barrier)
-      producer_bar();
+      producer_bar<NPROD>();
       if (MODE == FF3D_GEMM_SPARSE) {
-        for (int i = ptid; i < p.taps * TC_BM; i += 256) {
+        for (int i = ptid; i < p.taps * TC_BM; i += NPROD) {
           int t = i >> 7, rr = i & 127;
           int v = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
           aux_s[i] = v < 0 ? -1 : v * p.ldx;                 // element offset of the source row
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
           reinterpret_cast<int4*>(aux_s)[ptid] = info;
         }
       }
-      producer_bar();
+      producer_bar<NPROD>();
       // element offset of the source row feeding (row, tap t), or -1
       auto src_off = [&](int row, int t, int ky, int kx) -> long long {
         if (t >= p.taps) return -1;
@@ -304,10 +309,11 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
         return (long long)aux_s[t * TC_BM + row];
       };
       // my stages of this tile: global stage index (it * n_stages + s) has my parity
-      int s = (grp + it * n_stages) & 1;
+      int s = (grp - it * n_stages) % G;                      // first stage of this tile with (it*n_stages + s) % G == grp
+      if (s < 0) s += G;
       int t, cidx;                                           // tap and 32-channel chunk of stage s (cin >= 32)
-      if (p.cpt == 1) { t = s; cidx = 0; } else { t = 0; cidx = s; }
-      for (; s < n_stages; s += 2) {
+      t = s / p.cpt; cidx = s - t * p.cpt;
+      for (; s < n_stages; s += G) {
         int tap, coff, ky = 0, kx = 0;
         if (p.cin >= 32) { tap = t; coff = cidx * 32 + lane_coff; }
         else { tap = s * p.tps + lane_tap; coff = lane_coff; }
@@ -343,8 +349,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[ring.slot]);
-        ring.advance(2, n_slots);
-        if (p.cin >= 32) { cidx += 2; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
+        ring.advance(G, n_slots);
+        if (p.cin >= 32) { cidx += G; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
       }
       // epilogue of the PREVIOUS tile: its MMAs have had a whole tile's worth of gathers to finish, and the
       // tensor core keeps working on this tile out of the other TMEM accumulator buffer meanwhile
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
       prev_tile = tile;
     }
     if (prev_tile >= 0) epilogue(prev_tile, it - 1);
-  } else if (warp == 8) {
+  } else if (warp == 4 * G) {
     // =========================== B producer ===========================
     if (lane == 0) {
       Ring ring{0, 0u};
@@ -405,7 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 4 * G + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -413,6 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN <= 64 ? 2 : 1)) tcgemm_kernel(
 
 template <int MODE, int BN>
 static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
+  constexpr int G = BN == 128 ? 4 : 2;
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
   int n_slots = BN <= 64 ? 2 : 3;                       // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   if (n_slots > p.n_stages) n_slots = p.n_stages;
@@ -421,14 +428,14 @@ static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
                                           : (MODE == FF3D_GEMM_CONV2D ? (size_t)TC_BM * 16 : 0)) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tcgemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tcgemm_kernel<MODE, BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   // persistent CTAs: one (BN = 128) or two (BN <= 64) per SM, each looping over output tiles
   long long tiles = (long long)cdiv(p.M, TC_BM) * n_tiles_n;
   long long resident = (long long)num_sms() * (BN <= 64 ? 2 : 1);
   dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-  tcgemm_kernel<MODE, BN><<<grid, TC_THREADS, smem, st>>>(p, n_slots);
+  tcgemm_kernel<MODE, BN, G><<<grid, 128 * G + 64, smem, st>>>(p, n_slots);
   return check_launch("ff3d_tcgemm");
 }
 
