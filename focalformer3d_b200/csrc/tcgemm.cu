@@ -151,11 +151,11 @@ struct Ring {
 template <int N>
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-// G = number of 128-thread A-producer groups: 2 (and two CTAs per SM) for BN <= 64, 4 for BN = 128 (one CTA per SM):
-// either way four 16 KB gathers are in flight per SM
+// G = number of 128-thread A-producer groups = number of smem slots: 2 (and two CTAs per SM) for BN <= 64, 3 for
+// BN = 128 (one CTA per SM).  n_slots == G makes every group the sole owner of one slot, so a producer is never more
+// than one mbarrier phase ahead of the MMA issuer (the parity wait cannot tell phases two apart).
 template <int MODE, int BN, int G>
 __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
-  constexpr int NT = 128 * G + 64;
   constexpr int NPROD = 128 * G;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
@@ -212,10 +212,6 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
     const int r = tid & 127;                                  // epilogue: thread <-> tile row (TMEM lane)
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     Ring ring{grp % n_slots, (uint32_t)((grp / n_slots) & 1)};
-    constexpr int EG = (BN / 16) < G ? (BN / 16) : G;          // groups taking part in the epilogue column split
-    constexpr int CPG = BN / EG;                               // columns per participating group (multiple of 16)
-    const int c_begin = grp < EG ? grp * CPG : 0;
-    const int c_end = grp < EG ? c_begin + CPG : 0;
 
     auto epilogue = [&](int tile, int it) {
       const int m0 = (tile / n_tiles_n) * TC_BM;
@@ -242,7 +238,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       }
       const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS);
 #pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      for (int c0 = grp * 16; c0 < BN; c0 += 16 * G) {       // 16-column chunks dealt round-robin to the groups
         float v[16], v2[16];
         tmem_ld16(acc + (uint32_t)c0, v);                   // warp-collective: all lanes execute
         tmem_ld16(acc + (uint32_t)(BN + c0), v2);
@@ -419,10 +415,9 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
 
 template <int MODE, int BN>
 static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
-  constexpr int G = BN == 128 ? 4 : 2;
+  constexpr int G = BN == 128 ? 3 : 2;
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
-  int n_slots = BN <= 64 ? 2 : 3;                       // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
-  if (n_slots > p.n_stages) n_slots = p.n_stages;
+  const int n_slots = G;                                // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 4) * sizeof(uint64_t) + 32 +
                 (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TC_BM * sizeof(int)
                                           : (MODE == FF3D_GEMM_CONV2D ? (size_t)TC_BM * 16 : 0)) + 1024;

@@ -404,7 +404,7 @@ def test_head_update_and_box_decode(ops):
 
 # ------------------------------------------------------------------------------------------------ tcgen05 path
 @pytest.mark.parametrize("M,K,N", [(128, 32, 16), (1000, 128, 128), (300, 1024, 128), (2400, 128, 384), (129, 64, 64),
-                                   (4096, 512, 256)])
+                                   (4096, 512, 256), (60000, 288, 128), (80000, 64, 32), (40000, 96, 64)])
 def test_tcgemm_3xtf32_accuracy_vs_fp64(ops, M, K, N):
     """The tensor-core kernel must be fp32-grade (3xTF32), not TF32-grade: error vs fp64 ~1e-6 of the row norm,
     and indistinguishable from the SIMT fp32 kernel."""
