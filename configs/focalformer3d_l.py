@@ -62,6 +62,10 @@ model = dict(
                         out_size_factor=out_size_factor,
                         post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
                         score_threshold=0.0, code_size=10),
+        # use_sigmoid=True keeps num_classes at 10 (focal_decoder.py:164-166 adds a background class otherwise)
+        loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2, alpha=0.25, reduction='mean', loss_weight=1.0),
+        loss_bbox=dict(type='L1Loss', reduction='mean', loss_weight=0.25),
+        loss_heatmap=dict(type='GaussianFocalLoss', reduction='mean', loss_weight=1.0),
         decoder_cfg=_decoder),
     test_cfg=dict(pts=dict(dataset='nuScenes', grid_size=[1440, 1440, 40], out_size_factor=out_size_factor,
                            pc_range=point_cloud_range[0:2], voxel_size=voxel_size[:2], nms_type=None)))

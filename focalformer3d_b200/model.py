@@ -381,11 +381,15 @@ class FocalDecoder(ParamTree):
                  multiscale=False, multistage_heatmap=False, reuse_first_heatmap=False, extra_feat=False,
                  heatmap_box=False, bevpos=False, input_img=True, iterbev_wo_img=False, mask_heatmap_mode="poscls",
                  roi_feats=0, roi_dropout_rate=0.0, roi_expand_ratio=1.0, roi_based_reg=False, classaware_reg=False,
-                 boxpos=None, decoder_cfg=None, spec=None, **unused):
+                 boxpos=None, decoder_cfg=None, spec=None, loss_cls=dict(type='GaussianFocalLoss', reduction='mean'),
+                 **unused):
         super().__init__()
         if not (initialize_by_heatmap and multiscale and bevpos and extra_feat and mask_heatmap_mode == "poscls") \
                 or heatmap_box or classaware_reg or boxpos is not None:
             raise NotImplementedError("FocalDecoder: only the shipped FocalFormer3D LiDAR head variant is built")
+        if not loss_cls.get("use_sigmoid", False):
+            # focal_decoder.py:164-166 appends a background class in that case; no shipped config uses it
+            raise NotImplementedError("FocalDecoder: only loss_cls.use_sigmoid=True heads are built")
         stages = (multistage_heatmap or 0) + (1 if reuse_first_heatmap else 0)
         if stages < 1:
             raise NotImplementedError("FocalDecoder: single-stage (DeformFormer3D) head is a later scope row")

@@ -145,9 +145,13 @@ class FocalDecoder(nn.Module):
                  bbox_coder=None, multiscale=False, multistage_heatmap=False, reuse_first_heatmap=False,
                  extra_feat=False, heatmap_box=False, bevpos=False, input_img=True, iterbev_wo_img=False,
                  mask_heatmap_mode="poscls", roi_feats=0, roi_dropout_rate=0.0, roi_expand_ratio=1.0,
-                 roi_based_reg=False, classaware_reg=False, boxpos=None, decoder_cfg=None, **unused):
+                 roi_based_reg=False, classaware_reg=False, boxpos=None, decoder_cfg=None,
+                 loss_cls=dict(type='GaussianFocalLoss', reduction='mean'), **unused):
         super().__init__()
         assert initialize_by_heatmap and not heatmap_box and not classaware_reg and boxpos is None
+        # focal_decoder.py:164-166: a background class is appended unless loss_cls.use_sigmoid; every shipped config
+        # sets use_sigmoid=True (the softmax variant would break class_encoding's channel count in the reference)
+        assert loss_cls.get('use_sigmoid', False), 'only the use_sigmoid=True classification head is restated'
         self.num_classes = num_classes
         self.num_proposals_ori = self.num_proposals = num_proposals
         self.num_decoder_layers = num_decoder_layers

@@ -1,0 +1,212 @@
+"""Generate golden fixtures by running the REAL reference modules (in-tree part of the hot path) on the CPU.
+
+Run in the build container, where /root/reference exists:   python tests/golden/make_golden.py
+The fixtures (tests/golden/*.pt) travel with the repo; the reference does not.
+
+What runs from /root/reference, unmodified:
+  projects/mmdet3d_plugin/models/utils/utils.py               (MLP, gen_sineembed_for_position)
+  projects/mmdet3d_plugin/core/bbox/coders/transfusion_bbox_coder.py   (TransFusionBBoxCoder)
+  projects/mmdet3d_plugin/models/utils/decoder_utils.py        (FFN prediction heads)
+  projects/mmdet3d_plugin/models/utils/encoder_utils.py        (ConvBNReLU)
+  projects/mmdet3d_plugin/models/necks/focal_encoder.py        (FocalEncoder, FocalEncoderLayer)
+  projects/mmdet3d_plugin/models/dense_heads/focal_decoder.py  (FocalDecoder.forward / get_bboxes)
+What is stubbed (absent upstream packages mmcv / mmdet / mmdet3d): ConvModule, build_conv_layer,
+build_transformer_layer_sequence (-> oracle/transformer.py), rotation_3d_in_axis (-> oracle restatement), registries,
+losses, box containers, and the reference's hard-coded device='cuda' (torch.as_tensor / torch.ones wrappers).
+The weights are the repo's seeded synthetic state dict, loaded with strict=True into the real modules -- which also
+pins the checkpoint-key contract of the in-tree modules.
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+from torch import nn
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _pkg(name, path):
+    m = _mod(name)
+    m.__path__ = [path]
+    return m
+
+
+class _Registry:
+    def __init__(self):
+        self.map = {}
+
+    def register_module(self, *a, **k):
+        def deco(cls):
+            self.map[cls.__name__] = cls
+            return cls
+        return deco
+
+    def build(self, cfg, **kw):
+        cfg = dict(cfg)
+        return self.map[cfg.pop("type")](**cfg, **kw)
+
+
+def install_stubs():
+    sys.path.insert(0, ROOT)
+    from oracle import head as ohead, transformer as otr
+
+    class ConvModule(nn.Module):                       # mmcv ConvModule: conv(bias = not norm) + BN + ReLU
+        def __init__(self, cin, cout, kernel_size, stride=1, padding=0, bias="auto", conv_cfg=None, norm_cfg=None, **kw):
+            super().__init__()
+            conv = nn.Conv1d if (conv_cfg or {}).get("type") == "Conv1d" else nn.Conv2d
+            bn = nn.BatchNorm1d if (norm_cfg or {}).get("type") == "BN1d" else nn.BatchNorm2d
+            assert norm_cfg is not None
+            self.conv = conv(cin, cout, kernel_size, stride=stride, padding=padding, bias=False)
+            self.bn = bn(cout)
+
+        def forward(self, x):
+            return torch.relu(self.bn(self.conv(x)))
+
+    def build_conv_layer(cfg, *args, **kwargs):
+        conv = nn.Conv1d if (cfg or {}).get("type") == "Conv1d" else nn.Conv2d
+        return conv(*args, **kwargs)
+
+    def build_transformer_layer_sequence(cfg):
+        cfg = dict(cfg)
+        assert cfg.pop("type") == "DeformableDetrTransformerDecoder"
+        return otr.DeformableDetrTransformerDecoder(**cfg)
+
+    def force_fp32(*a, **k):
+        return (lambda f: f)
+
+    class _Loss(nn.Module):
+        def __init__(self, **kw):
+            super().__init__()
+
+    class LiDARInstance3DBoxes:
+        def __init__(self, tensor, box_dim=7, **kw):
+            self.tensor, self.box_dim = tensor, box_dim
+
+    def rotation_3d_in_axis(points, angles, axis=0):
+        assert axis == 2
+        xy = ohead.rotation_3d_in_axis_z(points[..., :2], angles)
+        return torch.cat([xy, points[..., 2:]], dim=-1)
+
+    HEADS, NECKS, BBOX_CODERS, TRANSFORMER = _Registry(), _Registry(), _Registry(), _Registry()
+    _mod("mmcv")
+    _mod("mmcv.cnn", ConvModule=ConvModule, build_conv_layer=build_conv_layer, kaiming_init=lambda *a, **k: None,
+         Linear=nn.Linear, build_activation_layer=None, build_norm_layer=None, xavier_init=None)
+    _mod("mmcv.runner", force_fp32=force_fp32)
+    _mod("mmcv.cnn.bricks"); _mod("mmcv.cnn.bricks.transformer", build_transformer_layer_sequence=build_transformer_layer_sequence)
+    _mod("mmdet"); _mod("mmdet.core", build_bbox_coder=lambda cfg: BBOX_CODERS.build(cfg), multi_apply=None,
+                        build_assigner=None, build_sampler=None, AssignResult=None)
+    _mod("mmdet.core.bbox", BaseBBoxCoder=object)
+    _mod("mmdet.core.bbox.builder", BBOX_CODERS=BBOX_CODERS)
+    _mod("mmdet.models"); _mod("mmdet.models.utils"); _mod("mmdet.models.utils.builder", TRANSFORMER=TRANSFORMER)
+    _mod("mmdet3d"); _mod("mmdet3d.models", builder=types.SimpleNamespace())
+    _mod("mmdet3d.core", circle_nms=None, draw_heatmap_gaussian=None, gaussian_radius=None, xywhr2xyxyr=None,
+         PseudoSampler=None, LiDARInstance3DBoxes=LiDARInstance3DBoxes)
+    _mod("mmdet3d.core.bbox"); _mod("mmdet3d.core.bbox.structures")
+    _mod("mmdet3d.core.bbox.structures.utils", rotation_3d_in_axis=rotation_3d_in_axis)
+    _mod("mmdet3d.models.builder", HEADS=HEADS, NECKS=NECKS, build_loss=lambda cfg: _Loss())
+    _mod("mmdet3d.models.utils", clip_sigmoid=None)
+    _mod("mmdet3d.models.fusion_layers", apply_3d_transformation=None)
+    _mod("mmdet3d.ops"); _mod("mmdet3d.ops.iou3d"); _mod("mmdet3d.ops.iou3d.iou3d_utils", nms_gpu=None)
+    # parent packages of the reference modules, WITHOUT executing their __init__ (they import the whole plugin)
+    base = os.path.join(REF, "projects", "mmdet3d_plugin")
+    _pkg("projects", os.path.join(REF, "projects"))
+    _pkg("projects.mmdet3d_plugin", base)
+    for sub in ("models", "models/utils", "models/dense_heads", "models/necks", "core", "core/bbox", "core/bbox/coders"):
+        _pkg("projects.mmdet3d_plugin." + sub.replace("/", "."), os.path.join(base, sub))
+    _mod("projects.mmdet3d_plugin.models.utils.ops", locatt_ops=None)          # JIT CUDA extension, LC configs only
+    # the copied-from-mmdet transformer.py is star-imported by focal_decoder.py but nothing of it is used
+    _mod("projects.mmdet3d_plugin.models.utils.transformer")
+    return LiDARInstance3DBoxes
+
+
+class no_cuda_device:
+    """The reference hard-codes device='cuda' (focal_decoder.py:837-863,904): run those calls on the CPU."""
+
+    def __enter__(self):
+        self.saved = (torch.as_tensor, torch.ones)
+
+        def strip(fn):
+            def w(*a, **k):
+                if k.get("device") == "cuda":
+                    k.pop("device")
+                return fn(*a, **k)
+            return w
+        torch.as_tensor, torch.ones = strip(torch.as_tensor), strip(torch.ones)
+
+    def __exit__(self, *a):
+        torch.as_tensor, torch.ones = self.saved
+
+
+def main():
+    assert os.path.isdir(REF), "run where /root/reference exists"
+    box_cls = install_stubs()
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict
+    fd = importlib.import_module("projects.mmdet3d_plugin.models.dense_heads.focal_decoder")
+    fe = importlib.import_module("projects.mmdet3d_plugin.models.necks.focal_encoder")
+    ut = importlib.import_module("projects.mmdet3d_plugin.models.utils.utils")
+    importlib.import_module("projects.mmdet3d_plugin.core.bbox.coders.transfusion_bbox_coder")
+
+    cfg = scaled_model_cfg(load_config(default_config_path())["model"], bev=16, num_proposals=12)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(11)
+    out = {"cfg_bev": 16, "cfg_num_proposals": 12, "weights_seed": 3}
+
+    # ---- utils.py
+    pos = torch.rand(2, 7, 2, generator=g) * 1.3 - 0.1
+    out["sine_in"], out["sine_out"] = pos, ut.gen_sineembed_for_position(pos)
+
+    # ---- FocalEncoder (real) on a synthetic SECONDFPN output
+    ne = dict(cfg["imgpts_neck"]); ne.pop("type")
+    enc = fe.FocalEncoder(**ne).eval()
+    enc.load_state_dict({k[len("imgpts_neck."):]: v for k, v in sd.items() if k.startswith("imgpts_neck.")}, strict=True)
+    neck = torch.randn(2, 512, 16, 16, generator=g) * 0.3
+    with torch.no_grad():
+        _, (conv_feat, stage_list) = enc(None, neck, [dict(), dict()])
+    out["enc_in"], out["enc_conv_feat"], out["enc_stage_feats"] = neck, conv_feat, [t.clone() for t in stage_list]
+
+    # ---- FocalDecoder (real): forward (B=2) and forward + get_bboxes (B=1, the reference asserts bs == 1)
+    hd = dict(cfg["pts_bbox_head"]); hd.pop("type")
+    head = fd.FocalDecoder(**hd, test_cfg=dict(cfg["test_cfg"]["pts"])).eval()
+    head.load_state_dict({k[len("pts_bbox_head."):]: v for k, v in sd.items() if k.startswith("pts_bbox_head.")}, strict=True)
+    for B, tag in ((2, "b2"), (1, "b1")):
+        feats = [torch.randn(B, 128, 16, 16, generator=g) * 0.5 for _ in range(3)]      # conv_feat, stage feat, extra
+        with torch.no_grad(), no_cuda_device():
+            res = head([feats[0].clone(), [feats[1].clone(), feats[2].clone()]], None, [dict()] * B)
+            r = res[0][0]
+            out[f"head_{tag}_in"] = feats
+            out[f"head_{tag}_out"] = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v])
+                                      for k, v in r.items() if k != "multistage_masks"}
+            out[f"head_{tag}_query_labels"] = head.query_labels.clone()
+            if B == 1:
+                boxes, scores, labels = head.get_bboxes(res, [dict(box_type_3d=box_cls)])[0]
+                out["bboxes_b1"] = dict(boxes=boxes.tensor.clone(), scores=scores.clone(), labels=labels.clone())
+    torch.save(out, os.path.join(OUT, "focalformer3d_l_intree.pt"))
+    n = sum(t.numel() for t in _tensors(out))
+    print(f"wrote {os.path.join(OUT, 'focalformer3d_l_intree.pt')} ({n} values)")
+
+
+def _tensors(o):
+    if torch.is_tensor(o):
+        yield o
+    elif isinstance(o, dict):
+        for v in o.values():
+            yield from _tensors(v)
+    elif isinstance(o, (list, tuple)):
+        for v in o:
+            yield from _tensors(v)
+
+
+if __name__ == "__main__":
+    main()
