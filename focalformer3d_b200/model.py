@@ -424,8 +424,12 @@ class FocalDecoder(ParamTree):
 
         def heat(name):
             s, b = bn_scale_shift(sd, f"{name}.0.bn", 1e-5)
+            w2 = sd[f"{name}.1.weight"]
+            co = (w2.shape[0] + 15) // 16 * 16        # zero-pad cout (10 -> 16) so the conv tiles on the tensor cores
+            w2p = torch.zeros((co,) + tuple(w2.shape[1:]), dtype=w2.dtype)
+            w2p[:w2.shape[0]] = w2
             return (pack_conv2d(sd[f"{name}.0.conv.weight"], s, dev), vec(b, dev),
-                    pack_conv2d(sd[f"{name}.1.weight"], None, dev), vec(sd[f"{name}.1.bias"], dev))
+                    pack_conv2d(w2p, None, dev), vec(sd[f"{name}.1.bias"], dev, co))
         pk["heat"] = []
         for i in range(self.stages):
             pk["heat"].append(heat("heatmap_head") if (i == 0 and self.reuse_first) else heat(f"heatmap_head_img.{i}"))
@@ -534,8 +538,8 @@ class FocalDecoder(ParamTree):
             w1, b1, w2, b2 = pk["heat"][s]
             t = torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
             ops.conv2d(feats[s], w1, b1, t, 3, act=ACT_RELU)
-            logits = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)
-            ops.conv2d(t, w2, b2, logits[..., :nc], 3, act=ACT_NONE)
+            logits = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)   # padded channels = 0
+            ops.conv2d(t, w2, b2, logits, 3, act=ACT_NONE)
             nms_heat = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
             top = torch.empty((B, k), dtype=torch.int32, device=dev)
             ops.hip_stage(logits, acc_mask, nms_heat, feats[s], pk["cls_w"], pk["cls_b"], k, self.nms_kernel_size,
