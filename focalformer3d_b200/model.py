@@ -85,7 +85,7 @@ def pack_linear(w, scale=None, dev="cuda"):
 
 
 def vec(v, dev, n=None):
-    v = v.float()
+    v = v.detach().float().cpu()
     if n is not None and v.numel() < n:
         v = torch.cat([v, torch.zeros(n - v.numel())])
     return v.contiguous().to(dev)
@@ -427,7 +427,7 @@ class FocalDecoder(ParamTree):
             w2 = sd[f"{name}.1.weight"]
             co = (w2.shape[0] + 15) // 16 * 16        # zero-pad cout (10 -> 16) so the conv tiles on the tensor cores
             w2p = torch.zeros((co,) + tuple(w2.shape[1:]), dtype=w2.dtype)
-            w2p[:w2.shape[0]] = w2
+            w2p[:w2.shape[0]] = w2.detach().cpu()
             return (pack_conv2d(sd[f"{name}.0.conv.weight"], s, dev), vec(b, dev),
                     pack_conv2d(w2p, None, dev), vec(sd[f"{name}.1.bias"], dev, co))
         pk["heat"] = []

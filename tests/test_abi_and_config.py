@@ -99,3 +99,17 @@ def test_model_builds_and_loads_state_dict_on_cpu(tiny_cfg, tiny_sd):
     assert set(model.state_dict()) == set(tiny_sd)
     with pytest.raises(RuntimeError):
         model.forward_raw([torch.zeros(4, 5)])                 # not prepared / no device: must fail loudly
+
+
+def test_weight_packing_runs_without_a_gpu(tiny_cfg, tiny_sd):
+    """prepare() folds BN and builds both weight layouts (SIMT [taps,cin,cout] and tcgen05 hi/lo images) on the host."""
+    _ensure_built()
+    from focalformer3d_b200.model import build_model
+    model = build_model(tiny_cfg)
+    model.load_state_dict(tiny_sd, strict=True)
+    model.prepare("cpu")
+    w = model.pts_bbox_head.pk["heat"][0][2]                 # 128 -> 10 heatmap conv, padded to 16 for the tensor cores
+    assert tuple(w.shape) == (9, 128, 16) and w.img is not None and tuple(w.img.shape) == (1, 36, 2, 16, 32)
+    hi, lo = w.img[0, :, 0], w.img[0, :, 1]
+    assert (hi.view(torch.int32) & 0x1FFF).abs().sum() == 0                      # hi parts are exact TF32 values
+    assert (lo.abs() <= hi.abs() * 2 ** -10 + 1e-30).all()
