@@ -215,6 +215,30 @@ __global__ void vox_gather_kernel(const float* __restrict__ pts, const int* __re
   }
 }
 
+// HardVFE (single VFELayer, max-pool): out[v, c] = max_k relu( sum_f x[v,k,f] * w[f,c] + b[c] ) over ALL max_points
+// slots, padded slots contributing relu(b[c]) (their features are masked to zero first) -- [upstream] mmdet3d v0.17.1
+// HardVFE/VFELayer as configured at projects/configs/focalformer3d/FocalFormer3D_Waymo_L.py:141-152.  BN folded into w, b.
+__global__ void vfe_hard_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points,
+                                const int* __restrict__ n_dev, int P, int F, const float* __restrict__ w,
+                                const float* __restrict__ b, float* __restrict__ out, int ldo, int C) {
+  long long total = (long long)(*n_dev) * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int v = (int)(e / C), c = (int)(e - (long long)v * C);
+    int np = num_points[v];
+    float bias = b[c];
+    float m = -INFINITY;
+    for (int k = 0; k < P; ++k) {
+      float a = bias;
+      if (k < np) {
+        const float* x = voxels + ((size_t)v * P + k) * F;
+        for (int f = 0; f < F; ++f) a = fmaf(x[f], w[f * C + c], a);
+      }
+      m = fmaxf(m, fmaxf(a, 0.f));
+    }
+    out[(size_t)v * ldo + c] = m;
+  }
+}
+
 static int next_pow2(long long v) {
   long long p = 1;
   while (p < v) p <<= 1;
@@ -303,4 +327,16 @@ extern "C" int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, 
   vox_gather_kernel<<<cdiv((long long)batch * max_voxels, 128), 128, 0, st>>>(points, slots, n_voxels_dev, p, voxels,
                                                                              num_points, mean_feats, mean_ld);
   return check_launch("ff3d_voxelize_hard");
+}
+
+extern "C" int ff3d_vfe_hard(const float* voxels, const int* num_points, const int* n_voxels_dev, int cap,
+                             int max_points, int n_feat, const float* w, const float* b, float* out, int ldo, int C,
+                             ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(voxels && num_points && n_voxels_dev && w && b && out && ldo >= C, "vfe_hard: bad arguments");
+  long long work = (long long)cap * C;
+  long long nb = (work + 255) / 256, lim = (long long)num_sms() * 32;
+  vfe_hard_kernel<<<(int)(nb < 1 ? 1 : (nb > lim ? lim : nb)), 256, 0, as_stream(stream)>>>(
+      voxels, num_points, n_voxels_dev, max_points, n_feat, w, b, out, ldo, C);
+  return check_launch("ff3d_vfe_hard");
 }

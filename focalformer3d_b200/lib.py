@@ -42,6 +42,7 @@ SIGNATURES = {
     "ff3d_version": (_I, []),
     "ff3d_voxelize_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "ff3d_voxelize_hard": (_I, [_P, _I, _I, _IP, _I, _FP, _FP, _I, _I, _P, _P, _P, _P, _I, _P, _P, _SZ, _P]),
+    "ff3d_vfe_hard": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "ff3d_sp_hash_build": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "ff3d_sp_subm_map": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "ff3d_sp_down_build": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P, _I, _I, _I, _I, _P, _P,

@@ -96,9 +96,34 @@ def vec(v, dev, n=None):
 class HardSimpleVFE(ParamTree):
     """[upstream] mmdet3d HardSimpleVFE: the mean is fused into ff3d_voxelize_hard (mean_feats output)."""
 
-    def __init__(self, num_features=4, **kw):
+    def __init__(self, num_features=4, spec=None, **kw):
         super().__init__()
         self.num_features = num_features
+
+
+@VOXEL_ENCODERS.register_module()
+class HardVFE(ParamTree):
+    """[upstream] mmdet3d v0.17.1 HardVFE as configured by the Waymo configs (FocalFormer3D_Waymo_L.py:141-152):
+    no distance / cluster-centre / voxel-centre features, one VFELayer (Linear no-bias + BN1d + ReLU), max over points."""
+
+    def __init__(self, in_channels=4, feat_channels=(), with_distance=False, with_cluster_center=False,
+                 with_voxel_center=False, norm_cfg=None, spec=None, **kw):
+        super().__init__()
+        if with_distance or with_cluster_center or with_voxel_center or len(feat_channels) != 1:
+            raise NotImplementedError("HardVFE: only the shipped single-layer, raw-feature variant is built")
+        self.in_channels, self.out_channels = in_channels, feat_channels[0]
+        self.eps = (norm_cfg or {}).get("eps", 1e-3)
+        self.build_params(spec)
+        self.pk = None
+
+    def prepare(self, dev):
+        sd = self.flat()
+        s, b = bn_scale_shift(sd, "vfe_layers.0.norm", self.eps)
+        w = sd["vfe_layers.0.linear.weight"].double() * s.view(-1, 1)            # [C, F]
+        self.pk = (w.t().contiguous().float().to(dev), vec(b, dev))
+
+    def forward(self, vox, max_points):
+        return ops.vfe_hard(vox, self.pk[0], self.pk[1], self.out_channels, max_points, self.in_channels)
 
 
 @MIDDLE_ENCODERS.register_module()
@@ -655,7 +680,7 @@ class FocalFormer3D(nn.Module):
                    imgpts_neck=imgpts_neck, pts_bbox_head=pts_bbox_head, test_cfg=test_cfg)
         spec = param_spec(cfg)
         self.voxel_cfg = dict(pts_voxel_layer)
-        self.pts_voxel_encoder = VOXEL_ENCODERS.build(pts_voxel_encoder)
+        self.pts_voxel_encoder = VOXEL_ENCODERS.build(pts_voxel_encoder, spec=sub_spec(spec, "pts_voxel_encoder"))
         self.pts_middle_encoder = MIDDLE_ENCODERS.build(pts_middle_encoder, spec=sub_spec(spec, "pts_middle_encoder"))
         depth = self._bev_depth(self.pts_middle_encoder)
         self.pts_backbone = BACKBONES.build(pts_backbone, spec=sub_spec(spec, "pts_backbone"), in_depth=depth)
@@ -677,8 +702,10 @@ class FocalFormer3D(nn.Module):
     def prepare(self, device="cuda"):
         """Fold BatchNorm, pack weights into kernel layouts on the device (call after load_state_dict)."""
         dev = torch.device(device)
-        for m in (self.pts_middle_encoder, self.pts_backbone, self.pts_neck, self.imgpts_neck, self.pts_bbox_head):
-            m.prepare(dev)
+        for m in (self.pts_voxel_encoder, self.pts_middle_encoder, self.pts_backbone, self.pts_neck, self.imgpts_neck,
+                  self.pts_bbox_head):
+            if hasattr(m, "prepare"):
+                m.prepare(dev)
         self._prepared_on = dev
         return self
 
@@ -699,8 +726,11 @@ class FocalFormer3D(nn.Module):
         mv = mv[1] if isinstance(mv, (tuple, list)) else mv
         mv = min(mv, max(int(p.shape[0]) for p in points))
         ops.mark("start")
+        hard_vfe = isinstance(self.pts_voxel_encoder, HardVFE)
         vox = ops.voxelize(allp, offs, vc["voxel_size"], vc["point_cloud_range"], vc["max_num_points"], mv,
-                           mean_ld=_pad4(max(self.pts_middle_encoder.in_channels, 8)), want_voxels=keep_stages)
+                           mean_ld=8, want_voxels=keep_stages or hard_vfe)
+        if hard_vfe:
+            vox["mean"] = self.pts_voxel_encoder(vox, vc["max_num_points"])      # [cap, 64] learned voxel features
         ops.mark("voxelize+vfe")
         me = self.pts_middle_encoder
         depth = self._bev_depth(me)

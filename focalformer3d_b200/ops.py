@@ -281,6 +281,16 @@ def voxelize(points, batch_offsets, voxel_size, pc_range, max_points, max_voxels
     return dict(coors=coors, num_points=nump, mean=mean, n_dev=n_dev, voxels=voxels)
 
 
+def vfe_hard(vox, w, b, Cout, max_points, n_feat):
+    """HardVFE: vox = dict from voxelize(want_voxels=True); returns [cap, Cout] voxel features."""
+    cap = vox["coors"].shape[0]
+    out = torch.empty((cap, Cout), dtype=torch.float32, device=vox["coors"].device)
+    check(lib.ff3d_vfe_hard(_ptr(vox["voxels"]), _ptr(vox["num_points"]), _ptr(vox["n_dev"]), cap, max_points, n_feat,
+                            _ptr(w), _ptr(b), _ptr(out), Cout, Cout, _stream()), "ff3d_vfe_hard")
+    _count()
+    return out
+
+
 def next_pow2(v):
     p = 1
     while p < v:

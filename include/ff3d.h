@@ -57,6 +57,13 @@ int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, const int* 
                        float* voxels, int* coors, int* num_points, float* mean_feats, int mean_ld,
                        int* n_voxels_dev, void* workspace, size_t workspace_bytes, ff3d_stream_t stream);
 
+/* HardVFE with one VFELayer and max pooling (Waymo configs): out[v,c] = max over all max_points slots of
+ * relu(x[v,k,:] . w[:,c] + b[c]); padded slots are masked to zero first and therefore contribute relu(b[c]).
+ * Replaces: [upstream] mmdet3d HardVFE / VFELayer at focalformer3d.py:166 (cfg FocalFormer3D_Waymo_L.py:141-152).
+ * voxels [cap, max_points, n_feat], w [n_feat, C] and b [C] with BatchNorm1d(eval) folded in, out [cap, ldo]. */
+int ff3d_vfe_hard(const float* voxels, const int* num_points, const int* n_voxels_dev, int cap, int max_points,
+                  int n_feat, const float* w, const float* b, float* out, int ldo, int C, ff3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sparse-conv rulebooks (output-stationary neighbour maps).
  * Replaces: [upstream] mmdet3d.ops.spconv get_indice_pairs (indice_cuda.cu) as used by every

@@ -77,6 +77,15 @@ def test_unmodified_reference_configs_load():
         assert rh[k] == v, k
     assert dict(ref.model.test_cfg.pts) == dict(mine.model.test_cfg.pts)
     assert set(param_spec(ref.model)) == set(param_spec(mine.model))
+    # Waymo: our config mirrors the shipped one on every key the forward path reads
+    refw = load_config(os.path.join(REF_CFG_DIR, "FocalFormer3D_Waymo_L.py"))
+    minew = load_config(os.path.join(ROOT, "configs", "focalformer3d_waymo_l.py"))
+    for part in ("pts_voxel_layer", "pts_voxel_encoder", "pts_middle_encoder", "pts_backbone", "pts_neck", "imgpts_neck"):
+        assert dict(refw.model[part]) == dict(minew.model[part]), part
+    for k, v in dict(minew.model.pts_bbox_head).items():
+        assert dict(refw.model.pts_bbox_head)[k] == v, k
+    assert dict(refw.model.test_cfg.pts) == dict(minew.model.test_cfg.pts)
+    assert "pts_voxel_encoder.vfe_layers.0.linear.weight" in param_spec(refw.model)
     for name in sorted(os.listdir(REF_CFG_DIR)):
         c = load_config(os.path.join(REF_CFG_DIR, name))
         assert c.model.type in ("FocalFormer3D",), name

@@ -55,6 +55,31 @@ def test_voxelize_matches_oracle(ops, max_voxels, max_points):
     assert n_dev[0] == base
 
 
+def test_hard_vfe_matches_oracle(ops):
+    from oracle.voxelize import HardVFE
+    from focalformer3d_b200.model import bn_scale_shift
+    rng = np.random.default_rng(3)
+    p = rng.uniform(-3.9, 3.9, (5000, 5)).astype(np.float32)
+    p[:, 2] = rng.uniform(-0.9, 0.9, 5000)
+    vox = ops.voxelize(torch.from_numpy(p).cuda(), [0, 5000], [0.25, 0.25, 0.5], [-4.0, -4.0, -1.0, 4.0, 4.0, 1.0], 5, 4000,
+                       want_voxels=True)
+    n = int(vox["n_dev"][0].item())
+    torch.manual_seed(0)
+    vfe = HardVFE(5, (64,)).eval()
+    for prm in vfe.parameters():
+        torch.nn.init.normal_(prm, std=0.5)
+    vfe.vfe_layers[0].norm.running_mean.normal_(0, 0.3)
+    vfe.vfe_layers[0].norm.running_var.uniform_(0.5, 1.5)
+    with torch.no_grad():
+        want = vfe(vox["voxels"][:n].cpu(), vox["num_points"][:n].cpu())
+    sd = {k: v.detach() for k, v in vfe.state_dict().items()}
+    s, b = bn_scale_shift(sd, "vfe_layers.0.norm", 1e-3)
+    w = (sd["vfe_layers.0.linear.weight"].double() * s.view(-1, 1)).t().contiguous().float().cuda()
+    got = ops.vfe_hard(vox, w, b.float().cuda(), 64, 5, 5)[:n].cpu()
+    assert (vox["num_points"][:n] < 5).any() and (vox["num_points"][:n] == 5).any()   # padded and full voxels
+    assert (got - want).abs().max().item() < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ implicit GEMM
 @pytest.mark.parametrize("M,K,N,act", [(300, 128, 128, 1), (257, 256, 20, 0), (1000, 1024, 128, 0), (64, 8, 16, 2),
                                        (130, 384, 288, 0)])
