@@ -154,16 +154,22 @@ __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" 
 // G = number of 128-thread A-producer groups = number of smem slots: 2 (and two CTAs per SM) for BN <= 64, 3 for
 // BN = 128 (one CTA per SM).  n_slots == G makes every group the sole owner of one slot, so a producer is never more
 // than one mbarrier phase ahead of the MMA issuer (the parity wait cannot tell phases two apart).
-template <int MODE, int BN, int G>
+// MT = 128-row sub-tiles per CTA tile.  MT = 2 (BN = 128, large M) halves the weight bytes streamed from L2 per
+// flop -- with 3xTF32 the B images (hi + lo) are the larger half of the L2 -> SM traffic and these layers are
+// L2-bandwidth bound -- at the price of single-buffered accumulators (TMEM: 2 sub-tiles x (main|cross) x 128 = 512).
+template <int MODE, int BN, int G, int MT>
 __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
   constexpr int NPROD = 128 * G;
+  constexpr int TM = TC_BM * MT;                                 // rows per CTA tile
+  constexpr bool DEFER = MT == 1;                                // double-buffered accumulators -> deferred epilogue
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
   constexpr uint32_t A_BYTES = TC_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
-  constexpr uint32_t SLOT_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr int ACC_COLS = 2 * BN;                               // main | cross-term accumulator
-  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // double buffered across tiles
+  constexpr uint32_t SLOT_BYTES = MT * 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int ACC_COLS = MT * 2 * BN;                          // per sub-tile: main | cross-term accumulator
+  constexpr int NBUF = DEFER ? 2 : 1;
+  constexpr int TMEM_COLS = NBUF * ACC_COLS < 32 ? 32 : NBUF * ACC_COLS;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_slots * SLOT_BYTES);
   uint64_t* empty_bar = full_bar + n_slots;
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   int Mv = p.M;
   if (p.m_dev) { int md = *p.m_dev; Mv = md < Mv ? md : Mv; }
   const int n_tiles_n = p.cout / BN;
-  const int total_tiles = ((Mv + TC_BM - 1) / TC_BM) * n_tiles_n;
+  const int total_tiles = ((Mv + TM - 1) / TM) * n_tiles_n;
   if ((int)blockIdx.x >= total_tiles) return;   // uniform for the whole CTA, before any barrier / TMEM use
 
   if (tid == 0) {
@@ -214,12 +220,14 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
     Ring ring{grp % n_slots, (uint32_t)((grp / n_slots) & 1)};
 
     auto epilogue = [&](int tile, int it) {
-      const int m0 = (tile / n_tiles_n) * TC_BM;
+      const int m0 = (tile / n_tiles_n) * TM;
       const int n0 = (tile - (tile / n_tiles_n) * n_tiles_n) * BN;
-      const int ab = it & 1;
-      mbar_wait(&tfull_bar[ab], (uint32_t)((it >> 1) & 1));
+      const int ab = DEFER ? (it & 1) : 0;
+      mbar_wait(&tfull_bar[ab], (uint32_t)(DEFER ? ((it >> 1) & 1) : (it & 1)));
       tc_fence_after();
-      const int m = m0 + r;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m = m0 + mt * TC_BM + r;
       const bool rvalid = m < Mv;
       float* yp = nullptr;
       if (rvalid) {
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
           yp = p.y + (long long)m * p.ldy;
         }
       }
-      const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS);
+      const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS + mt * 2 * BN);
 #pragma unroll 1
       for (int c0 = grp * 16; c0 < BN; c0 += 16 * G) {       // 16-column chunks dealt round-robin to the groups
         float v[16], v2[16];
@@ -262,24 +270,25 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
           }
         }
       }
+      }   // mt
       tc_fence_before();
       mbar_arrive(&tempty_bar[ab]);                          // NPROD arrivals free the accumulator buffer
     };
 
     int it = 0, prev_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / n_tiles_n) * TC_BM;
+      const int m0 = (tile / n_tiles_n) * TM;
       // ---- per-tile gather metadata (both groups are past the previous tile's stages after the first barrier)
       producer_bar<NPROD>();
       if (MODE == FF3D_GEMM_SPARSE) {
-        for (int i = ptid; i < p.taps * TC_BM; i += NPROD) {
-          int t = i >> 7, rr = i & 127;
+        for (int i = ptid; i < p.taps * TM; i += NPROD) {
+          int t = i / TM, rr = i - t * TM;
           int v = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
           aux_s[i] = v < 0 ? -1 : v * p.ldx;                 // element offset of the source row
         }
       } else if (MODE == FF3D_GEMM_CONV2D) {
-        if (ptid < TC_BM) {
-          int mm = m0 + ptid;
+        for (int rr0 = ptid; rr0 < TM; rr0 += NPROD) {
+          int mm = m0 + rr0;
           int4 info = make_int4(0, 0, 0, 0);
           if (mm < Mv) {
             int hw = p.Ho * p.Wo;
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
             int oy = rr / p.Wo, ox = rr - (rr / p.Wo) * p.Wo;
             info = make_int4((int)(b * p.x_bstride), oy * p.stride - p.pad, ox * p.stride - p.pad, 1);
           }
-          reinterpret_cast<int4*>(aux_s)[ptid] = info;
+          reinterpret_cast<int4*>(aux_s)[rr0] = info;
         }
       }
       producer_bar<NPROD>();
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
           if (!info.w || iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
           return ((long long)info.x + (long long)iy * p.W + ix) * p.ldx;
         }
-        return (long long)aux_s[t * TC_BM + row];
+        return (long long)aux_s[t * TM + row];
       };
       // my stages of this tile: global stage index (it * n_stages + s) has my parity
       int s = (grp - it * n_stages) % G;                      // first stage of this tile with (it*n_stages + s) % G == grp
@@ -314,10 +323,10 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         if (p.cin >= 32) { tap = t; coff = cidx * 32 + lane_coff; }
         else { tap = s * p.tps + lane_tap; coff = lane_coff; }
         if (MODE == FF3D_GEMM_CONV2D) { ky = tap / p.kw; kx = tap - ky * p.kw; }
-        float4 v[8];
+        float4 v[8 * MT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = pw * 32 + i * 4 + q;
+        for (int i = 0; i < 8 * MT; ++i) {
+          const int row = (i >> 3) * TC_BM + pw * 32 + (i & 7) * 4 + q;   // sub-tile (i >> 3), row inside it
           const long long so = src_off(row, tap, ky, kx);
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (so >= 0) {
@@ -329,11 +338,12 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
           }
         }
         mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
-        uint8_t* a_hi = smem + (size_t)ring.slot * SLOT_BYTES;
-        uint8_t* a_lo = a_hi + A_BYTES;
+        uint8_t* slot_base = smem + (size_t)ring.slot * SLOT_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = pw * 32 + i * 4 + q;
+        for (int i = 0; i < 8 * MT; ++i) {
+          const int row = pw * 32 + (i & 7) * 4 + q;
+          uint8_t* a_hi = slot_base + (size_t)(i >> 3) * (2 * A_BYTES);
+          uint8_t* a_lo = a_hi + A_BYTES;
           float4 h, l;
           split_tf32(v[i].x, h.x, l.x);
           split_tf32(v[i].y, h.y, l.y);
@@ -350,10 +360,14 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       }
       // epilogue of the PREVIOUS tile: its MMAs have had a whole tile's worth of gathers to finish, and the
       // tensor core keeps working on this tile out of the other TMEM accumulator buffer meanwhile
-      if (prev_tile >= 0) epilogue(prev_tile, it - 1);
-      prev_tile = tile;
+      if (DEFER) {
+        if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+        prev_tile = tile;
+      } else {
+        epilogue(tile, it);                                  // single-buffered accumulators (MT = 2)
+      }
     }
-    if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+    if (DEFER && prev_tile >= 0) epilogue(prev_tile, it - 1);
   } else if (warp == 4 * G) {
     // =========================== B producer ===========================
     if (lane == 0) {
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
         for (int s = 0; s < n_stages; ++s) {
           mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
-          uint8_t* b_hi = smem + (size_t)ring.slot * SLOT_BYTES + 2 * A_BYTES;
+          uint8_t* b_hi = smem + (size_t)ring.slot * SLOT_BYTES + MT * 2 * A_BYTES;
           mbar_arrive_expect_tx(&full_bar[ring.slot], 2 * B_BYTES);
           bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, &full_bar[ring.slot]);
           ring.advance(1, n_slots);
@@ -377,26 +391,30 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       Ring ring{0, 0u};
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int ab = it & 1;
-        mbar_wait(&tempty_bar[ab], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue of tile it-2 drained this buffer
+        const int ab = DEFER ? (it & 1) : 0;
+        // the epilogue that last read this accumulator buffer (tile it-2, or it-1 when single-buffered) has drained it
+        mbar_wait(&tempty_bar[ab], (uint32_t)((DEFER ? ((it >> 1) & 1) : (it & 1)) ^ 1));
         tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(ab * ACC_COLS);
-        const uint32_t d_cross = d_main + BN;
+        const uint32_t d_base = tmem_base + (uint32_t)(ab * ACC_COLS);
         for (int s = 0; s < n_stages; ++s) {
           mbar_wait(&full_bar[ring.slot], ring.phase);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + (size_t)ring.slot * SLOT_BYTES);
-          const uint32_t a_lo = a_hi + A_BYTES;
-          const uint32_t b_hi = a_lo + A_BYTES;
+          const uint32_t slot_a = smem_u32(smem + (size_t)ring.slot * SLOT_BYTES);
+          const uint32_t b_hi = slot_a + MT * 2 * A_BYTES;
           const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
-            const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
             const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
             const uint32_t acc = (s | k) ? 1u : 0u;
-            umma_tf32(d_cross, dal, dbh, idesc, acc);
-            umma_tf32(d_cross, dah, dbl, idesc, 1u);
-            umma_tf32(d_main, dah, dbh, idesc, acc);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t a_hi = slot_a + mt * 2 * A_BYTES, a_lo = a_hi + A_BYTES;
+              const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
+              const uint32_t d_main = d_base + (uint32_t)(mt * 2 * BN), d_cross = d_main + BN;
+              umma_tf32(d_cross, dal, dbh, idesc, acc);
+              umma_tf32(d_cross, dah, dbl, idesc, 1u);
+              umma_tf32(d_main, dah, dbh, idesc, acc);
+            }
           }
           umma_commit(&empty_bar[ring.slot]);   // frees the smem slot once these MMAs have read it
           ring.advance(1, n_slots);
@@ -413,25 +431,36 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   }
 }
 
-template <int MODE, int BN>
-static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
-  constexpr int G = BN == 128 ? 3 : 2;
-  constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
+template <int MODE, int BN, int G, int MT>
+static int launch_tc_cfg(const TcP& p, int n_tiles_n, cudaStream_t st) {
+  constexpr size_t SLOT_BYTES = (size_t)MT * 2 * TC_BM * 128 + 2 * (size_t)BN * 128;
+  constexpr int TM = TC_BM * MT;
   const int n_slots = G;                                // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 4) * sizeof(uint64_t) + 32 +
-                (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TC_BM * sizeof(int)
-                                          : (MODE == FF3D_GEMM_CONV2D ? (size_t)TC_BM * 16 : 0)) + 1024;
+                (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TM * sizeof(int)
+                                          : (MODE == FF3D_GEMM_CONV2D ? (size_t)TM * 16 : 0)) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tcgemm_kernel<MODE, BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tcgemm_kernel<MODE, BN, G, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   // persistent CTAs: one (BN = 128) or two (BN <= 64) per SM, each looping over output tiles
-  long long tiles = (long long)cdiv(p.M, TC_BM) * n_tiles_n;
+  long long tiles = (long long)cdiv(p.M, TM) * n_tiles_n;
   long long resident = (long long)num_sms() * (BN <= 64 ? 2 : 1);
   dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-  tcgemm_kernel<MODE, BN, G><<<grid, 128 * G + 64, smem, st>>>(p, n_slots);
+  tcgemm_kernel<MODE, BN, G, MT><<<grid, 128 * G + 64, smem, st>>>(p, n_slots);
   return check_launch("ff3d_tcgemm");
+}
+
+template <int MODE, int BN>
+static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
+  if constexpr (BN == 128) {
+    // enough 256-row tiles to fill the machine -> share each weight stage between two row sub-tiles
+    if ((long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms()) return launch_tc_cfg<MODE, BN, 2, 2>(p, n_tiles_n, st);
+    return launch_tc_cfg<MODE, BN, 3, 1>(p, n_tiles_n, st);
+  } else {
+    return launch_tc_cfg<MODE, BN, 2, 1>(p, n_tiles_n, st);
+  }
 }
 
 template <int MODE>

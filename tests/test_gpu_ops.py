@@ -99,7 +99,8 @@ def test_linear(ops, M, K, N, act):
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,H,W", [(16, 24, 3, 1, 13, 11), (32, 64, 3, 2, 12, 12), (32, 64, 3, 2, 11, 9),
-                                                   (64, 10, 3, 1, 9, 9), (256, 128, 1, 1, 7, 5), (128, 128, 3, 1, 20, 20)])
+                                                   (64, 10, 3, 1, 9, 9), (256, 128, 1, 1, 7, 5), (128, 128, 3, 1, 20, 20),
+                                                   (32, 128, 3, 1, 140, 141), (32, 256, 3, 2, 200, 200)])
 def test_conv2d_nhwc(ops, cin, cout, k, stride, H, W):
     g = torch.Generator().manual_seed(cin + cout + k)
     B = 2
@@ -223,6 +224,25 @@ def test_sparse_conv_matches_oracle(ops, k, s, p):
         occ_w = _to_dense(torch.ones(no, 1), ref.indices, no, ref.spatial_shape, B)
         assert torch.equal(occ_g, occ_w)                                         # identical active sites
     assert (got - want).abs().max().item() < 2e-4
+
+
+def test_sparse_conv_many_tiles_256_row_path(ops):
+    """Enough rows that the BN=128 kernel takes its 256-rows-per-CTA (MT=2) persistent path, SubM 32 -> 128."""
+    from oracle import sparse as osp
+    from focalformer3d_b200.model import pack_taps
+    B, shape, n, Ci, Co = 2, (9, 90, 90), 42000, 32, 128
+    idx, feat = _rand_level(B, shape, n, Ci, 21)
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    lvl = ops.SparseLevel(idx.cuda(), n_dev, n, B, shape)
+    lvl.build_hash()
+    wt = torch.randn(3, 3, 3, Ci, Co, generator=torch.Generator().manual_seed(5)) / 12
+    oconv = osp.SpConv3d(Ci, Co, 3, 1, 1, subm=True)
+    oconv.weight.data.copy_(wt)
+    with torch.no_grad():
+        ref = oconv(osp.SparseTensor(feat, idx, shape, B))
+    out = torch.zeros((n, Co), device="cuda")
+    ops.sparse_conv(feat.cuda(), lvl.subm_map(), lvl.n_dev, pack_taps(wt.reshape(-1, Ci, Co), "cuda"), None, out, act=0)
+    assert (out.cpu() - ref.features).abs().max().item() < 1e-4
 
 
 def test_sparse_to_bev_scatter(ops):
