@@ -66,6 +66,7 @@ __global__ void hip_nms_kernel(const float* __restrict__ heat, float* __restrict
 
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_MAXK = 1024;
+constexpr int SEL_CAP = 16384;   // contenders staged in dynamic shared memory (128 KB)
 
 __global__ void __launch_bounds__(SEL_THREADS) hip_select_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, const float* __restrict__ nms_heat,
@@ -90,15 +91,53 @@ __global__ void __launch_bounds__(SEL_THREADS) hip_select_kernel(
   __syncthreads();
 
   if (n > k) {
-    // exact k-th largest key by MSB-first radix select, 8 bits per pass
-    for (int pass = 0; pass < 8; ++pass) {
+    // exact k-th largest key by MSB-first radix select, 8 bits per pass.  Pass 0 reads the global candidate list;
+    // the contenders (keys sharing the winning top byte, typically a few thousand) are then staged in shared memory
+    // so passes 1..7 never touch global memory again; keys above the winning byte are selected on the spot.
+    extern __shared__ unsigned long long cont[];        // [SEL_CAP]
+    __shared__ int s_ncont;
+    for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+    if (tid == 0) s_ncont = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&hist[(int)(keys[i] >> 56)], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining, d = 255;
+      for (; d > 0; --d) {
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+      }
+      s_remaining = rem;
+      s_prefix = (unsigned long long)d << 56;
+    }
+    __syncthreads();
+    const int d0 = (int)(s_prefix >> 56);
+    const int ncont_total = hist[d0];
+    const bool staged = ncont_total <= SEL_CAP;
+    __syncthreads();
+    if (staged) {
+      for (int i = tid; i < n; i += SEL_THREADS) {
+        unsigned long long key = keys[i];
+        int d = (int)(key >> 56);
+        if (d > d0) {
+          int sidx = atomicAdd(&s_count, 1);
+          if (sidx < SEL_MAXK) sel[sidx] = key;
+        } else if (d == d0) {
+          cont[atomicAdd(&s_ncont, 1)] = key;
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned long long* src = staged ? cont : keys;
+    const int nsrc = staged ? ncont_total : n;
+    for (int pass = 1; pass < 8; ++pass) {
       int shift = 56 - 8 * pass;
       for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
       __syncthreads();
       unsigned long long prefix = s_prefix;
-      unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-      for (int i = tid; i < n; i += SEL_THREADS) {
-        unsigned long long key = keys[i];
+      unsigned long long himask = ~0ull << (shift + 8);
+      for (int i = tid; i < nsrc; i += SEL_THREADS) {
+        unsigned long long key = src[i];
         if ((key & himask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xFF)], 1);
       }
       __syncthreads();
@@ -115,11 +154,21 @@ __global__ void __launch_bounds__(SEL_THREADS) hip_select_kernel(
       __syncthreads();
     }
     unsigned long long thr = s_prefix;  // the k-th largest key (keys are unique)
-    for (int i = tid; i < n; i += SEL_THREADS) {
-      unsigned long long key = keys[i];
-      if (key >= thr) {
-        int s = atomicAdd(&s_count, 1);
-        if (s < SEL_MAXK) sel[s] = key;
+    if (staged) {
+      for (int i = tid; i < nsrc; i += SEL_THREADS) {
+        unsigned long long key = src[i];
+        if (key >= thr) {
+          int sidx = atomicAdd(&s_count, 1);
+          if (sidx < SEL_MAXK) sel[sidx] = key;
+        }
+      }
+    } else {
+      for (int i = tid; i < n; i += SEL_THREADS) {
+        unsigned long long key = keys[i];
+        if (key >= thr) {
+          int sidx = atomicAdd(&s_count, 1);
+          if (sidx < SEL_MAXK) sel[sidx] = key;
+        }
       }
     }
     __syncthreads();
@@ -245,7 +294,12 @@ extern "C" int ff3d_hip_stage(const float* logits, int ldl, float* acc_mask, flo
   if (nb > cap) nb = cap;
   hip_heat_kernel<<<nb, 256, 0, st>>>(logits, ldl, acc_mask, heat, p);
   hip_nms_kernel<<<nb, 256, 0, st>>>(heat, nms_heat, cand, cnt, p);
-  hip_select_kernel<<<B, SEL_THREADS, 0, st>>>(cand, cnt, nms_heat, acc_mask, feat, ldf, Cf, cls_w, cls_b, p, q0,
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(hip_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_CAP * 8);
+    attr_set = true;
+  }
+  hip_select_kernel<<<B, SEL_THREADS, SEL_CAP * sizeof(unsigned long long), st>>>(cand, cnt, nms_heat, acc_mask, feat, ldf, Cf, cls_w, cls_b, p, q0,
                                                nq_total, top_idx, query_feat, query_pos, query_score, query_label);
   return check_launch("ff3d_hip_stage");
 }

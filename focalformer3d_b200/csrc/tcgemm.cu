@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   constexpr int NPROD = 128 * G;
   constexpr int TM = TC_BM * MT;                                 // rows per CTA tile
   constexpr bool DEFER = MT == 1;                                // double-buffered accumulators -> deferred epilogue
+  // one CTA per SM has registers to spare: keep the NEXT stage's gather in flight while this one is split and
+  // stored, so a producer group always has 16 KB outstanding (the gather is latency-, not bandwidth-bound)
+  constexpr bool PREFETCH = (BN == 128 && MT == 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
   constexpr uint32_t A_BYTES = TC_BM * 128;
@@ -318,12 +321,11 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       if (s < 0) s += G;
       int t, cidx;                                           // tap and 32-channel chunk of stage s (cin >= 32)
       t = s / p.cpt; cidx = s - t * p.cpt;
-      for (; s < n_stages; s += G) {
+      auto gather = [&](int st, int tt, int ci, float4* v) {
         int tap, coff, ky = 0, kx = 0;
-        if (p.cin >= 32) { tap = t; coff = cidx * 32 + lane_coff; }
-        else { tap = s * p.tps + lane_tap; coff = lane_coff; }
+        if (p.cin >= 32) { tap = tt; coff = ci * 32 + lane_coff; }
+        else { tap = st * p.tps + lane_tap; coff = lane_coff; }
         if (MODE == FF3D_GEMM_CONV2D) { ky = tap / p.kw; kx = tap - ky * p.kw; }
-        float4 v[8 * MT];
 #pragma unroll
         for (int i = 0; i < 8 * MT; ++i) {
           const int row = (i >> 3) * TC_BM + pw * 32 + (i & 7) * 4 + q;   // sub-tile (i >> 3), row inside it
@@ -336,6 +338,17 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
               v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
             }
           }
+        }
+      };
+      float4 v[8 * MT], vn[PREFETCH ? 8 * MT : 1];
+      if (PREFETCH && s < n_stages) gather(s, t, cidx, v);
+      for (; s < n_stages; s += G) {
+        if (PREFETCH) {
+          int tn = t, cn = cidx + G;
+          while (cn >= p.cpt) { cn -= p.cpt; ++tn; }
+          if (s + G < n_stages) gather(s + G, tn, cn, vn);
+        } else {
+          gather(s, t, cidx, v);
         }
         mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
         uint8_t* slot_base = smem + (size_t)ring.slot * SLOT_BYTES;
@@ -357,6 +370,10 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         mbar_arrive(&full_bar[ring.slot]);
         ring.advance(G, n_slots);
         if (p.cin >= 32) { cidx += G; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
+        if (PREFETCH) {
+#pragma unroll
+          for (int i = 0; i < 8 * MT; ++i) v[i] = vn[i];
+        }
       }
       // epilogue of the PREVIOUS tile: its MMAs have had a whole tile's worth of gathers to finish, and the
       // tensor core keeps working on this tile out of the other TMEM accumulator buffer meanwhile
@@ -456,7 +473,9 @@ template <int MODE, int BN>
 static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
   if constexpr (BN == 128) {
     // enough 256-row tiles to fill the machine -> share each weight stage between two row sub-tiles
-    if ((long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms()) return launch_tc_cfg<MODE, BN, 2, 2>(p, n_tiles_n, st);
+    // (only the sparse gather profits: dense layers lose more from the single-buffered accumulators, measured)
+    if (MODE == FF3D_GEMM_SPARSE && (long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms())
+      return launch_tc_cfg<MODE, BN, 2, 2>(p, n_tiles_n, st);
     return launch_tc_cfg<MODE, BN, 3, 1>(p, n_tiles_n, st);
   } else {
     return launch_tc_cfg<MODE, BN, 2, 1>(p, n_tiles_n, st);

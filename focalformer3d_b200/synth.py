@@ -39,13 +39,15 @@ def param_spec(model_cfg):
     me = model_cfg["pts_middle_encoder"]
     if ve["type"] == "HardVFE":
         fc = ve["feat_channels"][0]
-        s["pts_voxel_encoder.vfe_layers.0.linear.weight"] = ((fc, ve["in_channels"]), ("w", ve["in_channels"]))
+        s["pts_voxel_encoder.vfe_layers.0.linear.weight"] = ((fc, ve["in_channels"]), ("w_in", ve["in_channels"]))
         _bn(s, "pts_voxel_encoder.vfe_layers.0.norm", fc)
     # --- SparseEncoder (mmdet3d v0.17.1; spconv-v1 weight layout [kD,kH,kW,Cin,Cout])
     p = "pts_middle_encoder"
     base = me.get("base_channels", 16)
     taps = (3.0, 10.0, 16.0, 21.0)        # measured mean active taps per SubM level on LiDAR-like clouds
-    s[f"{p}.conv_input.0.weight"] = ((3, 3, 3, me["in_channels"], base), ("spw_in", me["in_channels"] * taps[0]))
+    # raw point statistics reach conv_input only with the mean VFE; HardVFE hands it O(1) learned features
+    s[f"{p}.conv_input.0.weight"] = ((3, 3, 3, me["in_channels"], base),
+                                     ("spw_in" if ve["type"] == "HardSimpleVFE" else "spw", me["in_channels"] * taps[0]))
     _bn(s, f"{p}.conv_input.1", base)
     cin = base
     enc = me["encoder_channels"]
@@ -188,8 +190,12 @@ def make_state_dict(model_cfg, seed=0):
             continue
         if isinstance(kind, tuple):
             k, fan = kind
-            gain = {"w": 1.0, "w_small": 0.5, "spw": 1.2, "spw_in": 1.2}[k]
+            gain = {"w": 1.0, "w_small": 0.5, "spw": 1.2, "spw_in": 1.2, "w_in": 1.0}[k]
             t = torch.randn(shape, generator=g) * (gain / math.sqrt(fan))
+            if k == "w_in":              # HardVFE linear [C, F] on raw point features
+                t[:, :3] /= 20.0
+                if shape[1] > 3:
+                    t[:, 3] /= 128.0
             if k == "spw_in":            # raw inputs: metres (|x|~30), intensity 0..255, dt
                 t[..., :3, :] /= 20.0
                 if shape[3] > 3:
