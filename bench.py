@@ -20,7 +20,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "scenes/sec FocalFormer3D_L (nuScenes 10-sweep) forward"
+def _baseline_metric():
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "scenes/sec FocalFormer3D_L (nuScenes 10-sweep) at 1/2/4/8 B200; per-stage ms"
+
+
+METRIC = _baseline_metric()
 WORKLOAD = "FocalFormer3D_L LiDAR, synthetic nuScenes 10-sweep ~300k pts/scene, 0.075 m voxels, 180x180 BEV"
 
 
@@ -142,7 +150,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "scenes_per_step": 1, "points_per_scene": args.points},
+        "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": 1, "global_batch": 1, "points_per_scene": args.points,
+                   "parallelism": "host CPU threads"},
         "cpu_baseline": {"value": sps, "unit": "scenes/s", "cores": cpu_threads(), "kind": "port",
                          "sample": f"1 full-size scene per step x {args.steps} steps (oracle port of the reference algorithm: "
                                    "rulebook gather+mm+scatter sparse conv, ATen conv2d, nn.MultiheadAttention, grid_sample MSDA; "
@@ -182,7 +191,7 @@ def run_ours(args):
     sd = make_state_dict(cfg, 0)
     model = build_model(cfg)
     model.load_state_dict(sd, strict=True)
-    model.cuda().prepare("cuda")
+    model.prepare("cuda")
     # data-parallel sharding: rank r owns scenes r*bs .. r*bs+bs-1 of every step (DistributedSampler(shuffle=False) order)
     host = [p.pin_memory() for p in make_scenes(cfg, args.bs, args.points, seed0=rank * args.bs)]
     dev = [p.cuda() for p in host]

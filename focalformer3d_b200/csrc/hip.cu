@@ -13,8 +13,8 @@ struct HipP {
   int B, C, H, W, k, nms_kernel, ex_lo, ex_hi;
 };
 
-__global__ void hip_heat_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ acc_mask,
-                                float* __restrict__ heat, HipP p) {
+__global__ void hip_heat_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ logits2, int ldl2,
+                                const float* __restrict__ acc_mask, float* __restrict__ heat, HipP p) {
   long long total = (long long)p.B * p.C * p.H * p.W;
   int HW = p.H * p.W;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -24,6 +24,10 @@ __global__ void hip_heat_kernel(const float* __restrict__ logits, int ldl, const
     int b = (int)(r / p.C);
     float l = __ldg(logits + ((long long)b * HW + pos) * ldl + c);
     float s = 1.f / (1.f + expf(-l));
+    if (logits2) {   // single-stage head: (sigmoid(heatmap_head) + sigmoid(heatmap_head_img)) / 2  (focal_decoder.py:549)
+      float l2 = __ldg(logits2 + ((long long)b * HW + pos) * ldl2 + c);
+      s = (s + 1.f / (1.f + expf(-l2))) / 2.f;
+    }
     heat[e] = s * acc_mask[e];
   }
 }
@@ -267,7 +271,7 @@ static HipWs hip_layout(int B, int C, int H, int W) {
 
 extern "C" size_t ff3d_hip_workspace_bytes(int B, int C, int H, int W) { return ff3d::hip_layout(B, C, H, W).total; }
 
-extern "C" int ff3d_hip_stage(const float* logits, int ldl, float* acc_mask, float* nms_heat, const float* feat, int ldf,
+extern "C" int ff3d_hip_stage(const float* logits, int ldl, const float* logits2, int ldl2, float* acc_mask, float* nms_heat, const float* feat, int ldf,
                               int Cf, const float* cls_w, const float* cls_b, int B, int C, int H, int W, int k,
                               int nms_kernel, int exempt_lo, int exempt_hi, int q0, int nq_total, int* top_idx,
                               float* query_feat, float* query_pos, float* query_score, int* query_label,
@@ -292,7 +296,7 @@ extern "C" int ff3d_hip_stage(const float* logits, int ldl, float* acc_mask, flo
   int nb = (int)((total + 255) / 256);
   int cap = num_sms() * 16;
   if (nb > cap) nb = cap;
-  hip_heat_kernel<<<nb, 256, 0, st>>>(logits, ldl, acc_mask, heat, p);
+  hip_heat_kernel<<<nb, 256, 0, st>>>(logits, ldl, logits2, ldl2, acc_mask, heat, p);
   hip_nms_kernel<<<nb, 256, 0, st>>>(heat, nms_heat, cand, cnt, p);
   static bool attr_set = false;
   if (!attr_set) {

@@ -374,6 +374,11 @@ class FocalEncoder(ParamTree):
             stages.append(new_feat)
             feat, cat1 = new_feat, nxt
         extra = None
+        if not stages and extra_out is not None:
+            # DeformFormer3D (num_layers=None): the shared-conv output itself is the decoder's level-0 feature
+            # (focal_encoder.py:220-222 returns it twice; focal_decoder.py:541-545,812)
+            extra_out.copy_(conv_feat)
+            extra = extra_out
         if self.extra_feat and stages:
             extra = extra_out if extra_out is not None else torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
             ops.conv2d(stages[-1], self.pk["extra"][0], self.pk["extra"][1], extra, 3, act=ACT_NONE)   # :218-219
@@ -409,15 +414,18 @@ class FocalDecoder(ParamTree):
                  boxpos=None, decoder_cfg=None, spec=None, loss_cls=dict(type='GaussianFocalLoss', reduction='mean'),
                  **unused):
         super().__init__()
-        if not (initialize_by_heatmap and multiscale and bevpos and extra_feat and mask_heatmap_mode == "poscls") \
+        if not (initialize_by_heatmap and multiscale and bevpos and mask_heatmap_mode == "poscls") \
                 or heatmap_box or classaware_reg or boxpos is not None:
-            raise NotImplementedError("FocalDecoder: only the shipped FocalFormer3D LiDAR head variant is built")
+            raise NotImplementedError("FocalDecoder: only the shipped LiDAR head variants are built")
         if not loss_cls.get("use_sigmoid", False):
             # focal_decoder.py:164-166 appends a background class in that case; no shipped config uses it
             raise NotImplementedError("FocalDecoder: only loss_cls.use_sigmoid=True heads are built")
         stages = (multistage_heatmap or 0) + (1 if reuse_first_heatmap else 0)
-        if stages < 1:
-            raise NotImplementedError("FocalDecoder: single-stage (DeformFormer3D) head is a later scope row")
+        if stages >= 1 and not extra_feat:
+            raise NotImplementedError("FocalDecoder: multi-stage heads without extra_feat are not used by any shipped config")
+        if stages < 1 and not (input_img or iterbev_wo_img):
+            raise NotImplementedError("FocalDecoder: single-stage head without heatmap_head_img")
+        self.single_stage = stages < 1            # DeformFormer3D: focal_decoder.py:539-586
         self.num_classes, self.num_proposals, self.hc = num_classes, num_proposals, hidden_channel
         self.num_decoder_layers, self.num_heads = num_decoder_layers, num_heads
         self.nms_kernel_size, self.test_cfg = nms_kernel_size, test_cfg
@@ -456,6 +464,8 @@ class FocalDecoder(ParamTree):
             return (pack_conv2d(sd[f"{name}.0.conv.weight"], s, dev), vec(b, dev),
                     pack_conv2d(w2p, None, dev), vec(sd[f"{name}.1.bias"], dev, co))
         pk["heat"] = []
+        if self.single_stage:
+            pk["heat"] = [heat("heatmap_head"), heat("heatmap_head_img")]
         for i in range(self.stages):
             pk["heat"].append(heat("heatmap_head") if (i == 0 and self.reuse_first) else heat(f"heatmap_head_img.{i}"))
         pk["cls_w"] = sd["class_encoding.weight"].reshape(hc, nc).t().contiguous().float().to(dev)      # [C, Cf]
@@ -549,9 +559,10 @@ class FocalDecoder(ParamTree):
         B, H, W, hc = conv_feat.shape
         dev = conv_feat.device
         nc, k = self.num_classes, self.num_proposals
-        nq = k * self.stages
-        feats = ([conv_feat] if self.reuse_first else []) + list(stage_feats)
-        assert len(feats) == self.stages
+        n_sel = 1 if self.single_stage else self.stages
+        nq = k * n_sel
+        feats = ([conv_feat] if (self.reuse_first or self.single_stage) else []) + list(stage_feats)
+        assert len(feats) == n_sel
         # --- HIP stages (:588-791)
         acc_mask = torch.ones((B, nc, H, W), dtype=torch.float32, device=dev)
         q_feat = torch.empty((B * nq, hc), dtype=torch.float32, device=dev)
@@ -559,17 +570,27 @@ class FocalDecoder(ParamTree):
         q_score = torch.empty((B * nq, nc), dtype=torch.float32, device=dev)
         q_label = torch.empty((B * nq,), dtype=torch.int32, device=dev)
         dense_heatmaps, nms_heats, tops = [], [], []
-        for s in range(self.stages):
-            w1, b1, w2, b2 = pk["heat"][s]
+        def heat_logits(hw, x):
+            w1, b1, w2, b2 = hw
             t = torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
-            ops.conv2d(feats[s], w1, b1, t, 3, act=ACT_RELU)
-            logits = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)   # padded channels = 0
-            ops.conv2d(t, w2, b2, logits, 3, act=ACT_NONE)
+            ops.conv2d(x, w1, b1, t, 3, act=ACT_RELU)
+            lg = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)       # padded channels = 0
+            ops.conv2d(t, w2, b2, lg, 3, act=ACT_NONE)
+            return lg
+
+        for s in range(n_sel):
+            logits2 = None
+            if self.single_stage:      # heatmap = (sigmoid(heatmap_head(x)) + sigmoid(heatmap_head_img(x))) / 2   :547-549
+                logits = heat_logits(pk["heat"][0], feats[0])
+                logits2 = heat_logits(pk["heat"][1], feats[0])
+                dense_heatmaps.append(logits)
+            else:
+                logits = heat_logits(pk["heat"][s], feats[s])
             nms_heat = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
             top = torch.empty((B, k), dtype=torch.int32, device=dev)
             ops.hip_stage(logits, acc_mask, nms_heat, feats[s], pk["cls_w"], pk["cls_b"], k, self.nms_kernel_size,
-                          self.exempt, s * k, nq, top, q_feat, q_pos, q_score, q_label)
-            dense_heatmaps.append(logits)
+                          self.exempt, s * k, nq, top, q_feat, q_pos, q_score, q_label, logits2=logits2)
+            dense_heatmaps.append(logits if logits2 is None else logits2)
             nms_heats.append(nms_heat)
             tops.append(top)
             ops.mark(f"hip_stage{s}")

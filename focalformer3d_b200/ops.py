@@ -355,15 +355,16 @@ class SparseLevel:
 
 # --------------------------------------------------------------------------------------------------------------
 def hip_stage(logits, acc_mask, nms_heat, feat, cls_w, cls_b, k, nms_kernel, exempt, q0, nq_total, top_idx,
-              query_feat, query_pos, query_score, query_label):
+              query_feat, query_pos, query_score, query_label, logits2=None):
     B, H, W, _, ldl, _ = _nhwc_geom(logits, "hip.logits")
+    ldl2 = _nhwc_geom(logits2, "hip.logits2")[4] if logits2 is not None else 0
     _, _, _, Cf, ldf, fbs = _nhwc_geom(feat, "hip.feat")
     if fbs != H * W:
         raise L.Ff3dError("hip_stage: batch-dense feature view required")
     Cc = acc_mask.shape[1]
     ws_bytes = lib.ff3d_hip_workspace_bytes(B, Cc, H, W)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=logits.device)
-    check(lib.ff3d_hip_stage(_ptr(logits), ldl, _ptr(acc_mask), _ptr(nms_heat), _ptr(feat), ldf, Cf, _ptr(cls_w),
+    check(lib.ff3d_hip_stage(_ptr(logits), ldl, _ptr(logits2), ldl2, _ptr(acc_mask), _ptr(nms_heat), _ptr(feat), ldf, Cf, _ptr(cls_w),
                              _ptr(cls_b), B, Cc, H, W, k, nms_kernel, exempt[0], exempt[1], q0, nq_total, _ptr(top_idx),
                              _ptr(query_feat), _ptr(query_pos), _ptr(query_score), _ptr(query_label), _ptr(ws),
                              ws_bytes, _stream()), "ff3d_hip_stage")

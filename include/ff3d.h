@@ -153,7 +153,8 @@ int ff3d_layernorm(const float* x, const float* gamma, const float* beta, float*
 /* ------------------------------------------------------------------------------------------------
  * Hard-Instance-Probing stage: sigmoid * accumulated mask -> class-aware local-max NMS -> top-k ->
  * query gathers -> accumulated-mask update.  Replaces focal_decoder.py:631-782 (one HIP stage).
- * logits [B,H,W,ldl] NHWC (first C channels used); acc_mask [B,C,H,W] fp32 (in/out);
+ * logits [B,H,W,ldl] NHWC (first C channels used); logits2 (optional, NULL for HIP stages): second heatmap whose
+ * sigmoid is averaged with the first (single-stage DeformFormer3D head, focal_decoder.py:547-549); acc_mask [B,C,H,W] fp32 (in/out);
  * nms_heat [B,C,H,W] fp32 workspace/out (the NMS'ed masked heatmap of this stage);
  * feat [B,H,W,ldf] stage feature; cls_w [C, Cf] (class_encoding weight transposed), cls_b [Cf];
  * outputs at query slot q0..q0+k-1 of nq_total: top_idx [B,k] int32 (flat class*H*W + pos, canonical order:
@@ -162,7 +163,7 @@ int ff3d_layernorm(const float* x, const float* gamma, const float* beta, float*
  * exempt_lo..exempt_hi: classes using a 1x1 window (nuScenes 8..9, Waymo 1..2), focal_decoder.py:678-683,777-780.
  */
 size_t ff3d_hip_workspace_bytes(int B, int C, int H, int W);
-int ff3d_hip_stage(const float* logits, int ldl, float* acc_mask, float* nms_heat, const float* feat, int ldf, int Cf,
+int ff3d_hip_stage(const float* logits, int ldl, const float* logits2, int ldl2, float* acc_mask, float* nms_heat, const float* feat, int ldf, int Cf,
                    const float* cls_w, const float* cls_b, int B, int C, int H, int W, int k, int nms_kernel,
                    int exempt_lo, int exempt_hi, int q0, int nq_total, int* top_idx, float* query_feat,
                    float* query_pos, float* query_score, int* query_label, void* workspace, size_t workspace_bytes,

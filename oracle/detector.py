@@ -65,10 +65,11 @@ class FocalFormer3D(nn.Module):
         """points: list[B] of [Ni, F] -> (head output dict, list of per-scene result dicts)."""
         pts_feats = self.extract_pts_feat(points, stages)
         _, new_pts = self.imgpts_neck(None, pts_feats[0], None)
+        second = list(new_pts[1]) if isinstance(new_pts[1], (list, tuple)) else new_pts[1]
         if stages is not None:
             stages["conv_feat"] = new_pts[0]
-            stages["stage_feats"] = list(new_pts[1])
-        outs = self.pts_bbox_head([new_pts[0], list(new_pts[1])], None, None)
+            stages["stage_feats"] = list(second) if isinstance(second, list) else [second]
+        outs = self.pts_bbox_head([new_pts[0], second], None, None)
         res = self.pts_bbox_head.get_bboxes(outs)
         return outs[0][0], res
 

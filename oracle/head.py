@@ -267,7 +267,7 @@ class FocalDecoder(nn.Module):
             query_feat = query_feat + self.class_encoding(F.one_hot(cls, self.num_classes).permute(0, 2, 1).float())
             query_pos = bev_pos.gather(index=pos[:, :, None].expand(-1, -1, 2), dim=1)
             query_heatmap_score = heatmap.gather(index=pos[:, None, :].expand(-1, self.num_classes, -1), dim=-1)
-            dbg["top_proposals"] = [top]
+            dbg["top_proposals"], dbg["nms_heatmap"] = [top], [heatmap]
         else:
             dense_heatmap = self.heatmap_head(lidar_feat)                        # :588
             multistage_feats = stage_list

@@ -86,6 +86,12 @@ def test_unmodified_reference_configs_load():
         assert dict(refw.model.pts_bbox_head)[k] == v, k
     assert dict(refw.model.test_cfg.pts) == dict(minew.model.test_cfg.pts)
     assert "pts_voxel_encoder.vfe_layers.0.linear.weight" in param_spec(refw.model)
+    refd = load_config(os.path.join(REF_CFG_DIR, "DeformFormer3D_L.py"))
+    mined = load_config(os.path.join(ROOT, "configs", "deformformer3d_l.py"))
+    for part in ("imgpts_neck", "pts_bbox_head"):
+        for k, v in dict(mined.model[part]).items():
+            assert dict(refd.model[part])[k] == v, (part, k)
+    assert "pts_bbox_head.heatmap_head_img.0.conv.weight" in param_spec(refd.model)      # single module, no index
     for name in sorted(os.listdir(REF_CFG_DIR)):
         c = load_config(os.path.join(REF_CFG_DIR, name))
         assert c.model.type in ("FocalFormer3D",), name

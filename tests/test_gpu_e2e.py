@@ -30,12 +30,23 @@ def _waymo_tiny():
     return cfg, make_state_dict(cfg, 1), pts
 
 
-@pytest.fixture(scope="module", params=["nuscenes_l", "waymo_l"])
+def _deform_tiny():
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_points
+    cfg = scaled_model_cfg(load_config(default_config_path("deformformer3d_l"))["model"], bev=24, num_proposals=20)
+    pts = [torch.from_numpy(synth_points(n, cfg["pts_voxel_layer"]["point_cloud_range"], seed=20 + s))
+           for s, n in enumerate((6000, 6500))]
+    return cfg, make_state_dict(cfg, 2), pts
+
+
+@pytest.fixture(scope="module", params=["nuscenes_l", "waymo_l", "deformformer_l"])
 def pair(request, tiny_cfg, tiny_sd, tiny_points):
     from focalformer3d_b200.model import build_model
     from oracle.detector import build_oracle
     if request.param == "waymo_l":           # HardVFE, 3 classes, 3 HIP stages, no velocity head, 2 encoder layers
         tiny_cfg, tiny_sd, tiny_points = _waymo_tiny()
+    if request.param == "deformformer_l":    # no HIP: single averaged heatmap, one decoder stage, no ROI, no fusion layers
+        tiny_cfg, tiny_sd, tiny_points = _deform_tiny()
     model = build_model(tiny_cfg)
     model.load_state_dict(tiny_sd, strict=True)
     model.cuda().prepare("cuda")
@@ -149,7 +160,7 @@ def test_simple_test_signature(pair):
     assert len(out) == len(tiny_points)
     for o in out:
         d = o["pts_bbox"]
-        assert d["boxes_3d"].shape[1] == (9 if pair["name"] == "nuscenes_l" else 7) and d["boxes_3d"].shape[0] == d["scores_3d"].shape[0] == d["labels_3d"].shape[0]
+        assert d["boxes_3d"].shape[1] == (7 if pair["name"] == "waymo_l" else 9) and d["boxes_3d"].shape[0] == d["scores_3d"].shape[0] == d["labels_3d"].shape[0]
         assert d["boxes_3d"].device.type == "cpu" and d["boxes_3d"].shape[0] <= 200
 
 

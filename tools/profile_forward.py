@@ -11,7 +11,7 @@ n_fwd = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cfg = load_config(default_config_path())["model"]
 model = build_model(cfg)
 model.load_state_dict(make_state_dict(cfg, 0), strict=True)
-model.cuda().prepare("cuda")
+model.prepare("cuda")          # weights are packed on the host and copied once: no torch kernels before the forward
 pts = [torch.from_numpy(synth_points(300000, cfg["pts_voxel_layer"]["point_cloud_range"], seed=s)).cuda() for s in range(4)]
 for _ in range(n_fwd):
     model.forward_raw(pts)
