@@ -38,11 +38,12 @@ class Profiler:
 
     def __init__(self):
         self.enabled = False
+        self.keep_records = True
         self.records = []      # (label, start, end, flops, bytes, n_dev_or_None, meta)
         self.marks = []        # (name, event)
 
-    def start(self):
-        self.enabled, self.records, self.marks = True, [], []
+    def start(self, records=True):
+        self.enabled, self.keep_records, self.records, self.marks = True, records, [], []
 
     def stop(self):
         self.enabled = False
@@ -54,7 +55,7 @@ class Profiler:
             self.marks.append((name, e))
 
     def begin(self):
-        if not self.enabled:
+        if not self.enabled or not self.keep_records:
             return None
         e = torch.cuda.Event(enable_timing=True)
         e.record()
