@@ -59,11 +59,22 @@ __global__ void hip_nms_kernel(const float* __restrict__ heat, float* __restrict
       v = (h == m) ? h : 0.f;
     }
     nms_heat[e] = v;
-    if (v > 0.f) {
+    // warp-aggregated append (one atomic per warp and scene instead of one per candidate); a warp's elements may
+    // straddle two scenes, so aggregate per scene of the lane
+    const bool cand_ok = v > 0.f;
+    const unsigned active = __activemask();
+    const unsigned same_b = __match_any_sync(active, b);
+    const unsigned voters = __ballot_sync(active, cand_ok) & same_b;
+    if (cand_ok) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(voters) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&cand_cnt[b], __popc(voters));
+      base = __shfl_sync(voters, base, leader);
+      const int slot = base + __popc(voters & ((1u << lane) - 1u));
       unsigned int flat = (unsigned int)(c * HW + pos);
-      unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-      int slot = atomicAdd(&cand_cnt[b], 1);
-      cand[(size_t)b * p.C * HW + slot] = key;
+      cand[(size_t)b * p.C * HW + slot] =
+          ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
     }
   }
 }

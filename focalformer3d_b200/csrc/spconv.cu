@@ -72,8 +72,16 @@ __global__ void sp_down_sites_kernel(const int* __restrict__ coors_in, const int
     if (*overflow) continue;   // capacity already exceeded: stop filling the table (keeps probing short)
     int s = hash_insert(hkeys_out, hmask_out, lin_key(c.x, oz, oy, ox, g.Do, g.Ho, g.Wo), &ins);
     if (s < 0) { *overflow = 1; continue; }
+    // warp-aggregated row allocation: one atomicAdd per converged warp instead of one per new site
+    const unsigned act = __activemask();
+    const unsigned vot = __ballot_sync(act, ins);
     if (ins) {
-      int row = atomicAdd(n_out_dev, 1);
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(vot) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(n_out_dev, __popc(vot));
+      base = __shfl_sync(vot, base, leader);
+      const int row = base + __popc(vot & ((1u << lane) - 1u));
       if (row < cap_out) {
         reinterpret_cast<int4*>(coors_out)[row] = make_int4(c.x, oz, oy, ox);
         hvals_out[s] = row;

@@ -140,7 +140,8 @@ class SparseEncoder(ParamTree):
         self.base_channels, self.encoder_channels, self.encoder_paddings = base_channels, encoder_channels, encoder_paddings
         self.build_params(spec)
         self.pk = None
-        self.cap_growth = (4.0, 1.0, 1.0, 1.0)
+        # row-capacity growth per strided conv (level-2 sites measured at 1.25-2.4x level 1; overflow raises)
+        self.cap_growth = (3.0, 1.0, 1.0, 1.0)
 
     def prepare(self, dev):
         sd = self.flat()
