@@ -19,7 +19,7 @@
 //              After the main loop both groups run the epilogue, half the columns each
 //              (tcgen05.ld 32x32b: thread <-> TMEM lane <-> tile row).
 //   warp 8     B producer: one cp.async.bulk (UBLKCP) per stage of the host-pre-swizzled [hi | lo] weight image.
-//   warp 9     TMEM alloc/dealloc + single-thread tcgen05.mma issue (12 MMAs of 128 x BN x 8 per stage),
+//   warp 9     TMEM alloc/dealloc + single-thread tcgen05.mma issue (per K=8 step: one 128 x 2BN and one 128 x BN MMA),
 //              tcgen05.commit releases smem stages / signals the epilogue.
 // Sparse mode stages the tile's whole neighbour map (taps x 128 int32) in shared memory up front, so the gather's
 // dependent index load is off the per-stage critical path.
@@ -404,7 +404,10 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BN);
+      // [main | cross] accumulators are adjacent TMEM columns and [B_hi | B_lo] adjacent smem tiles, so
+      // A_hi x [B_hi | B_lo] is ONE N = 2*BN MMA; A_lo x B_hi (N = BN) completes the cross term: 2 MMAs and
+      // 2 reads of the A tiles per K step instead of 3 (the kernel is shared-memory-bandwidth bound)
+      const uint32_t idesc_wide = make_idesc(2 * BN), idesc_cross = make_idesc(BN);
       Ring ring{0, 0u};
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -418,19 +421,18 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
           tc_fence_after();
           const uint32_t slot_a = smem_u32(smem + (size_t)ring.slot * SLOT_BYTES);
           const uint32_t b_hi = slot_a + MT * 2 * A_BYTES;
-          const uint32_t b_lo = b_hi + B_BYTES;
+          static_assert(B_BYTES % 1024 == 0, "B_lo must continue B_hi's 8-row swizzle atoms");
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
-            const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
+            const uint64_t dbh = make_desc(b_hi + k * 32);   // as an N = 2*BN operand it runs on into B_lo
             const uint32_t acc = (s | k) ? 1u : 0u;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t a_hi = slot_a + mt * 2 * A_BYTES, a_lo = a_hi + A_BYTES;
               const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
               const uint32_t d_main = d_base + (uint32_t)(mt * 2 * BN), d_cross = d_main + BN;
-              umma_tf32(d_cross, dal, dbh, idesc, acc);
-              umma_tf32(d_cross, dah, dbl, idesc, 1u);
-              umma_tf32(d_main, dah, dbh, idesc, acc);
+              umma_tf32(d_main, dah, dbh, idesc_wide, acc);    // main += A_hi*B_hi ; cross += A_hi*B_lo
+              umma_tf32(d_cross, dal, dbh, idesc_cross, 1u);   // cross += A_lo*B_hi
             }
           }
           umma_commit(&empty_bar[ring.slot]);   // frees the smem slot once these MMAs have read it
