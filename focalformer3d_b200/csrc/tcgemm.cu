@@ -511,11 +511,21 @@ extern "C" int ff3d_tcgemm_stages(int cin, int taps) {
   return (taps + tps - 1) / tps;
 }
 
+extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn, ff3d_stream_t stream);
+
 extern "C" int ff3d_tcgemm(const ff3d_gemm_desc* d, const float* wimg, ff3d_stream_t stream) {
+  return ff3d_tcgemm_bn(d, wimg, 0, stream);
+}
+
+// bn = N tile the weight images were packed for (0 = ff3d_tcgemm_ntile's default).  A smaller tile than the default
+// (e.g. 64 for cout = 512) gives small-M / huge-K layers enough CTAs to fill the machine.
+extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn, ff3d_stream_t stream) {
   using namespace ff3d;
   FF3D_REQUIRE(d != nullptr && wimg != nullptr, "ff3d_tcgemm: null argument");
-  int bn = ff3d_tcgemm_ntile(d->cin, d->cout);
-  FF3D_REQUIRE(bn > 0, "ff3d_tcgemm: shape cin=%d cout=%d is not tensor-core tileable", d->cin, d->cout);
+  if (bn == 0) bn = ff3d_tcgemm_ntile(d->cin, d->cout);
+  FF3D_REQUIRE(bn > 0 && ff3d_tcgemm_ntile(d->cin, d->cout) > 0 && d->cout % bn == 0 &&
+                   (bn == 16 || bn == 32 || bn == 64 || bn == 128),
+               "ff3d_tcgemm: shape cin=%d cout=%d (N tile %d) is not tensor-core tileable", d->cin, d->cout, bn);
   FF3D_REQUIRE(d->ldx % 4 == 0 && d->x && d->y && d->taps > 0, "ff3d_tcgemm: bad operands");
   FF3D_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wimg) & 15) == 0,
                "ff3d_tcgemm: x and wimg must be 16-byte aligned");

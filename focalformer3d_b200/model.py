@@ -58,13 +58,13 @@ def bn_scale_shift(sd, name, eps):
     return s, b
 
 
-def pack_taps(w_tco, dev):
+def pack_taps(w_tco, dev, bn=None):
     """[taps, cin, cout] (float64/32) -> ops.PackedW: fp32 [taps, pad4(cin), pad4(cout)] for the SIMT kernel plus,
     when the shape is tensor-core tileable, the pre-swizzled hi/lo TF32 images for the tcgen05 kernel."""
     t, ci, co = w_tco.shape
     out = torch.zeros((t, _pad4(ci), _pad4(co)), dtype=torch.float32)
     out[:, :ci, :co] = w_tco.float()
-    return ops.PackedW(out.contiguous(), dev)
+    return ops.PackedW(out.contiguous(), dev, bn)
 
 
 def pack_conv2d(w, scale=None, dev="cuda"):
@@ -76,12 +76,12 @@ def pack_conv2d(w, scale=None, dev="cuda"):
     return pack_taps(w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co), dev)
 
 
-def pack_linear(w, scale=None, dev="cuda"):
+def pack_linear(w, scale=None, dev="cuda", bn=None):
     """nn.Linear / Conv1d(k=1) weight [out, in(,1)] -> [1, in, out]."""
     w = w.double().reshape(w.shape[0], -1)
     if scale is not None:
         w = w * scale.view(-1, 1)
-    return pack_taps(w.t().unsqueeze(0), dev)
+    return pack_taps(w.t().unsqueeze(0), dev, bn)
 
 
 def vec(v, dev, n=None):
@@ -482,7 +482,9 @@ class FocalDecoder(ParamTree):
             pk["roi"] = []
             for i, w in enumerate(ws):
                 s, b = bn_scale_shift(sd, f"roi_mlp.{i * self.roi_step + 1}", 1e-5)
-                pk["roi"].append((pack_linear(w, s, dev), vec(b, dev)))
+                # roi_mlp.0 is [B*Nq ~ 2400 rows] x [18816 -> 512]: N tile 64 instead of 128 doubles the CTA count
+                bn = 64 if (i == 0 and w.shape[0] % 64 == 0) else None
+                pk["roi"].append((pack_linear(w, s, dev, bn=bn), vec(b, dev)))
         pk["dim_t"] = (10000 ** (2 * (torch.arange(128, dtype=torch.float32) // 2) / 128)).to(dev)
         pk["stage"] = []
         for i in range(self.num_decoder_layers):

@@ -83,14 +83,16 @@ import os as _os
 USE_TC = _os.environ.get("FF3D_TC", "1") != "0"
 
 
-def tc_weight_images(w):
+def tc_weight_images(w, bn=None):
     """[taps, cin, cout] fp32 (cin in {8,16} or a multiple of 32) -> [n_tiles, n_stages, 2, bn, 32] fp32: per
     (N tile, pipeline K-step) the hi and lo TF32 parts of the weights as 128B-swizzled K-major smem images
     (row n = output channel, 16-byte chunk j stored at chunk j ^ (n % 8)): one cp.async.bulk per stage."""
     taps, cin, cout = w.shape
-    bn = lib.ff3d_tcgemm_ntile(cin, cout)
-    if bn <= 0:
+    default_bn = lib.ff3d_tcgemm_ntile(cin, cout)
+    if default_bn <= 0:
         return None, 0
+    bn = bn or default_bn
+    assert cout % bn == 0 and bn in (16, 32, 64, 128)
     n_stages = lib.ff3d_tcgemm_stages(cin, taps)
     if cin >= 32:
         kmat = w.reshape(taps * cin, cout)                                    # stage s = rows [32 s, 32 s + 32)
@@ -119,9 +121,9 @@ def tc_weight_images(w):
 class PackedW:
     """Device weights of one GEMM-like layer: ``w`` [taps, cin, ldw] (SIMT kernel) and ``img`` (tcgen05 kernel)."""
 
-    def __init__(self, w_cpu, dev):
+    def __init__(self, w_cpu, dev, bn=None):
         self.w = w_cpu.to(dev)
-        img, self.bn = tc_weight_images(w_cpu)
+        img, self.bn = tc_weight_images(w_cpu, bn)
         self.img = img.to(dev) if img is not None else None
 
     @property
@@ -132,7 +134,7 @@ class PackedW:
 def _gemm(d, w, what):
     """Dispatch one implicit-GEMM launch: tcgen05 3xTF32 kernel when the layer is tensor-core tileable."""
     if USE_TC and w.img is not None:
-        check(lib.ff3d_tcgemm(C.byref(d), _ptr(w.img), _stream()), f"ff3d_tcgemm({what})")
+        check(lib.ff3d_tcgemm_bn(C.byref(d), _ptr(w.img), w.bn, _stream()), f"ff3d_tcgemm({what})")
     else:
         check(lib.ff3d_igemm(C.byref(d), _stream()), f"ff3d_igemm({what})")
 

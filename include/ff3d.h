@@ -138,6 +138,8 @@ int ff3d_igemm(const ff3d_gemm_desc* desc, ff3d_stream_t stream);
  * the hi and lo TF32 parts of w as 128B-swizzled K-major shared-memory images (focalformer3d_b200/ops.py
  * tc_weight_images).  desc->w / ldw are ignored. */
 int ff3d_tcgemm(const ff3d_gemm_desc* desc, const float* wimg, ff3d_stream_t stream);
+/* same with an explicit N tile (16/32/64/128 dividing cout) the images were packed for; 0 = default */
+int ff3d_tcgemm_bn(const ff3d_gemm_desc* desc, const float* wimg, int ntile, ff3d_stream_t stream);
 int ff3d_tcgemm_ntile(int cin, int cout);
 int ff3d_tcgemm_stages(int cin, int taps);
 
