@@ -482,9 +482,9 @@ class FocalDecoder(ParamTree):
             pk["roi"] = []
             for i, w in enumerate(ws):
                 s, b = bn_scale_shift(sd, f"roi_mlp.{i * self.roi_step + 1}", 1e-5)
-                # roi_mlp.0 is [B*Nq ~ 2400 rows] x [18816 -> 512]: N tile 64 instead of 128 doubles the CTA count
-                bn = 64 if (i == 0 and w.shape[0] % 64 == 0) else None
-                pk["roi"].append((pack_linear(w, s, dev, bn=bn), vec(b, dev)))
+                # (measured: a 64-wide N tile for roi_mlp.0 -- more CTAs for its ~2400 rows -- is 1.5x SLOWER:
+                #  the 180 MB gathered-ROI operand is then re-read 8x instead of 4x; kept on the default 128)
+                pk["roi"].append((pack_linear(w, s, dev), vec(b, dev)))
         pk["dim_t"] = (10000 ** (2 * (torch.arange(128, dtype=torch.float32) // 2) / 128)).to(dev)
         pk["stage"] = []
         for i in range(self.num_decoder_layers):
