@@ -285,10 +285,12 @@ def run_ours(args):
         t, fl, by, cnt = agg[dom]
         n_launch = max(cnt // reps, 1)
         t_l, fl_l, by_l = t / n_launch, fl / n_launch, by / n_launch
-        traffic = None
+        traffic, ncu_detail = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(dom)            # dram__bytes_read.sum + dram__bytes_write.sum, one launch
+                tj = json.load(f)
+            traffic = tj.get(dom)                          # dram__bytes_read.sum + dram__bytes_write.sum, one launch
+            ncu_detail = tj.get("_detail", {}).get(dom)    # same capture: tensor-pipe / DRAM / L2 percentages
         except Exception:
             pass
         if dom.startswith("spconv"):
@@ -305,6 +307,10 @@ def run_ours(args):
                     "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                     "share_of_step": t / step_ms,
                     "note": "3xTF32 split accumulation: 3 tensor-core MMAs per fp32-grade product; flops counted once"}
+        if ncu_detail:
+            roof["ncu"] = {"tensor_pipe_tf32_pct_of_peak": ncu_detail["tensor_pct"], "dram_pct_of_peak": ncu_detail["dram_pct"],
+                           "l2_pct_of_peak": ncu_detail["l2_pct"], "kernel": ncu_detail["kernel"],
+                           "source": "profiles/r01_ncu_tcgemm_*.txt (ncu --set full, one launch)"}
         roof["by_kernel_family_ms"] = {k: round(v[0], 3) for k, v in kinds.items()}
         roof["sparse_encoder_family"] = {"GB/s": kinds["spconv"][2] / max(kinds["spconv"][0], 1e-9) / 1e6,
                                          "TFLOP/s": kinds["spconv"][1] / max(kinds["spconv"][0], 1e-9) / 1e9,
