@@ -47,6 +47,8 @@ class FocalFormer3D(nn.Module):
     @torch.no_grad()
     def extract_pts_feat(self, points, stages=None):
         voxels, num_points, coors = self.voxelize(points)
+        dev = next(self.parameters()).device           # .cuda() turns the oracle into the stock-PyTorch GPU stand-in
+        voxels, num_points, coors = voxels.to(dev), num_points.to(dev), coors.to(dev)
         vf = self.pts_voxel_encoder(voxels, num_points, coors)
         batch_size = int(coors[-1, 0]) + 1
         x = self.pts_middle_encoder(vf, coors, batch_size)

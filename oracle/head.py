@@ -240,11 +240,12 @@ class FocalDecoder(nn.Module):
             extra_feats = stage_list.pop(-1)                                     # :526-528
         B, C = lidar_feat.shape[:2]
         lidar_feat_flatten = lidar_feat.view(B, C, -1)
-        bev_pos = self.bev_pos.repeat(B, 1, 1)
+        dev = lidar_feat.device
+        bev_pos = self.bev_pos.repeat(B, 1, 1).to(dev)
         if self.multiscale:
             s = lidar_feat.shape[2]
-            bev_pos_2 = self.create_2D_grid(s // 2, s // 2).repeat(B, 1, 1) * 2
-            bev_pos_4 = self.create_2D_grid(s // 4, s // 4).repeat(B, 1, 1) * 4
+            bev_pos_2 = self.create_2D_grid(s // 2, s // 2).repeat(B, 1, 1).to(dev) * 2
+            bev_pos_4 = self.create_2D_grid(s // 4, s // 4).repeat(B, 1, 1).to(dev) * 4
         query_box = None
         dbg = {}
         if not self.multistage_heatmap:                                          # :539-586
@@ -337,11 +338,11 @@ class FocalDecoder(nn.Module):
         dbg["stage_query_feat"], dbg["roi_feat"], dbg["value"] = [], [], []
         for i in range(self.num_decoder_layers):                                 # :826-958
             if not self.multiscale:
-                spatial_shapes = torch.as_tensor([list(lidar_feat.shape[-2:])], dtype=torch.long)
+                spatial_shapes = torch.as_tensor([list(lidar_feat.shape[-2:])], dtype=torch.long, device=dev)
                 lidar_feat_flatten = lidar_feat.flatten(2, 3)
                 ms = [lidar_feat]
             else:
-                spatial_shapes = torch.as_tensor([list(m.shape[2:]) for m in ms], dtype=torch.long)
+                spatial_shapes = torch.as_tensor([list(m.shape[2:]) for m in ms], dtype=torch.long, device=dev)
                 lidar_feat_flatten = ms_flat
                 if self.bevpos and i == 0:
                     bev_pos = torch.cat([bev_pos, bev_pos_2, bev_pos_4], dim=1)  # :846-848
@@ -365,9 +366,9 @@ class FocalDecoder(nn.Module):
                 gp = gp + std[:, None, :2]
                 gp = gp.view(B, nq, self.roi_feats ** 2, 2)
                 if self.test_cfg["dataset"] == "nuScenes":
-                    pcr = torch.tensor([-54, -54, -5.0, 54, 54, 3.0])
+                    pcr = torch.tensor([-54, -54, -5.0, 54, 54, 3.0], device=dev)
                 else:
-                    pcr = torch.tensor([-75.2, -75.2, -2, 75.2, 75.2, 4])
+                    pcr = torch.tensor([-75.2, -75.2, -2, 75.2, 75.2, 4], device=dev)
                 gp = (gp - pcr[:2]) / (pcr[3:5] - pcr[:2])
                 gp = (gp * 2.0 - 1.0).clip(min=-2.0, max=2.0)
                 rf = torch.cat([F.grid_sample(f, gp, mode="bilinear", align_corners=False) for f in ms], dim=1)
@@ -380,7 +381,7 @@ class FocalDecoder(nn.Module):
                 query=query_feat.permute(2, 0, 1), key=None, value=value_in.permute(2, 0, 1),
                 query_pos=query_pos_embed.permute(1, 0, 2), reference_points=reference_points,
                 spatial_shapes=spatial_shapes, level_start_index=level_start_index,
-                valid_ratios=torch.ones((B, 1, 2)), key_padding_mask=None, attn_masks=None)   # :927-933
+                valid_ratios=torch.ones((B, 1, 2), device=dev), key_padding_mask=None, attn_masks=None)   # :927-933
             query_feat = query_feat.permute(1, 2, 0)
             dbg["stage_query_feat"].append(query_feat)
             query_pos = reference_points * WH
@@ -405,7 +406,8 @@ class FocalDecoder(nn.Module):
 
     @staticmethod
     def get_dense_grid_points(rois, n, grid_size):                               # :1655-1664
-        ii, jj = torch.meshgrid(torch.arange(grid_size), torch.arange(grid_size), indexing="ij")
+        ii, jj = torch.meshgrid(torch.arange(grid_size, device=rois.device), torch.arange(grid_size, device=rois.device),
+                                indexing="ij")
         dense_idx = torch.stack([ii.reshape(-1), jj.reshape(-1)], dim=1)[None].repeat(n, 1, 1).float()
         size = rois.view(n, -1)[:, 3:5]
         return (dense_idx + 0.5) / grid_size * size[:, None] - size[:, None] / 2

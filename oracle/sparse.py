@@ -54,6 +54,8 @@ def build_rulebook(indices, spatial_shape, ksize, stride, padding, subm):
     """
     k, s, p = _to3(ksize), _to3(stride), _to3(padding)
     idx = indices.long()
+    dev = idx.device
+    T = lambda v: torch.tensor(v, device=dev)
     if subm:
         oshape = tuple(spatial_shape)
         out_idx = idx
@@ -63,11 +65,11 @@ def build_rulebook(indices, spatial_shape, ksize, stride, padding, subm):
         for kz in range(k[0]):
             for ky in range(k[1]):
                 for kx in range(k[2]):
-                    v = idx[:, 1:] + torch.tensor([p[0] - kz, p[1] - ky, p[2] - kx])
-                    st = torch.tensor(s)
+                    v = idx[:, 1:] + T([p[0] - kz, p[1] - ky, p[2] - kx])
+                    st = T(s)
                     ok = (v % st == 0).all(1)
                     o = torch.div(v, st, rounding_mode="floor")
-                    ok &= (o >= 0).all(1) & (o < torch.tensor(oshape)).all(1)
+                    ok &= (o >= 0).all(1) & (o < T(oshape)).all(1)
                     cands.append(torch.cat([idx[ok, :1], o[ok]], 1))
         allc = torch.cat(cands, 0)
         keys = torch.unique(_lin(allc, oshape))          # sorted; the order of output rows is
@@ -77,12 +79,12 @@ def build_rulebook(indices, spatial_shape, ksize, stride, padding, subm):
     sk, order = torch.sort(in_keys)
     pairs = []
     No = out_idx.shape[0]
-    orow = torch.arange(No)
+    orow = torch.arange(No, device=dev)
     for kz in range(k[0]):
         for ky in range(k[1]):
             for kx in range(k[2]):
-                ic = out_idx[:, 1:] * torch.tensor(s) - torch.tensor(p) + torch.tensor([kz, ky, kx])
-                ok = (ic >= 0).all(1) & (ic < torch.tensor(spatial_shape)).all(1)
+                ic = out_idx[:, 1:] * T(s) - T(p) + T([kz, ky, kx])
+                ok = (ic >= 0).all(1) & (ic < T(spatial_shape)).all(1)
                 q = _lin(torch.cat([out_idx[:, :1], ic], 1), spatial_shape)
                 rows, hit = _lookup(sk, order, q.clamp(min=0))
                 ok &= hit

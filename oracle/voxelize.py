@@ -131,7 +131,7 @@ class HardVFE(torch.nn.Module):
 
     def forward(self, features, num_points, coors=None):
         M, P, _ = features.shape
-        mask = (torch.arange(P)[None, :] < num_points[:, None]).type_as(features)
+        mask = (torch.arange(P, device=features.device)[None, :] < num_points[:, None]).type_as(features)
         x = features * mask[..., None]
         l = self.vfe_layers[0]
         y = l.linear(x)                                        # [M, P, C]
