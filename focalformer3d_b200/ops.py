@@ -131,9 +131,15 @@ class PackedW:
         return self.w.shape
 
 
+# rows below which a plain linear layer goes to the fp32 SIMT kernel: a persistent tcgen05 CTA pays ~10 us of fixed
+# cost (TMEM alloc, barrier init, pipeline fill) that a [<= few thousand rows] x 128 GEMM never amortises
+TC_MIN_ROWS = int(_os.environ.get("FF3D_TC_MIN_ROWS", "0"))
+
+
 def _gemm(d, w, what):
     """Dispatch one implicit-GEMM launch: tcgen05 3xTF32 kernel when the layer is tensor-core tileable."""
-    if USE_TC and w.img is not None:
+    small = d.mode == GEMM_ROWS and d.M < TC_MIN_ROWS and d.cin <= 1024
+    if USE_TC and w.img is not None and not small:
         check(lib.ff3d_tcgemm_bn(C.byref(d), _ptr(w.img), w.bn, _stream()), f"ff3d_tcgemm({what})")
     else:
         check(lib.ff3d_igemm(C.byref(d), _stream()), f"ff3d_igemm({what})")
