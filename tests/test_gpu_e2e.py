@@ -201,3 +201,65 @@ def test_full_size_properties():
     n = [int(x.item()) for x in st["level_sizes"]]
     assert n[0] == int(st["vox"]["n_dev"][0].item()) and all(v > 0 for v in n)
     assert boxes.shape == (2, 600, 9) and torch.isfinite(boxes).all()
+
+
+def test_voxel_cap_parity(tiny_cfg, tiny_sd, tiny_points):
+    """max_voxels smaller than the number of occupied voxels: voxels created after the cap are dropped in
+    first-appearance order (reference semantics) -- end-to-end parity with the cap active."""
+    import copy
+    from focalformer3d_b200.model import build_model
+    from oracle.detector import build_oracle
+    cfg = copy.deepcopy(tiny_cfg)
+    cfg["pts_voxel_layer"]["max_voxels"] = (1000, 1500)
+    model = build_model(cfg)
+    model.load_state_dict(tiny_sd, strict=True)
+    model.prepare("cuda")
+    res, det, st = model.forward_raw([p.cuda() for p in tiny_points], keep_stages=True)
+    oracle = build_oracle(cfg)
+    oracle.load_state_dict(tiny_sd, strict=True)
+    ost = {}
+    ref, _ = oracle.forward_raw(tiny_points, ost)
+    n = int(st["vox"]["n_dev"][0].item())
+    assert n == ost["coors"].shape[0] == 2 * 1500                       # both scenes hit the cap
+    assert torch.equal(st["vox"]["coors"][:n].cpu(), ost["coors"].int())
+    pm, po = _match(res, oracle, ref)
+    for key in ("center", "dim", "heatmap"):
+        a = res[key].cpu()[..., -pm.shape[1]:].gather(2, pm[:, None].expand(-1, res[key].shape[1], -1))
+        b = ref[key][..., -po.shape[1]:].gather(2, po[:, None].expand(-1, ref[key].shape[1], -1))
+        assert (a - b).abs().max().item() < TOL, key
+
+
+def test_batch_with_an_empty_scene_runs(tiny_cfg, tiny_sd, tiny_points):
+    """A scene with no in-range points contributes no voxels; its queries come from an all-background BEV map.
+    (The reference derives the batch size from the last voxel's batch index, focalformer3d.py:167, and would
+    mis-size the batch here; we keep the true batch size.)"""
+    from focalformer3d_b200.model import build_model
+    model = build_model(tiny_cfg)
+    model.load_state_dict(tiny_sd, strict=True)
+    model.prepare("cuda")
+    far = torch.full((50, 5), 1000.0)
+    res, (boxes, scores, labels, keep), _ = model.forward_raw([tiny_points[0].cuda(), far.cuda()])
+    torch.cuda.synchronize()
+    assert boxes.shape[0] == 2 and torch.isfinite(boxes).all() and torch.isfinite(res["heatmap"]).all()
+    single, _, _ = model.forward_raw([tiny_points[0].cuda()])
+    assert torch.equal(single["_top_proposals"][0][0], res["_top_proposals"][0][0])     # scene 0 is unaffected
+
+
+def test_waymo_full_size_properties():
+    """FocalFormer3D_Waymo_L at its full geometry (1536^2 x 40 voxels, 192^2 BEV, 3 HIP stages x 200)."""
+    from focalformer3d_b200.config import load_config, default_config_path
+    from focalformer3d_b200.synth import make_state_dict, synth_points
+    from focalformer3d_b200.model import build_model
+    cfg = load_config(default_config_path("focalformer3d_waymo_l"))["model"]
+    model = build_model(cfg)
+    model.load_state_dict(make_state_dict(cfg, 0), strict=True)
+    model.prepare("cuda")
+    pts = [torch.from_numpy(synth_points(180000, cfg["pts_voxel_layer"]["point_cloud_range"], seed=s, n_beams=64, n_sweeps=1)).cuda()
+           for s in range(2)]
+    res, (boxes, scores, labels, keep), st = model.forward_raw(pts, keep_stages=True)
+    torch.cuda.synchronize()
+    assert int(st["overflow"].item()) == 0
+    assert res["center"].shape == (2, 2, 1200) and res["heatmap"].shape == (2, 3, 1200) and "vel" not in res
+    assert boxes.shape == (2, 600, 7) and torch.isfinite(boxes).all()
+    tops = [set(t[0].tolist()) for t in res["_top_proposals"]]
+    assert all(len(t) == 200 for t in tops) and not (tops[0] & tops[1]) and not (tops[1] & tops[2]) and not (tops[0] & tops[2])
