@@ -91,6 +91,26 @@ def default_config_path(name="focalformer3d_l"):
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", name + ".py")
 
 
+def scaled_camera_cfg(model_cfg, bev, img_hw, num_proposals=None):
+    """Smaller variant of a camera-only config: BEV cells per side and image size (H, W multiples of 32)."""
+    m = copy.deepcopy(model_cfg)
+    osf = m["pts_bbox_head"]["bbox_coder"]["out_size_factor"]
+    vs = m["pts_bbox_head"]["bbox_coder"]["voxel_size"]
+    old = m["imgpts_neck"]["pc_range"]
+    half = bev * osf * vs[0] / 2.0
+    rng = [-half, -half, old[2], half, half, old[5]]
+    m["imgpts_neck"]["pc_range"] = rng
+    m["imgpts_neck"]["img_scale"] = tuple(img_hw)
+    m["pts_bbox_head"]["bbox_coder"]["pc_range"] = rng[:2]
+    m["pts_bbox_head"]["bbox_coder"]["post_center_range"] = [rng[0] * 1.2, rng[1] * 1.2, -10.0, rng[3] * 1.2, rng[4] * 1.2, 10.0]
+    if num_proposals is not None:
+        m["pts_bbox_head"]["num_proposals"] = num_proposals
+    t = m["test_cfg"]["pts"]
+    t["grid_size"] = [bev * osf, bev * osf, t["grid_size"][2]]
+    t["pc_range"] = rng[:2]
+    return _wrap(m)
+
+
 def scaled_model_cfg(model_cfg, bev, z_cells=None, num_proposals=None, max_voxels=None):
     """Derive a geometrically smaller variant of a LiDAR config (same layers, same voxel size, smaller
     range) for parity tests the CPU oracle finishes in seconds.  ``bev`` = BEV cells per side."""

@@ -255,12 +255,30 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         tmem_ld16(acc + (uint32_t)(BN + c0), v2);
         if (rvalid) {
           const int n = n0 + c0;
+          // residual row segment: 64 contiguous bytes per thread -> four 16-byte loads (one request per row and
+          // instruction instead of sixteen scalar ones; this thread-per-row epilogue is LSU-wavefront bound)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += v2[i];
+          float* rs = v2;                                    // the cross-term registers are free again
+          if (p.res) {
+            const float* rp = p.res + (long long)m * p.ldres + n;
+            if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(rp + i));
+                rs[i] = t.x; rs[i + 1] = t.y; rs[i + 2] = t.z; rs[i + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) rs[i] = __ldg(rp + i);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a = v[i] + v2[i];
+            float a = v[i];
             if (p.bias) a += __ldg(p.bias + n + i);
             if (p.res_after_act) a = apply_act(a, p.act);
-            if (p.res) a += __ldg(p.res + (long long)m * p.ldres + n + i);
+            if (p.res) a += rs[i];
             if (!p.res_after_act) a = apply_act(a, p.act);
             v[i] = a;
           }

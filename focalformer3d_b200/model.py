@@ -295,6 +295,168 @@ class SECONDFPN(ParamTree):
         return out
 
 
+@BACKBONES.register_module()
+class ResNet(ParamTree):
+    """[upstream] mmdet 2.14 ResNet-50 (style 'pytorch', norm_eval) as configured at DeformFormer3D_C_R50.py
+    img_backbone and called from focalformer3d.py:133-153.  BatchNorm folded; every conv is one implicit-GEMM launch
+    with the ReLU / residual in its epilogue."""
+
+    STAGES = ((64, 3), (128, 4), (256, 6), (512, 3))
+
+    def __init__(self, depth=50, num_stages=4, out_indices=(0, 1, 2, 3), style="pytorch", spec=None, **kw):
+        super().__init__()
+        if depth != 50 or style != "pytorch" or num_stages != 4:
+            raise NotImplementedError("ResNet: only depth 50, style 'pytorch' is built (DeformFormer3D_C_R50)")
+        self.out_indices = tuple(out_indices)
+        self.build_params(spec)
+        self.pk = None
+
+    def prepare(self, dev):
+        sd = self.flat()
+
+        def cb(conv, bn, pad_cin=None):
+            w = sd[conv + ".weight"]
+            s, b = bn_scale_shift(sd, bn, 1e-5)
+            if pad_cin:
+                w = torch.cat([w, w.new_zeros(w.shape[0], pad_cin - w.shape[1], *w.shape[2:])], 1)
+            return pack_conv2d(w, s, dev), vec(b, dev)
+        pk = {"stem": cb("conv1", "bn1", pad_cin=8)}
+        for li, (planes, blocks) in enumerate(self.STAGES, start=1):
+            for b in range(blocks):
+                q = f"layer{li}.{b}"
+                pk[q] = [cb(f"{q}.conv{n}", f"{q}.bn{n}") for n in (1, 2, 3)]
+                if b == 0:
+                    pk[q].append(cb(f"{q}.downsample.0", f"{q}.downsample.1"))
+        self.pk = pk
+
+    def forward(self, x):
+        """x [n, H, W, 8] NHWC (3 image channels + zero padding).  Returns the four stage outputs (NHWC)."""
+        n, H, W, _ = x.shape
+        dev = x.device
+
+        def new(h, w, c):
+            return torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+        Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        y = new(Ho, Wo, 64)
+        ops.conv2d(x, *self.pk["stem"], y, 7, stride=2, pad=3, act=ACT_RELU)
+        x = ops.maxpool3x3s2(y)
+        outs = []
+        for li, (planes, blocks) in enumerate(self.STAGES, start=1):
+            for b in range(blocks):
+                layers = self.pk[f"layer{li}.{b}"]
+                st = 2 if (b == 0 and li > 1) else 1
+                _, H, W, _ = x.shape
+                Ho, Wo = (H + 2 - 3) // st + 1, (W + 2 - 3) // st + 1
+                t1 = new(H, W, planes)
+                ops.conv2d(x, *layers[0], t1, 1, act=ACT_RELU)
+                t2 = new(Ho, Wo, planes)
+                ops.conv2d(t1, *layers[1], t2, 3, stride=st, act=ACT_RELU)
+                if b == 0:
+                    idn = new(Ho, Wo, planes * 4)
+                    ops.conv2d(x, *layers[3], idn, 1, stride=st, pad=0, act=ACT_NONE)
+                else:
+                    idn = x
+                y = new(Ho, Wo, planes * 4)
+                ops.conv2d(t2, *layers[2], y, 1, act=ACT_RELU, res=idn)
+                x = y
+            if li - 1 in self.out_indices:
+                outs.append(x)
+        return outs
+
+
+@NECKS.register_module()
+class FPN(ParamTree):
+    """[upstream] mmdet 2.14 FPN (no norm / activation).  Only level 0 is consumed downstream
+    (focalformer3d.py:186 passes img_feats[0]), so only fpn_convs[0] is evaluated; the other fpn_convs tensors are
+    accepted from the checkpoint and unused."""
+
+    def __init__(self, in_channels, out_channels, num_outs, spec=None, **kw):
+        super().__init__()
+        self.in_channels, self.out_channels = list(in_channels), out_channels
+        self.build_params(spec)
+        self.pk = None
+
+    def prepare(self, dev):
+        sd = self.flat()
+        self.pk = dict(
+            lat=[(pack_conv2d(sd[f"lateral_convs.{i}.conv.weight"], None, dev), vec(sd[f"lateral_convs.{i}.conv.bias"], dev))
+                 for i in range(len(self.in_channels))],
+            out0=(pack_conv2d(sd["fpn_convs.0.conv.weight"], None, dev), vec(sd["fpn_convs.0.conv.bias"], dev)))
+
+    def forward(self, xs):
+        lat = []
+        for x, (w, b) in zip(xs, self.pk["lat"]):
+            n, H, W, _ = x.shape
+            y = torch.empty((n, H, W, self.out_channels), dtype=torch.float32, device=x.device)
+            ops.conv2d(x, w, b, y, 1, act=ACT_NONE)
+            lat.append(y)
+        for i in range(len(lat) - 1, 0, -1):
+            ops.upsample_add(lat[i - 1], lat[i])
+        out = torch.empty_like(lat[0])
+        ops.conv2d(lat[0], *self.pk["out0"], out, 3, act=ACT_NONE)
+        return out
+
+
+class LiftSplatShoot:
+    """models/necks/lss.py:149-383 at test time: depthnet 1x1 -> fused soft-max / lift / splat kernel -> bevencode."""
+
+    CAM_C, LD = 64, 128
+
+    def __init__(self, sd, prefix, pc_range, grid, hidden, dev):
+        import numpy as np
+        f32 = np.float32
+        self.frustum = sd[prefix + ".frustum"].detach().float().contiguous().to(dev)
+        self.D, self.fH, self.fW = self.frustum.shape[:3]
+        # gen_dx_bx (lss.py:77-82) in the fp32 arithmetic torch.Tensor([...]) gives the reference
+        lows, highs = pc_range[:3], pc_range[3:]
+        self.dx = [f32(grid)] * 3
+        bx = [f32(lo + grid / 2.0) for lo in lows]
+        self.lo = [f32(b) - f32(d) / f32(2.0) for b, d in zip(bx, self.dx)]
+        self.nxyz = [int((hi - lo) / grid) for lo, hi in zip(lows, highs)]
+        D, Cc = self.D, self.CAM_C
+        w = sd[prefix + ".camencode.depthnet.weight"].double().reshape(D + Cc, -1)
+        b = sd[prefix + ".camencode.depthnet.bias"].double()
+        order = list(range(D, D + Cc)) + list(range(D))                       # context first (16-byte aligned), then depth
+        wp = torch.zeros((self.LD, w.shape[1]), dtype=torch.float64)
+        wp[:D + Cc] = w[order]
+        self.depthnet = (pack_linear(wp, None, dev), vec(b[order], dev, self.LD))
+        Z = self.nxyz[2]
+        self.bevenc = []
+        for i in range(4):
+            wc = sd[f"{prefix}.bevencode.{3 * i}.weight"]
+            s, sh = bn_scale_shift(sd, f"{prefix}.bevencode.{3 * i + 1}", 1e-5)
+            if i == 0:
+                # reference channel order after the s2c reshape is c*Z + z; the splat kernel writes z*64 + c
+                co, ci, kh, kw = wc.shape
+                wc = wc.view(co, Cc, Z, kh, kw).permute(0, 2, 1, 3, 4).reshape(co, ci, kh, kw)
+            co = wc.shape[0]
+            co_pad = -(-co // 128) * 128
+            if co_pad != co and co > 128:
+                # 832 output channels would tile as 13 x 64 and re-gather the A operand 13 times; 7 x 128 with 64 zero
+                # channels is ~4x faster on the tensor-core kernel.  The next conv reads the [:co] channel slice.
+                wc = wc.double() * s.view(-1, 1, 1, 1)
+                wc = torch.cat([wc, wc.new_zeros(co_pad - co, *wc.shape[1:])], 0)
+                self.bevenc.append((pack_conv2d(wc, None, dev), vec(sh, dev, co_pad), co))
+            else:
+                self.bevenc.append((pack_conv2d(wc, s, dev), vec(sh, dev), co))
+
+    def __call__(self, feat, rots, trans, B, out):
+        """feat [B*cams, fH, fW, 256]; rots [B*cams, 9]; trans [B*cams, 3]; out [B, ny, nx, hidden] view."""
+        n_img, fH, fW, _ = feat.shape
+        dev = feat.device
+        dn = torch.empty((n_img, fH, fW, self.LD), dtype=torch.float32, device=dev)
+        ops.conv2d(feat, *self.depthnet, dn, 1, act=ACT_NONE)
+        nx, ny, nz = self.nxyz
+        bev = torch.empty((B, ny, nx, nz * self.CAM_C), dtype=torch.float32, device=dev)
+        ops.lss_splat(dn, self.frustum, rots, trans, bev, n_img // B, self.D, self.lo, self.dx)
+        x = bev
+        for i, (w, b, co) in enumerate(self.bevenc):
+            y = out if i == 3 else torch.empty((B, ny, nx, w.shape[-1]), dtype=torch.float32, device=dev)
+            ops.conv2d(x, w, b, y, 3, act=ACT_RELU)
+            x = y[..., :co]
+        return out, dn, bev
+
+
 class _IR:
     """torchvision InvertedResidual (focal_encoder.py:36-38) packed: optional 1x1 expand, dw3x3, 1x1 project."""
 
@@ -333,9 +495,12 @@ class FocalEncoder(ParamTree):
                  input_pts=True, iterbev_wo_img=False, extra_feat=False, iter_bev_cam=False, cam_lss=False,
                  newbevpool=False, pc_range=None, img_scale=None, spec=None, **kw):
         super().__init__()
-        if input_img or not input_pts or iterbev != "bevfusionmb2" or not iterbev_wo_img:
-            raise NotImplementedError("FocalEncoder: only the LiDAR-only bevfusionmb2 path is built (SURVEY.md 8f: "
-                                      "camera/fusion branches are the next scope row)")
+        self.camera_only = bool(input_img and cam_lss and cam_lss != "proj" and not input_pts and not num_layers
+                                and not multistage_heatmap)
+        if not self.camera_only and (input_img or not input_pts or iterbev != "bevfusionmb2" or not iterbev_wo_img):
+            raise NotImplementedError("FocalEncoder: built paths are LiDAR-only bevfusionmb2 and camera-only "
+                                      "Lift-Splat-Shoot (SURVEY.md 8f: LiDAR+camera fusion is the next scope row)")
+        self.pc_range, self.img_scale = pc_range, img_scale
         self.num_layers = num_layers or 0
         self.hidden = hidden_channel
         self.multistage_heatmap, self.extra_feat = multistage_heatmap, extra_feat
@@ -344,6 +509,9 @@ class FocalEncoder(ParamTree):
 
     def prepare(self, dev):
         sd = self.flat()
+        if self.camera_only:
+            self.pk = {"lss": LiftSplatShoot(sd, "cam_lss", list(self.pc_range), 0.6, self.hidden, dev)}   # :129-131
+            return
         pk = {"shared": (pack_conv2d(sd["shared_conv_pts.weight"], None, dev), vec(sd["shared_conv_pts.bias"], dev))}
         for i in range(self.num_layers):
             q = f"fusion_blocks.{i}"
@@ -352,6 +520,22 @@ class FocalEncoder(ParamTree):
             s, b = bn_scale_shift(sd, "extra_output.bn", 1e-5)
             pk["extra"] = (pack_conv2d(sd["extra_output.conv.weight"], s, dev), vec(b, dev))
         self.pk = pk
+
+    @staticmethod
+    def camera_rots_trans(img_metas, dev):
+        """focal_encoder.py:178-194: per camera inverse(lidar2img) -> rotation [B*N, 9] and translation [B*N, 3].
+        36 4x4 inverses: done on the host (LAPACK), uploaded once per call."""
+        mats = torch.stack([torch.as_tensor(m["lidar2img"], dtype=torch.float32).reshape(-1, 4, 4) for m in img_metas])
+        inv = torch.inverse(mats.cpu())
+        rots = inv[..., :3, :3].reshape(-1, 9).contiguous().to(dev)
+        trans = inv[..., :3, 3].reshape(-1, 3).contiguous().to(dev)
+        return rots, trans
+
+    def forward_camera(self, img_feat, img_metas, out):
+        """img_feat [B*N, fH, fW, 256] (FPN level 0) -> out [B, ny, nx, hidden]; returned twice by the reference
+        (focal_encoder.py:196-197: conv_feat and decoder feature are the same tensor)."""
+        rots, trans = self.camera_rots_trans(img_metas, img_feat.device)
+        return self.pk["lss"](img_feat, rots, trans, len(img_metas), out)
 
     def forward(self, pts_feats, extra_out=None):
         """pts_feats [B,H,W,512] NHWC.  Returns (conv_feat view, [stage feature views...], extra view)."""
@@ -697,12 +881,23 @@ class FocalFormer3D(nn.Module):
                  pts_neck=None, imgpts_neck=None, pts_bbox_head=None, train_cfg=None, test_cfg=None, input_img=True,
                  input_pts=True, img_backbone=None, img_neck=None, **unused):
         super().__init__()
-        if input_img or not input_pts or img_backbone is not None:
-            raise NotImplementedError("FocalFormer3D: camera / fusion configs are the next scope row (SURVEY.md 8f)")
+        if input_img and input_pts:
+            raise NotImplementedError("FocalFormer3D: LiDAR+camera fusion configs are the next scope row (SURVEY.md 8f)")
+        self.input_img, self.input_pts = bool(input_img), bool(input_pts)
         cfg = dict(pts_voxel_layer=pts_voxel_layer, pts_voxel_encoder=pts_voxel_encoder,
                    pts_middle_encoder=pts_middle_encoder, pts_backbone=pts_backbone, pts_neck=pts_neck,
-                   imgpts_neck=imgpts_neck, pts_bbox_head=pts_bbox_head, test_cfg=test_cfg)
+                   imgpts_neck=imgpts_neck, pts_bbox_head=pts_bbox_head, test_cfg=test_cfg, input_img=input_img,
+                   input_pts=input_pts, img_backbone=img_backbone, img_neck=img_neck)
         spec = param_spec(cfg)
+        tcfg = test_cfg["pts"] if (test_cfg and "pts" in test_cfg) else test_cfg
+        self._prepared_on = None
+        if self.input_img:
+            # camera-only (DeformFormer3D_C_R50): focalformer3d.py:133-153 image tower, no LiDAR tower is built
+            self.img_backbone = BACKBONES.build(img_backbone, spec=sub_spec(spec, "img_backbone"))
+            self.img_neck = NECKS.build(img_neck, spec=sub_spec(spec, "img_neck"))
+            self.imgpts_neck = NECKS.build(imgpts_neck, spec=sub_spec(spec, "imgpts_neck"), input_img=True)
+            self.pts_bbox_head = HEADS.build(pts_bbox_head, spec=sub_spec(spec, "pts_bbox_head"), test_cfg=tcfg)
+            return
         self.voxel_cfg = dict(pts_voxel_layer)
         self.pts_voxel_encoder = VOXEL_ENCODERS.build(pts_voxel_encoder, spec=sub_spec(spec, "pts_voxel_encoder"))
         self.pts_middle_encoder = MIDDLE_ENCODERS.build(pts_middle_encoder, spec=sub_spec(spec, "pts_middle_encoder"))
@@ -710,9 +905,7 @@ class FocalFormer3D(nn.Module):
         self.pts_backbone = BACKBONES.build(pts_backbone, spec=sub_spec(spec, "pts_backbone"), in_depth=depth)
         self.pts_neck = NECKS.build(pts_neck, spec=sub_spec(spec, "pts_neck"))
         self.imgpts_neck = NECKS.build(imgpts_neck, spec=sub_spec(spec, "imgpts_neck"))
-        tcfg = test_cfg["pts"] if (test_cfg and "pts" in test_cfg) else test_cfg
         self.pts_bbox_head = HEADS.build(pts_bbox_head, spec=sub_spec(spec, "pts_bbox_head"), test_cfg=tcfg)
-        self._prepared_on = None
 
     @staticmethod
     def _bev_depth(me):
@@ -726,8 +919,7 @@ class FocalFormer3D(nn.Module):
     def prepare(self, device="cuda"):
         """Fold BatchNorm, pack weights into kernel layouts on the device (call after load_state_dict)."""
         dev = torch.device(device)
-        for m in (self.pts_voxel_encoder, self.pts_middle_encoder, self.pts_backbone, self.pts_neck, self.imgpts_neck,
-                  self.pts_bbox_head):
+        for m in self.children():
             if hasattr(m, "prepare"):
                 m.prepare(dev)
         self._prepared_on = dev
@@ -735,10 +927,46 @@ class FocalFormer3D(nn.Module):
 
     # ---- the hot path
     @torch.no_grad()
-    def forward_raw(self, points, keep_stages=False):
+    def forward_camera(self, img, img_metas, keep_stages=False):
+        """img [B, N, 3, H, W] float32 (already normalised, as the test pipeline hands it to simple_test);
+        img_metas: list[B] of dict(lidar2img=[N, 4, 4]).  focalformer3d.py:133-153,186 + focal_encoder.py:171-197."""
+        dev = self._prepared_on
+        B, N, Cc, H, W = img.shape
+        ops.mark("start")
+        x = ops.nchw_to_nhwc(img.to(dev, torch.float32).reshape(B * N, Cc, H, W).contiguous(), 8)
+        feats = self.img_backbone(x)
+        ops.mark("img_backbone")
+        f0 = self.img_neck(feats)
+        ops.mark("img_neck")
+        head = self.pts_bbox_head
+        lss = self.imgpts_neck.pk["lss"]
+        nx, ny, _ = lss.nxyz
+        geom = ops.LevelGeom([(ny >> l, nx >> l) for l in range(head.n_levels)])
+        ms_value = torch.empty((B, geom.n_tokens, head.hc), dtype=torch.float32, device=dev)
+        bev_feat = torch.empty((B, ny, nx, head.hc), dtype=torch.float32, device=dev)
+        _, dn, bev = self.imgpts_neck.forward_camera(f0, img_metas, bev_feat)
+        # the same tensor is the heatmap input and level 0 of the decoder's value pyramid (focal_encoder.py:196-197)
+        ms_value[:, :ny * nx].view(B, ny, nx, head.hc).copy_(bev_feat)
+        ops.mark("lift_splat+bevencode")
+        res = head(bev_feat, [], ms_value, geom)
+        det = head.get_bboxes()
+        ops.mark("heads+decode")
+        self._overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+        stages = None
+        if keep_stages:
+            stages = dict(img_nhwc=x, backbone=feats, img_feat=f0, depthnet=dn, bev=bev, conv_feat=bev_feat,
+                          ms_value=ms_value)
+        return res, det, stages
+
+    @torch.no_grad()
+    def forward_raw(self, points, keep_stages=False, img=None, img_metas=None):
         """points: list[B] of CUDA float32 [Ni, F].  Returns (head dict, (boxes, scores, labels, keep), stages)."""
         if self._prepared_on is None:
             raise RuntimeError("call model.prepare(device) after loading weights")
+        if self.input_img:
+            if img is None or img_metas is None:
+                raise ValueError("camera config: forward_raw needs img [B,N,3,H,W] and img_metas with 'lidar2img'")
+            return self.forward_camera(img, img_metas, keep_stages)
         dev = self._prepared_on
         B = len(points)
         offs = [0]
@@ -786,7 +1014,7 @@ class FocalFormer3D(nn.Module):
 
     def simple_test(self, points, img_metas=None, img=None, rescale=False):
         """Reference signature (focalformer3d.py:321): list of dict(pts_bbox=dict(boxes_3d, scores_3d, labels_3d)) on CPU."""
-        _, (boxes, scores, labels, keep), _ = self.forward_raw(points)
+        _, (boxes, scores, labels, keep), _ = self.forward_raw(points, img=img, img_metas=img_metas)
         if int(self._overflow.item()):
             raise RuntimeError("sparse encoder level capacity exceeded; raise SparseEncoder.cap_growth")
         out = []

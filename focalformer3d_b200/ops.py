@@ -266,6 +266,60 @@ def add_bcast_rows(a, p, out):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------------------
+# camera branch
+def nchw_to_nhwc(img, ld):
+    """[n, C, H, W] fp32 CUDA -> [n, H, W, ld] (zero channel padding)."""
+    _chk_f32(img, "nchw_to_nhwc.img")
+    n, Cc, H, W = img.shape
+    out = torch.empty((n, H, W, ld), dtype=torch.float32, device=img.device)
+    t0 = prof.begin()
+    check(lib.ff3d_nchw_to_nhwc(_ptr(img), _ptr(out), n, Cc, H, W, ld, _stream()), "ff3d_nchw_to_nhwc")
+    prof.end(t0, "nchw_to_nhwc", 0.0, 4.0 * n * H * W * (Cc + ld))
+    _count()
+    return out
+
+
+def maxpool3x3s2(x):
+    _chk_f32(x, "maxpool.x")
+    n, H, W, Cc = x.shape
+    out = torch.empty((n, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.float32, device=x.device)
+    t0 = prof.begin()
+    check(lib.ff3d_maxpool3x3s2(_ptr(x), _ptr(out), n, H, W, Cc, _stream()), "ff3d_maxpool3x3s2")
+    prof.end(t0, "maxpool3x3s2", 0.0, 4.0 * (x.numel() + out.numel()))
+    _count()
+    return out
+
+
+def upsample_add(dst, src):
+    """dst [n,Hd,Wd,C] += nearest-upsampled src [n,Hs,Ws,C] (in place)."""
+    _chk_f32(dst, "upsample_add.dst")
+    _chk_f32(src, "upsample_add.src")
+    n, Hd, Wd, Cc = dst.shape
+    _, Hs, Ws, _ = src.shape
+    t0 = prof.begin()
+    check(lib.ff3d_upsample_add(_ptr(dst), _ptr(src), n, Hd, Wd, Hs, Ws, Cc, _stream()), "ff3d_upsample_add")
+    prof.end(t0, "upsample_add", 0.0, 4.0 * (2 * dst.numel() + src.numel()))
+    _count()
+    return dst
+
+
+def lss_splat(dn, frustum, rots, trans, bev, cams, D, lo, dx):
+    """dn [B*cams, fH, fW, ld] (64 context | D depth logits); bev [B, ny, nx, nz*64] is zeroed and filled."""
+    _chk_f32(dn, "lss_splat.dn")
+    _chk_f32(bev, "lss_splat.bev")
+    n_img, fH, fW, ld = dn.shape
+    B, ny, nx, cz = bev.shape
+    lo3 = (C.c_float * 3)(*[float(v) for v in lo])
+    dx3 = (C.c_float * 3)(*[float(v) for v in dx])
+    t0 = prof.begin()
+    check(lib.ff3d_lss_splat(_ptr(dn), ld, _ptr(frustum), _ptr(rots), _ptr(trans), _ptr(bev), B, cams, D, fH, fW, lo3, dx3,
+                             nx, ny, cz // 64, _stream()), "ff3d_lss_splat")
+    prof.end(t0, "lss_splat", 2.0 * n_img * fH * fW * D * 64, 4.0 * (dn.numel() + bev.numel() + n_img * fH * fW * D * 64))
+    _count(2)
+    return bev
+
+
 def voxelize(points, batch_offsets, voxel_size, pc_range, max_points, max_voxels, mean_ld=8, want_voxels=False):
     """points [N, F] (samples concatenated), batch_offsets python list [B+1].
     Returns dict(coors [cap,4], num_points [cap], mean [cap, mean_ld], n_dev [1+B] (total, per sample), voxels?)."""

@@ -32,9 +32,61 @@ def _inverted_residual(spec, name, cin, cout, expand):
     _bn(spec, f"{name}.conv.{i + 2}", cout)
 
 
+def _resnet50_spec(s, p):
+    """[upstream] mmdet ResNet-50 (torchvision key names)."""
+    s[f"{p}.conv1.weight"] = ((64, 3, 7, 7), ("w_img", 3 * 49))
+    _bn(s, f"{p}.bn1", 64)
+    inpl = 64
+    for li, (planes, blocks) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        for b in range(blocks):
+            q = f"{p}.layer{li}.{b}"
+            s[f"{q}.conv1.weight"] = ((planes, inpl, 1, 1), ("w", inpl))
+            _bn(s, f"{q}.bn1", planes)
+            s[f"{q}.conv2.weight"] = ((planes, planes, 3, 3), ("w", planes * 9))
+            _bn(s, f"{q}.bn2", planes)
+            s[f"{q}.conv3.weight"] = ((planes * 4, planes, 1, 1), ("w_res", planes))
+            _bn(s, f"{q}.bn3", planes * 4)
+            if b == 0:
+                s[f"{q}.downsample.0.weight"] = ((planes * 4, inpl, 1, 1), ("w", inpl))
+                _bn(s, f"{q}.downsample.1", planes * 4)
+            inpl = planes * 4
+
+
+def camera_param_spec(model_cfg, s):
+    """Image branch + Lift-Splat-Shoot tensors (camera configs: focalformer3d.py:133-153, lss.py:149-210)."""
+    if model_cfg.get("img_backbone"):
+        assert model_cfg["img_backbone"]["depth"] == 50
+        _resnet50_spec(s, "img_backbone")
+    nk = model_cfg.get("img_neck")
+    if nk:
+        oc = nk["out_channels"]
+        for i, ci in enumerate(nk["in_channels"]):
+            s[f"img_neck.lateral_convs.{i}.conv.weight"] = ((oc, ci, 1, 1), ("w", ci))
+            s[f"img_neck.lateral_convs.{i}.conv.bias"] = ((oc,), "b")
+            s[f"img_neck.fpn_convs.{i}.conv.weight"] = ((oc, oc, 3, 3), ("w", oc * 9))
+            s[f"img_neck.fpn_convs.{i}.conv.bias"] = ((oc,), "b")
+    ne = model_cfg["imgpts_neck"]
+    if ne.get("cam_lss"):
+        H, W = ne["img_scale"]
+        fH, fW = H // 4, W // 4
+        D, camC, hc = 41, 64, ne["hidden_channel"]
+        r = ne["pc_range"]
+        cz = int(camC * ((r[5] - r[2]) // 0.6))
+        q = "imgpts_neck.cam_lss"
+        s[f"{q}.frustum"] = ((D, fH, fW, 3), ("frustum", (H, W, fH, fW)))
+        s[f"{q}.camencode.depthnet.weight"] = ((D + camC, 256, 1, 1), ("w", 256))
+        s[f"{q}.camencode.depthnet.bias"] = ((D + camC,), "b")
+        for i, (ci, co) in enumerate(((cz, cz), (cz, 512), (512, 512), (512, hc))):
+            s[f"{q}.bevencode.{3 * i}.weight"] = ((co, ci, 3, 3), ("w_bev" if i == 0 else "w", ci * 9))
+            _bn(s, f"{q}.bevencode.{3 * i + 1}", co)
+
+
 def param_spec(model_cfg):
-    """name -> (shape, init kind) for every tensor of the reference state dict (LiDAR-only configs)."""
+    """name -> (shape, init kind) for every tensor of the reference state dict."""
     s = {}
+    camera_param_spec(model_cfg, s)
+    if not model_cfg.get("input_pts", True):          # camera-only (DeformFormer3D_C_R50): no LiDAR tower
+        return _head_spec(model_cfg, s)
     ve = model_cfg["pts_voxel_encoder"]
     me = model_cfg["pts_middle_encoder"]
     if ve["type"] == "HardVFE":
@@ -85,9 +137,15 @@ def param_spec(model_cfg):
         else:
             s[f"pts_neck.deblocks.{i}.0.weight"] = ((c, ci, 1, 1), ("w", ci))
         _bn(s, f"pts_neck.deblocks.{i}.1", c)
+    return _head_spec(model_cfg, s)
+
+
+def _head_spec(model_cfg, s):
     # --- FocalEncoder
     ne = model_cfg["imgpts_neck"]
     hc = ne["hidden_channel"]
+    if not ne.get("input_pts", True):
+        return _decoder_spec(model_cfg, s)
     s["imgpts_neck.shared_conv_pts.weight"] = ((hc, ne["in_channels_pts"], 3, 3), ("w", ne["in_channels_pts"] * 9))
     s["imgpts_neck.shared_conv_pts.bias"] = ((hc,), "b")
     for i in range(ne["num_layers"] or 0):
@@ -97,6 +155,10 @@ def param_spec(model_cfg):
     if ne.get("extra_feat"):
         s["imgpts_neck.extra_output.conv.weight"] = ((hc, hc, 3, 3), ("w", hc * 9))
         _bn(s, "imgpts_neck.extra_output.bn", hc)
+    return _decoder_spec(model_cfg, s)
+
+
+def _decoder_spec(model_cfg, s):
     # --- FocalDecoder
     hd = model_cfg["pts_bbox_head"]
     h = "pts_bbox_head"
@@ -188,9 +250,18 @@ def make_state_dict(model_cfg, seed=0):
         if kind == "count":
             sd[name] = torch.zeros((), dtype=torch.long)
             continue
+        if isinstance(kind, tuple) and kind[0] == "frustum":
+            H, W, fH, fW = kind[1]                     # lss.py:215-226 (not random: it is geometry)
+            ds = torch.arange(4.0, 45.0, 1.0).view(-1, 1, 1).expand(-1, fH, fW)
+            D = ds.shape[0]
+            xs = torch.linspace(0, W - 1, fW).view(1, 1, fW).expand(D, fH, fW)
+            ys = torch.linspace(0, H - 1, fH).view(1, fH, 1).expand(D, fH, fW)
+            sd[name] = torch.stack((xs, ys, ds), -1).contiguous()
+            continue
         if isinstance(kind, tuple):
             k, fan = kind
-            gain = {"w": 1.0, "w_small": 0.5, "spw": 1.2, "spw_in": 1.2, "w_in": 1.0}[k]
+            gain = {"w": 1.0, "w_small": 0.5, "spw": 1.2, "spw_in": 1.2, "w_in": 1.0, "w_img": 1.0, "w_res": 0.3,
+                    "w_bev": 4.0}[k]
             t = torch.randn(shape, generator=g) * (gain / math.sqrt(fan))
             if k == "w_in":              # HardVFE linear [C, F] on raw point features
                 t[:, :3] /= 20.0
@@ -254,3 +325,25 @@ def synth_points(n_points, pc_range, seed=0, n_sweeps=10, n_beams=32, n_features
     m = ((pts[:, 0] > r[0]) & (pts[:, 0] < r[3]) & (pts[:, 1] > r[1]) & (pts[:, 1] < r[4])
          & (pts[:, 2] > r[2]) & (pts[:, 2] < r[5]))
     return np.ascontiguousarray(pts[m])
+
+
+def synth_cameras(n_cams=6, img_hw=(448, 800), seed=0):
+    """Seeded pinhole rig: n cameras at yaw k*360/n, focal ~0.79 * W, 1.5 m up, looking outwards.
+    Returns lidar2img [n, 4, 4] float32 (pixel = K [R|t] X_lidar, homogeneous, z forward)."""
+    rng = np.random.default_rng(seed)
+    H, W = img_hw
+    f = 0.79 * W
+    K = np.array([[f, 0, W / 2.0, 0], [0, f, H / 2.0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float64)
+    mats = []
+    for k in range(n_cams):
+        yaw = 2 * np.pi * k / n_cams + rng.normal(0, 0.01)
+        # camera axes in the lidar frame: z forward (cos yaw, sin yaw, 0), x right, y down
+        fwd = np.array([np.cos(yaw), np.sin(yaw), 0.0])
+        right = np.array([np.sin(yaw), -np.cos(yaw), 0.0])
+        down = np.array([0.0, 0.0, -1.0])
+        R = np.stack([right, down, fwd])                     # lidar -> camera rotation
+        t = -R @ np.array([0.3 * np.cos(yaw), 0.3 * np.sin(yaw), 1.5])
+        E = np.eye(4)
+        E[:3, :3], E[:3, 3] = R, t
+        mats.append(K @ E)
+    return np.stack(mats).astype(np.float32)

@@ -219,6 +219,26 @@ int ff3d_box_decode(const float* pred, int ldp, int cls_col, int has_vel, const 
                     const float* post_range6, float* boxes, float* scores, int* labels, unsigned char* keep,
                     ff3d_stream_t stream);
 
+/* ---- camera branch (DeformFormer3D_C_R50) -------------------------------------------------
+ * Image repack for the NHWC convolution path: x [n, C, H, W] planar (what extract_img_feat receives,
+ * focalformer3d.py:133-141) -> y [n, H, W, ld], channels [C, ld) zero (ld % 4 == 0). */
+int ff3d_nchw_to_nhwc(const float* x, float* y, int n, int C, int H, int W, int ld, ff3d_stream_t stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) of the ResNet stem ([upstream] mmdet ResNet.maxpool): x [n,H,W,C] ->
+ * y [n, (H-1)/2+1, (W-1)/2+1, C]. */
+int ff3d_maxpool3x3s2(const float* x, float* y, int n, int H, int W, int C, ff3d_stream_t stream);
+/* FPN top-down step ([upstream] mmdet FPN.forward: laterals[i-1] += F.interpolate(laterals[i], size, 'nearest')):
+ * dst [n,Hd,Wd,C] += src [n,Hs,Ws,C] at (min(floor(y*Hs/Hd),Hs-1), min(floor(x*Ws/Wd),Ws-1)). */
+int ff3d_upsample_add(float* dst, const float* src, int n, int Hd, int Wd, int Hs, int Ws, int C, ff3d_stream_t stream);
+/* Lift-Splat-Shoot lift + splat (lss.py:126-146 CamEncode soft-max / outer product, :228-271 get_geometry without
+ * augmentation matrices, :324-362 voxel_pooling, :373-377 s2c) in one pass, no [B,N,D,H,W,C] volume in HBM.
+ *   dn      [B*cams, fH, fW, ld] depthnet output, columns [0,64) context features, [64, 64+D) depth logits
+ *   frustum [D, fH, fW, 3] (u, v, depth) as stored in the checkpoint;  rots [B*cams, 9], trans [B*cams, 3]
+ *   bev     [B, ny, nx, nz*64] (zeroed here), channel = z*64 + c; cell = trunc((R (u d, v d, d) + t - lo) / dx)
+ * Cell indices are bit-exact w.r.t. the oracle; per-cell sums are atomics (fp32 addition order is not fixed). */
+int ff3d_lss_splat(const float* dn, int ld, const float* frustum, const float* rots, const float* trans, float* bev,
+                   int B, int cams, int D, int fH, int fW, const float* lo3, const float* dx3, int nx, int ny, int nz,
+                   ff3d_stream_t stream);
+
 /* Misc elementwise helpers used by the head glue (all fp32). */
 int ff3d_add_rows(const float* a, const float* b, float* y, long long n, ff3d_stream_t stream);
 /* y[b, r, :] = a[b, r, :] + p[r, :]   (value + cached BEV positional embedding, focal_decoder.py:886) */

@@ -23,7 +23,18 @@ class FocalFormer3D(nn.Module):
                  pts_neck=None, imgpts_neck=None, pts_bbox_head=None, train_cfg=None, test_cfg=None,
                  input_img=True, input_pts=True, **unused):
         super().__init__()
-        assert not input_img and input_pts, "oracle covers the LiDAR-only configs"
+        self.input_img, self.input_pts = input_img, input_pts
+        head = _strip(pts_bbox_head)
+        head["test_cfg"] = test_cfg["pts"] if test_cfg and "pts" in test_cfg else test_cfg
+        if input_img:
+            # camera-only (DeformFormer3D_C_R50): focalformer3d.py:133-153 + focal_encoder.py:171-197
+            assert not input_pts, "oracle covers LiDAR-only and camera-only configs (fusion is the next scope row)"
+            from .camera import ResNet50, FPN, CameraFocalEncoder
+            self.img_backbone = ResNet50(**unused.get("img_backbone", {}))
+            self.img_neck = FPN(**_strip(unused["img_neck"]))
+            self.imgpts_neck = CameraFocalEncoder(**_strip(imgpts_neck))
+            self.pts_bbox_head = FocalDecoder(**head)
+            return
         self.voxel_cfg = pts_voxel_layer
         ve = _strip(pts_voxel_encoder)
         if pts_voxel_encoder["type"] == "HardSimpleVFE":
@@ -34,8 +45,6 @@ class FocalFormer3D(nn.Module):
         self.pts_backbone = SECOND(**_strip(pts_backbone))
         self.pts_neck = SECONDFPN(**_strip(pts_neck))
         self.imgpts_neck = FocalEncoder(**_strip(imgpts_neck))
-        head = _strip(pts_bbox_head)
-        head["test_cfg"] = test_cfg["pts"] if test_cfg and "pts" in test_cfg else test_cfg
         self.pts_bbox_head = FocalDecoder(**head)
 
     def voxelize(self, points):
@@ -63,10 +72,19 @@ class FocalFormer3D(nn.Module):
         return x
 
     @torch.no_grad()
-    def forward_raw(self, points, stages=None):
-        """points: list[B] of [Ni, F] -> (head output dict, list of per-scene result dicts)."""
-        pts_feats = self.extract_pts_feat(points, stages)
-        _, new_pts = self.imgpts_neck(None, pts_feats[0], None)
+    def forward_raw(self, points, stages=None, img=None, img_metas=None):
+        """points: list[B] of [Ni, F] (or None for camera-only) -> (head output dict, list of per-scene result dicts).
+        img: [B, N, 3, H, W]; img_metas: list[B] of dict(lidar2img=[N, 4, 4])."""
+        if self.input_img:
+            B, N, C, H, W = img.shape
+            c = self.img_backbone(img.view(B * N, C, H, W).float())                          # focalformer3d.py:133-153
+            feats = self.img_neck(c)
+            if stages is not None:
+                stages["img_backbone"], stages["img_feat"] = c, feats[0]
+            _, new_pts = self.imgpts_neck(feats[0], None, img_metas)                          # only level 0 (:186)
+        else:
+            pts_feats = self.extract_pts_feat(points, stages)
+            _, new_pts = self.imgpts_neck(None, pts_feats[0], None)
         second = list(new_pts[1]) if isinstance(new_pts[1], (list, tuple)) else new_pts[1]
         if stages is not None:
             stages["conv_feat"] = new_pts[0]

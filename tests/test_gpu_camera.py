@@ -1,0 +1,203 @@
+"""Camera branch (DeformFormer3D_C_R50): kernel parity and end-to-end parity against the CPU
+oracle on a reduced image / BEV size.  Bars: Lift-Splat-Shoot voxel indices and the selected proposal indices
+bit-exact, feature maps / heatmaps / box regressions within 1e-3 (mixed abs/rel for unnormalised feature maps)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+IMG_HW = (64, 96)
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).cpu()
+
+
+def _close(a, b, what="", tol=TOL):
+    err = ((a - b).abs() / (1.0 + b.abs())).max().item()
+    assert err < tol, f"{what}: max mixed abs/rel err {err}"
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+def test_nchw_to_nhwc():
+    from focalformer3d_b200 import ops
+    x = torch.randn(5, 3, 13, 22, device="cuda")
+    y = ops.nchw_to_nhwc(x, 8)
+    assert torch.equal(y[..., :3], x.permute(0, 2, 3, 1))
+    assert torch.count_nonzero(y[..., 3:]).item() == 0
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (15, 25), (1, 1)])
+def test_maxpool(hw):
+    from focalformer3d_b200 import ops
+    x = torch.randn(3, hw[0], hw[1], 64, device="cuda") - 2.0        # mostly negative: a zero-padded pool would differ
+    y = ops.maxpool3x3s2(x)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2), 3, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("shapes", [((8, 12), (4, 6)), ((25, 13), (13, 7)), ((7, 5), (2, 3))])
+def test_upsample_add(shapes):
+    from focalformer3d_b200 import ops
+    (Hd, Wd), (Hs, Ws) = shapes
+    dst = torch.randn(2, Hd, Wd, 32, device="cuda")
+    src = torch.randn(2, Hs, Ws, 32, device="cuda")
+    ref = dst + F.interpolate(src.permute(0, 3, 1, 2), size=(Hd, Wd), mode="nearest").permute(0, 2, 3, 1)
+    ops.upsample_add(dst, src)
+    assert torch.equal(dst, ref)
+
+
+@pytest.mark.parametrize("k,stride,pad,cin,cout", [(7, 2, 3, 8, 64), (1, 2, 0, 64, 128), (3, 2, 1, 64, 64),
+                                                   (3, 1, 1, 832, 64), (1, 1, 0, 256, 128)])
+def test_resnet_conv_shapes(k, stride, pad, cin, cout):
+    """The conv geometries the image tower adds to the implicit-GEMM kernel (7x7/s2 stem with 8 padded channels,
+    strided 1x1 shortcut, strided 3x3, the 832-channel bevencode input)."""
+    from focalformer3d_b200 import ops
+    from focalformer3d_b200.model import pack_conv2d
+    g = torch.Generator().manual_seed(k * 100 + cin)
+    H, W = (37, 52) if cin <= 64 else (20, 24)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)).float()
+    pw = pack_conv2d(w, None, "cuda")
+    out = torch.empty((2, ref.shape[2], ref.shape[3], cout), device="cuda")
+    ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), pw, b.cuda(), out, k, stride=stride, pad=pad, act=ops.ACT_RELU)
+    # 3xTF32 with fp32 tensor-core accumulation: error grows with K (7488 for the 832-channel 3x3)
+    assert (_nchw(out) - ref).abs().max().item() < (2e-5 if cin * k * k < 2048 else 2e-4)
+
+
+def test_lss_splat_matches_oracle():
+    """Same depthnet output in, same pooled BEV out; voxel indices are validated through an indicator splat."""
+    from focalformer3d_b200 import ops
+    from focalformer3d_b200.synth import synth_cameras
+    from oracle.camera import LiftSplatShoot, lidar2img_to_rots_trans
+    B, N, (H, W) = 2, 6, IMG_HW
+    rng = [-7.2, -7.2, -5.0, 7.2, 7.2, 3.0]
+    lss = LiftSplatShoot(img_scale=(H, W), pc_range=rng, grid=0.6, inputC=256, outputC=128, camC=64, downsample=4)
+    D, fH, fW = lss.D, lss.fH, lss.fW
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(B * N, D + 64, fH, fW, generator=g) * 2.0            # oracle column order: depth | context
+    rt = [lidar2img_to_rots_trans(synth_cameras(N, (H, W), seed=b)) for b in range(B)]
+    rots, trans = torch.stack([r for r, _ in rt]), torch.stack([t for _, t in rt])
+    depth = logits[:, :D].softmax(1)
+    feat = (depth.unsqueeze(1) * logits[:, D:].unsqueeze(2)).view(B, N, 64, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    geom = lss.get_geometry(rots, trans)
+    vox = lss.voxel_pooling(geom, feat)                                       # [B, C, Z, X, Y]
+    Bv, Cv, Zv, Xv, Yv = vox.shape
+    ref = vox.permute(0, 4, 3, 2, 1).reshape(B, Yv, Xv, Zv * Cv)              # ours: [B, y, x, z*64 + c]
+    dn = torch.zeros(B * N, fH, fW, 128)
+    dn[..., :64] = logits[:, D:].permute(0, 2, 3, 1)
+    dn[..., 64:64 + D] = logits[:, :D].permute(0, 2, 3, 1)
+    bev = torch.empty((B, Yv, Xv, Zv * 64), device="cuda")
+    lo = (lss.bx - lss.dx / 2.0).tolist()
+    ops.lss_splat(dn.cuda(), lss.frustum.data.cuda(), rots.reshape(-1, 9).cuda(), trans.reshape(-1, 3).cuda(), bev, N, D,
+                  lo, lss.dx.tolist())
+    got = bev.cpu()
+    assert torch.equal(got != 0, ref != 0), "set of touched (cell, channel) differs: voxel indices are not bit-exact"
+    assert (got - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    # occupancy counts: context == 1, uniform depth -> every cell holds (#points in the cell) / D exactly-ish
+    dn2 = torch.zeros_like(dn)
+    dn2[..., :64] = 1.0
+    ops.lss_splat(dn2.cuda(), lss.frustum.data.cuda(), rots.reshape(-1, 9).cuda(), trans.reshape(-1, 3).cuda(), bev, N, D,
+                  lo, lss.dx.tolist())
+    idx = lss.voxel_indices(geom).view(B, -1, 3)
+    nx = lss.nx.tolist()
+    for b in range(B):
+        gi = idx[b]
+        kept = ((gi >= 0) & (gi < torch.tensor(nx))).all(1)
+        gi = gi[kept]
+        cnt = torch.zeros(nx[1], nx[0], nx[2])
+        cnt.index_put_((gi[:, 1], gi[:, 0], gi[:, 2]), torch.ones(gi.shape[0]), accumulate=True)
+        ours = bev[b].cpu().view(nx[1], nx[0], nx[2], 64)[..., 0] * D
+        assert torch.equal(ours.round(), cnt), "per-cell point counts differ"
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+@pytest.fixture(scope="module")
+def cam():
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_camera_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_cameras
+    from focalformer3d_b200.model import build_model
+    from oracle.detector import build_oracle
+    cfg = scaled_camera_cfg(load_config(default_config_path("deformformer3d_c_r50"))["model"], bev=24, img_hw=IMG_HW,
+                            num_proposals=16)
+    sd = make_state_dict(cfg, 4)
+    B = 2
+    img = torch.randn(B, 6, 3, *IMG_HW, generator=torch.Generator().manual_seed(5))
+    metas = [dict(lidar2img=synth_cameras(6, IMG_HW, seed=b)) for b in range(B)]
+    model = build_model(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.prepare("cuda")
+    res, det, st = model.forward_raw(None, keep_stages=True, img=img.cuda(), img_metas=metas)
+    torch.cuda.synchronize()
+    oracle = build_oracle(cfg)
+    oracle.load_state_dict(sd, strict=True)
+    ost = {}
+    ref, rdet = oracle.forward_raw(None, ost, img=img, img_metas=metas)
+    return dict(model=model, res=res, det=det, st=st, oracle=oracle, ref=ref, rdet=rdet, ost=ost, img=img, metas=metas)
+
+
+def test_camera_image_tower(cam):
+    st, ost = cam["st"], cam["ost"]
+    for i, (a, b) in enumerate(zip(st["backbone"], ost["img_backbone"])):
+        _close(_nchw(a), b, f"ResNet-50 stage {i}")
+    _close(_nchw(st["img_feat"]), ost["img_feat"], "FPN level 0")
+
+
+def test_camera_lift_splat(cam):
+    st, lss = cam["st"], cam["oracle"].imgpts_neck.cam_lss
+    D = lss.D
+    depth = st["depthnet"][..., 64:64 + D].softmax(-1).permute(0, 3, 1, 2).cpu()
+    assert (depth - lss.debug["depth"]).abs().max().item() < 1e-4
+    pooled = lss.debug["pooled"]                                               # [B, c*Z+z, Y, X]
+    B, CZ, Y, X = pooled.shape
+    Z = CZ // 64
+    ours = st["bev"].view(B, Y, X, Z, 64).permute(0, 4, 3, 1, 2).reshape(B, CZ, Y, X).cpu()
+    assert ((ours != 0) != (pooled != 0)).float().mean().item() < 1e-5
+    _close(ours, pooled, "pooled BEV volume")
+    _close(_nchw(st["conv_feat"]), cam["ost"]["conv_feat"], "bevencode output")
+
+
+def test_camera_head(cam):
+    res, ref, oracle = cam["res"], cam["ref"], cam["oracle"]
+    dbg = oracle.pts_bbox_head.debug
+    for a, b in zip(res["dense_heatmap"], ref["dense_heatmap"]):
+        assert (a.cpu() - b).abs().max().item() < TOL
+    top, otop = res["_top_proposals"][0].cpu().long(), dbg["top_proposals"][0]
+    for b in range(top.shape[0]):
+        assert set(top[b].tolist()) == set(otop[b].tolist()), f"scene {b}: proposal sets differ"
+    pm, po = top.argsort(1), otop.argsort(1)
+    assert torch.equal(res["query_labels"].cpu().gather(1, pm), oracle.pts_bbox_head.query_labels.gather(1, po))
+    for key in ("center", "height", "dim", "rot", "vel", "heatmap"):
+        a, b = res[key].cpu(), ref[key]
+        aa = a.gather(2, pm[:, None].expand(-1, a.shape[1], -1))
+        bb = b.gather(2, po[:, None].expand(-1, b.shape[1], -1))
+        err = (aa - bb).abs().max().item()
+        assert err < TOL, f"{key}: max abs err {err}"
+
+
+def test_camera_final_boxes(cam):
+    boxes, scores, labels, keep = (t.cpu() for t in cam["det"])
+    top, otop = cam["res"]["_top_proposals"][0].cpu().long(), cam["oracle"].pts_bbox_head.debug["top_proposals"][0]
+    pm, po = top.argsort(1), otop.argsort(1)
+    for b, r in enumerate(cam["rdet"]):
+        ok = r["keep"]
+        assert torch.equal(keep[b][pm[b]].bool(), ok[po[b]])
+        assert r["boxes_3d"].shape[0] == int(ok.sum())
+        ref_boxes = torch.zeros(ok.shape[0], r["boxes_3d"].shape[1])
+        ref_scores, ref_labels = torch.zeros(ok.shape[0]), torch.zeros(ok.shape[0], dtype=torch.int32)
+        ref_boxes[ok], ref_scores[ok], ref_labels[ok] = r["boxes_3d"], r["scores_3d"], r["labels_3d"].int()
+        sel_m, sel_o = pm[b][keep[b][pm[b]].bool()], po[b][ok[po[b]]]
+        assert sel_m.numel() > 0
+        assert (boxes[b][sel_m] - ref_boxes[sel_o]).abs().max().item() < TOL
+        assert (scores[b][sel_m] - ref_scores[sel_o]).abs().max().item() < TOL
+        assert torch.equal(labels[b][sel_m].int(), ref_labels[sel_o])
+
+
+def test_camera_simple_test_api(cam):
+    out = cam["model"].simple_test(None, img_metas=cam["metas"], img=cam["img"].cuda())
+    assert len(out) == 2 and set(out[0]["pts_bbox"]) == {"boxes_3d", "scores_3d", "labels_3d"}
+    assert out[0]["pts_bbox"]["boxes_3d"].shape[1] == 9
