@@ -10,6 +10,7 @@ What runs from /root/reference, unmodified:
   projects/mmdet3d_plugin/models/utils/encoder_utils.py        (ConvBNReLU)
   projects/mmdet3d_plugin/models/necks/focal_encoder.py        (FocalEncoder, FocalEncoderLayer)
   projects/mmdet3d_plugin/models/dense_heads/focal_decoder.py  (FocalDecoder.forward / get_bboxes)
+  projects/mmdet3d_plugin/models/necks/lss.py                  (LiftSplatShoot, through FocalEncoder's camera path)
 What is stubbed (absent upstream packages mmcv / mmdet / mmdet3d): ConvModule, build_conv_layer,
 build_transformer_layer_sequence (-> oracle/transformer.py), rotation_3d_in_axis (-> oracle restatement), registries,
 losses, box containers, and the reference's hard-coded device='cuda' (torch.as_tensor / torch.ones wrappers).
@@ -116,7 +117,9 @@ def install_stubs():
     _mod("mmdet3d.core.bbox.structures.utils", rotation_3d_in_axis=rotation_3d_in_axis)
     _mod("mmdet3d.models.builder", HEADS=HEADS, NECKS=NECKS, build_loss=lambda cfg: _Loss())
     _mod("mmdet3d.models.utils", clip_sigmoid=None)
-    _mod("mmdet3d.models.fusion_layers", apply_3d_transformation=None)
+    # test-time: no point-cloud augmentation recorded in img_metas -> the transformation is the identity
+    _mod("mmdet3d.models.fusion_layers", apply_3d_transformation=lambda pts, coord, meta, reverse=False: pts)
+    _mod("matplotlib"); _mod("matplotlib.pyplot"); _mod("mpl_toolkits"); _mod("mpl_toolkits.mplot3d", Axes3D=None)
     _mod("mmdet3d.ops"); _mod("mmdet3d.ops.iou3d"); _mod("mmdet3d.ops.iou3d.iou3d_utils", nms_gpu=None)
     # parent packages of the reference modules, WITHOUT executing their __init__ (they import the whole plugin)
     base = os.path.join(REF, "projects", "mmdet3d_plugin")
@@ -135,6 +138,8 @@ class no_cuda_device:
 
     def __enter__(self):
         self.saved = (torch.as_tensor, torch.ones)
+        self.saved_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t          # lss.py:191-193, focal_encoder.py:184 call .cuda()
 
         def strip(fn):
             def w(*a, **k):
@@ -146,6 +151,7 @@ class no_cuda_device:
 
     def __exit__(self, *a):
         torch.as_tensor, torch.ones = self.saved
+        torch.Tensor.cuda = self.saved_cuda
 
 
 def main():
@@ -195,6 +201,43 @@ def main():
     torch.save(out, os.path.join(OUT, "focalformer3d_l_intree.pt"))
     n = sum(t.numel() for t in _tensors(out))
     print(f"wrote {os.path.join(OUT, 'focalformer3d_l_intree.pt')} ({n} values)")
+    camera_golden(fe)
+
+
+def camera_golden(fe):
+    """Real FocalEncoder camera path (focal_encoder.py:171-197 -> lss.py LiftSplatShoot.forward) of the
+    DeformFormer3D_C_R50 config on a reduced image / BEV size: lidar2img inversion, frustum geometry, truncating voxel
+    indices, sort + cumsum pooling, s2c, bevencode.  Weights: the repo's seeded synthetic state dict, strict load."""
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_camera_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_cameras
+    img_hw, bev = (32, 64), 16
+    cfg = scaled_camera_cfg(load_config(default_config_path("deformformer3d_c_r50"))["model"], bev=bev, img_hw=img_hw,
+                            num_proposals=12)
+    sd = make_state_dict(cfg, seed=6)
+    g = torch.Generator().manual_seed(12)
+    ne = dict(cfg["imgpts_neck"]); ne.pop("type")
+    with no_cuda_device():
+        enc = fe.FocalEncoder(**ne).eval()
+        enc.load_state_dict({k[len("imgpts_neck."):]: v for k, v in sd.items() if k.startswith("imgpts_neck.")}, strict=True)
+        B, N = 2, 6
+        feat = torch.randn(B * N, 256, img_hw[0] // 4, img_hw[1] // 4, generator=g) * 0.7
+        metas = [dict(lidar2img=synth_cameras(N, img_hw, seed=40 + b)) for b in range(B)]
+        with torch.no_grad():
+            none, (bev_a, bev_b) = enc(feat, None, metas)
+            lss = enc.cam_lss
+            # the intermediate the kernels are compared on: pooled volume before bevencode, from the same real module
+            rots = torch.stack([torch.stack([torch.Tensor(m).inverse()[:3, :3] for m in md["lidar2img"]]) for md in metas])
+            trans = torch.stack([torch.stack([torch.Tensor(m).inverse()[:3, 3] for m in md["lidar2img"]]) for md in metas])
+            vox, depth = lss.get_voxels(feat.view(B, N, *feat.shape[1:]), rots, trans, img_metas=metas)
+    assert none is None and bev_a is bev_b
+    pooled = lss.s2c(vox).contiguous()                       # [B, c*Z + z, Y, X]; stored as (flat index, value) pairs
+    nz = pooled.flatten().nonzero().flatten()
+    out = dict(img_hw=img_hw, bev=bev, weights_seed=6, feat=feat, lidar2img=torch.stack([torch.as_tensor(m["lidar2img"]) for m in metas]),
+               bev_out=bev_a.clone(), depth=depth.clone(), pooled_shape=tuple(pooled.shape), pooled_idx=nz.int(),
+               pooled_val=pooled.flatten()[nz].clone())
+    path = os.path.join(OUT, "deformformer3d_c_r50_lss.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({sum(t.numel() for t in _tensors(out))} values, {nz.numel()} non-zeros of the pooled volume)")
 
 
 def _tensors(o):

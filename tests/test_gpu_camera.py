@@ -201,3 +201,31 @@ def test_camera_simple_test_api(cam):
     out = cam["model"].simple_test(None, img_metas=cam["metas"], img=cam["img"].cuda())
     assert len(out) == 2 and set(out[0]["pts_bbox"]) == {"boxes_3d", "scores_3d", "labels_3d"}
     assert out[0]["pts_bbox"]["boxes_3d"].shape[1] == 9
+
+
+def test_cuda_lss_matches_reference_golden():
+    """The CUDA depthnet + splat + bevencode against the fixture produced by the REAL reference LiftSplatShoot."""
+    import os
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_camera_cfg
+    from focalformer3d_b200.synth import make_state_dict
+    from focalformer3d_b200.model import build_model
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deformformer3d_c_r50_lss.pt")
+    gold = torch.load(path, map_location="cpu")
+    cfg = scaled_camera_cfg(load_config(default_config_path("deformformer3d_c_r50"))["model"], bev=gold["bev"],
+                            img_hw=gold["img_hw"], num_proposals=12)
+    model = build_model(cfg)
+    model.load_state_dict(make_state_dict(cfg, seed=gold["weights_seed"]), strict=True)
+    model.prepare("cuda")
+    B = gold["lidar2img"].shape[0]
+    metas = [dict(lidar2img=m.numpy()) for m in gold["lidar2img"]]
+    feat = gold["feat"].permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.empty((B, gold["bev"], gold["bev"], 128), device="cuda")
+    _, dn, bev = model.imgpts_neck.forward_camera(feat, metas, out)
+    ref = torch.zeros(int(torch.tensor(gold["pooled_shape"]).prod()))
+    ref[gold["pooled_idx"].long()] = gold["pooled_val"]
+    ref = ref.view(*gold["pooled_shape"])                                      # [B, c*Z+z, Y, X]
+    Bp, CZ, Y, X = ref.shape
+    ours = bev.view(B, Y, X, CZ // 64, 64).permute(0, 4, 3, 1, 2).reshape(B, CZ, Y, X).cpu()
+    assert torch.equal(ours != 0, ref != 0), "voxel indices differ from the reference's"
+    assert (ours - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    _close(_nchw(out), gold["bev_out"], "bevencode output vs reference")
