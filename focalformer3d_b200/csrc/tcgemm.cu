@@ -51,17 +51,19 @@ constexpr int TC_MAX_TAPS = 27;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// All shared-memory traffic of this kernel goes through 32-bit shared-space addresses: the 1024-byte alignment of the
+// dynamic window is established on the ADDRESS, not by rounding a generic pointer (which loses the address space and
+// makes every access a generic LD/ST on the long scoreboard).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   while (!done) {
     asm volatile(
@@ -69,15 +71,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
   }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128i(uint32_t addr, int4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));   // volatile: ordered against the barrier asms
+  return v;
+}
+__device__ __forceinline__ int4 lds128i(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -105,9 +125,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -164,7 +183,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   constexpr bool DEFER = MT == 1;                                // double-buffered accumulators -> deferred epilogue
   // one CTA per SM has registers to spare: keep the NEXT stage's gather in flight while this one is split and
   // stored, so a producer group always has 16 KB outstanding (the gather is latency-, not bandwidth-bound)
-  constexpr bool PREFETCH = (BN == 128 && MT == 1);
+  constexpr bool PREFETCH = (BN == 128);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
   constexpr uint32_t A_BYTES = TC_BM * 128;
@@ -173,14 +192,14 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   constexpr int ACC_COLS = MT * 2 * BN;                          // per sub-tile: main | cross-term accumulator
   constexpr int NBUF = DEFER ? 2 : 1;
   constexpr int TMEM_COLS = NBUF * ACC_COLS < 32 ? 32 : NBUF * ACC_COLS;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_slots * SLOT_BYTES);
-  uint64_t* empty_bar = full_bar + n_slots;
-  uint64_t* tfull_bar = empty_bar + n_slots;    // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  // SPARSE: nbr element offsets [taps][128]; CONV2D: int4 row info [128] (16-byte aligned)
-  int* aux_s = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;   // shared-space address of slot 0
+  const uint32_t full_bar = smem + (uint32_t)n_slots * SLOT_BYTES;   // [n_slots] x 8 bytes
+  const uint32_t empty_bar = full_bar + 8u * n_slots;
+  const uint32_t tfull_bar = empty_bar + 8u * n_slots;           // [2]
+  const uint32_t tempty_bar = tfull_bar + 16u;                   // [2]
+  const uint32_t tmem_ptr = tempty_bar + 16u;
+  // SPARSE: nbr element offsets [taps][TM]; CONV2D: int4 row info [128] (16-byte aligned)
+  const uint32_t aux_s = (tmem_ptr + 4u + 15u) & ~15u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int Mv = p.M;
@@ -190,20 +209,19 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   if ((int)blockIdx.x >= total_tiles) return;   // uniform for the whole CTA, before any barrier / TMEM use
 
   if (tid == 0) {
-    for (int s = 0; s < n_slots; ++s) { mbar_init(&full_bar[s], TC_BM + 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NPROD); }
+    for (int s = 0; s < n_slots; ++s) { mbar_init(full_bar + 8u * s, TC_BM + 1); mbar_init(empty_bar + 8u * s, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8u * i, 1); mbar_init(tempty_bar + 8u * i, NPROD); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4 * G + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "n"(TMEM_COLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "n"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = (uint32_t)lds32(tmem_ptr);
   const int n_stages = p.n_stages;
 
   if (warp < 4 * G) {
@@ -226,7 +244,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       const int m0 = (tile / n_tiles_n) * TM;
       const int n0 = (tile - (tile / n_tiles_n) * n_tiles_n) * BN;
       const int ab = DEFER ? (it & 1) : 0;
-      mbar_wait(&tfull_bar[ab], (uint32_t)(DEFER ? ((it >> 1) & 1) : (it & 1)));
+      mbar_wait(tfull_bar + 8u * ab, (uint32_t)(DEFER ? ((it >> 1) & 1) : (it & 1)));
       tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -250,33 +268,38 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS + mt * 2 * BN);
 #pragma unroll 1
       for (int c0 = grp * 16; c0 < BN; c0 += 16 * G) {       // 16-column chunks dealt round-robin to the groups
+        const int n = n0 + c0;
+        // bias / residual loads first: their latency overlaps the TMEM read.  Residual row segment = 64 contiguous
+        // bytes per thread -> four 16-byte loads (this thread-per-row epilogue is LSU-wavefront bound)
+        float bs[16], rs[16];
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));   // bias is padded + 16B aligned
+            bs[i] = t.x; bs[i + 1] = t.y; bs[i + 2] = t.z; bs[i + 3] = t.w;
+          }
+        }
+        if (p.res && rvalid) {
+          const float* rp = p.res + (long long)m * p.ldres + n;
+          if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rp + i));
+              rs[i] = t.x; rs[i + 1] = t.y; rs[i + 2] = t.z; rs[i + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rs[i] = __ldg(rp + i);
+          }
+        }
         float v[16], v2[16];
         tmem_ld16(acc + (uint32_t)c0, v);                   // warp-collective: all lanes execute
         tmem_ld16(acc + (uint32_t)(BN + c0), v2);
         if (rvalid) {
-          const int n = n0 + c0;
-          // residual row segment: 64 contiguous bytes per thread -> four 16-byte loads (one request per row and
-          // instruction instead of sixteen scalar ones; this thread-per-row epilogue is LSU-wavefront bound)
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += v2[i];
-          float* rs = v2;                                    // the cross-term registers are free again
-          if (p.res) {
-            const float* rp = p.res + (long long)m * p.ldres + n;
-            if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(rp + i));
-                rs[i] = t.x; rs[i + 1] = t.y; rs[i + 2] = t.z; rs[i + 3] = t.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) rs[i] = __ldg(rp + i);
-            }
-          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a = v[i];
-            if (p.bias) a += __ldg(p.bias + n + i);
+            float a = v[i] + v2[i];
+            if (p.bias) a += bs[i];
             if (p.res_after_act) a = apply_act(a, p.act);
             if (p.res) a += rs[i];
             if (!p.res_after_act) a = apply_act(a, p.act);
@@ -293,7 +316,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       }
       }   // mt
       tc_fence_before();
-      mbar_arrive(&tempty_bar[ab]);                          // NPROD arrivals free the accumulator buffer
+      mbar_arrive(tempty_bar + 8u * ab);                     // NPROD arrivals free the accumulator buffer
     };
 
     int it = 0, prev_tile = -1;
@@ -305,12 +328,12 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         for (int i = ptid; i < p.taps * TM; i += NPROD) {
           int t = i / TM, rr = i - t * TM;
           int v = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
-          aux_s[i] = v < 0 ? -1 : v * p.ldx;                 // element offset of the source row
+          sts32(aux_s + 4u * i, v < 0 ? -1 : v * p.ldx);    // element offset of the source row
         }
       } else if (MODE == FF3D_GEMM_CONV2D) {
         for (int rr0 = ptid; rr0 < TM; rr0 += NPROD) {
           int mm = m0 + rr0;
-          int4 info = make_int4(0, 0, 0, 0);
+          int4 info = make_int4(0, -32768, -32768, 0);       // rows past M: every tap is out of bounds
           if (mm < Mv) {
             int hw = p.Ho * p.Wo;
             int b = mm / hw;
@@ -318,36 +341,38 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
             int oy = rr / p.Wo, ox = rr - (rr / p.Wo) * p.Wo;
             info = make_int4((int)(b * p.x_bstride), oy * p.stride - p.pad, ox * p.stride - p.pad, 1);
           }
-          reinterpret_cast<int4*>(aux_s)[rr0] = info;
+          sts128i(aux_s + 16u * rr0, info);
         }
       }
       producer_bar<NPROD>();
-      // element offset of the source row feeding (row, tap t), or -1
-      auto src_off = [&](int row, int t, int ky, int kx) -> long long {
-        if (t >= p.taps) return -1;
-        if (MODE == FF3D_GEMM_ROWS) return (m0 + row < Mv) ? (long long)(m0 + row) * p.ldx : -1;
-        if (MODE == FF3D_GEMM_CONV2D) {
-          const int4 info = reinterpret_cast<const int4*>(aux_s)[row];
-          int iy = info.y + ky, ix = info.z + kx;
-          if (!info.w || iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return -1;
-          return ((long long)info.x + (long long)iy * p.W + ix) * p.ldx;
-        }
-        return (long long)aux_s[t * TM + row];
-      };
       // my stages of this tile: global stage index (it * n_stages + s) has my parity
       int s = (grp - it * n_stages) % G;                      // first stage of this tile with (it*n_stages + s) % G == grp
       if (s < 0) s += G;
       int t, cidx;                                           // tap and 32-channel chunk of stage s (cin >= 32)
       t = s / p.cpt; cidx = s - t * p.cpt;
-      auto gather = [&](int st, int tt, int ci, float4* v) {
+      int umt = 0;                                           // 128-row sub-tile of the gather cursor (s, t, cidx, umt)
+      // one gather unit = 8 x 16 bytes per thread = the 32 K-values of 128 rows (one sub-tile of one stage)
+      auto gather = [&](float4* v) {
         int tap, coff, ky = 0, kx = 0;
-        if (p.cin >= 32) { tap = tt; coff = ci * 32 + lane_coff; }
-        else { tap = st * p.tps + lane_tap; coff = lane_coff; }
+        if (p.cin >= 32) { tap = t; coff = cidx * 32 + lane_coff; }
+        else { tap = s * p.tps + lane_tap; coff = lane_coff; }
         if (MODE == FF3D_GEMM_CONV2D) { ky = tap / p.kw; kx = tap - ky * p.kw; }
+        const bool tap_ok = tap < p.taps;
 #pragma unroll
-        for (int i = 0; i < 8 * MT; ++i) {
-          const int row = (i >> 3) * TC_BM + pw * 32 + (i & 7) * 4 + q;   // sub-tile (i >> 3), row inside it
-          const long long so = src_off(row, tap, ky, kx);
+        for (int i = 0; i < 8; ++i) {
+          const int row = umt * TC_BM + pw * 32 + i * 4 + q;
+          long long so = -1;                                 // element offset of the source row feeding (row, tap)
+          if (MODE == FF3D_GEMM_ROWS) {
+            if (tap_ok && m0 + row < Mv) so = (long long)(m0 + row) * p.ldx;
+          } else if (MODE == FF3D_GEMM_CONV2D) {
+            // staged per-tile row info (batch pixel base, top-left input y, x); rows past M hold y = x = -32768
+            const int4 info = lds128i(aux_s + 16u * (uint32_t)row);
+            const int iy = info.y + ky, ix = info.z + kx;
+            if (tap_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
+              so = ((long long)info.x + (long long)(iy * p.W + ix)) * p.ldx;
+          } else {
+            if (tap_ok) so = (long long)lds32(aux_s + 4u * (uint32_t)(tap * TM + row));
+          }
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (so >= 0) {
             v[i] = __ldg(reinterpret_cast<const float4*>(p.x + so + coff));
@@ -358,39 +383,58 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
           }
         }
       };
-      float4 v[8 * MT], vn[PREFETCH ? 8 * MT : 1];
-      if (PREFETCH && s < n_stages) gather(s, t, cidx, v);
-      for (; s < n_stages; s += G) {
-        if (PREFETCH) {
-          int tn = t, cn = cidx + G;
-          while (cn >= p.cpt) { cn -= p.cpt; ++tn; }
-          if (s + G < n_stages) gather(s + G, tn, cn, vn);
-        } else {
-          gather(s, t, cidx, v);
-        }
-        mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
-        uint8_t* slot_base = smem + (size_t)ring.slot * SLOT_BYTES;
+      auto advance_cursor = [&]() {
+        if (++umt < MT) return;
+        umt = 0;
+        s += G;
+        if (p.cin >= 32) { cidx += G; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
+      };
+      // split one gathered unit into the hi / lo TF32 images of this group's smem slot; the last sub-tile of a stage
+      // hands the slot to the MMA issuer
+      auto commit_unit = [&](const float4* v, int mt) {
+        if (mt == 0) mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
+        const uint32_t a_hi = smem + (uint32_t)ring.slot * SLOT_BYTES + (uint32_t)mt * (2 * A_BYTES);
+        const uint32_t a_lo = a_hi + A_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8 * MT; ++i) {
-          const int row = pw * 32 + (i & 7) * 4 + q;
-          uint8_t* a_hi = slot_base + (size_t)(i >> 3) * (2 * A_BYTES);
-          uint8_t* a_lo = a_hi + A_BYTES;
+        for (int i = 0; i < 8; ++i) {
           float4 h, l;
           split_tf32(v[i].x, h.x, l.x);
           split_tf32(v[i].y, h.y, l.y);
           split_tf32(v[i].z, h.z, l.z);
           split_tf32(v[i].w, h.w, l.w);
-          const uint32_t o = swz(row, j);
-          *reinterpret_cast<float4*>(a_hi + o) = h;
-          *reinterpret_cast<float4*>(a_lo + o) = l;
+          const uint32_t o = swz(pw * 32 + i * 4 + q, j);
+          sts128(a_hi + o, h);
+          sts128(a_lo + o, l);
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[ring.slot]);
-        ring.advance(G, n_slots);
-        if (p.cin >= 32) { cidx += G; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
-        if (PREFETCH) {
-#pragma unroll
-          for (int i = 0; i < 8 * MT; ++i) v[i] = vn[i];
+        if (mt == MT - 1) {
+          fence_proxy_async();
+          mbar_arrive(full_bar + 8u * ring.slot);
+          ring.advance(G, n_slots);
+        }
+      };
+      if (PREFETCH) {
+        // two register sets in ping-pong: the loads of the next unit are in flight while this one is split and stored
+        // (no register moves between the sets -- a move would wait for the very loads it is supposed to overlap)
+        float4 va[8], vb[8];
+        int mta = 0, mtb = 0;
+        bool have = s < n_stages;
+        if (have) { gather(va); mta = umt; advance_cursor(); }
+        while (have) {
+          bool more = s < n_stages;
+          if (more) { gather(vb); mtb = umt; advance_cursor(); }
+          commit_unit(va, mta);
+          if (!more) break;
+          have = s < n_stages;
+          if (have) { gather(va); mta = umt; advance_cursor(); }
+          commit_unit(vb, mtb);
+        }
+      } else {
+        float4 v[8];
+        while (s < n_stages) {
+          gather(v);
+          const int mt = umt;
+          advance_cursor();
+          commit_unit(v, mt);
         }
       }
       // epilogue of the PREVIOUS tile: its MMAs have had a whole tile's worth of gathers to finish, and the
@@ -411,10 +455,10 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         const int ntile = tile - (tile / n_tiles_n) * n_tiles_n;
         const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
         for (int s = 0; s < n_stages; ++s) {
-          mbar_wait(&empty_bar[ring.slot], ring.phase ^ 1u);
-          uint8_t* b_hi = smem + (size_t)ring.slot * SLOT_BYTES + MT * 2 * A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[ring.slot], 2 * B_BYTES);
-          bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, &full_bar[ring.slot]);
+          mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
+          const uint32_t b_hi = smem + (uint32_t)ring.slot * SLOT_BYTES + MT * 2 * A_BYTES;
+          mbar_arrive_expect_tx(full_bar + 8u * ring.slot, 2 * B_BYTES);
+          bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, full_bar + 8u * ring.slot);
           ring.advance(1, n_slots);
         }
       }
@@ -431,13 +475,13 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int ab = DEFER ? (it & 1) : 0;
         // the epilogue that last read this accumulator buffer (tile it-2, or it-1 when single-buffered) has drained it
-        mbar_wait(&tempty_bar[ab], (uint32_t)((DEFER ? ((it >> 1) & 1) : (it & 1)) ^ 1));
+        mbar_wait(tempty_bar + 8u * ab, (uint32_t)((DEFER ? ((it >> 1) & 1) : (it & 1)) ^ 1));
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(ab * ACC_COLS);
         for (int s = 0; s < n_stages; ++s) {
-          mbar_wait(&full_bar[ring.slot], ring.phase);
+          mbar_wait(full_bar + 8u * ring.slot, ring.phase);
           tc_fence_after();
-          const uint32_t slot_a = smem_u32(smem + (size_t)ring.slot * SLOT_BYTES);
+          const uint32_t slot_a = smem + (uint32_t)ring.slot * SLOT_BYTES;
           const uint32_t b_hi = slot_a + MT * 2 * A_BYTES;
           static_assert(B_BYTES % 1024 == 0, "B_lo must continue B_hi's 8-row swizzle atoms");
 #pragma unroll
@@ -453,10 +497,10 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
               umma_tf32(d_cross, dal, dbh, idesc_cross, 1u);   // cross += A_lo*B_hi
             }
           }
-          umma_commit(&empty_bar[ring.slot]);   // frees the smem slot once these MMAs have read it
+          umma_commit(empty_bar + 8u * ring.slot);   // frees the smem slot once these MMAs have read it
           ring.advance(1, n_slots);
         }
-        umma_commit(&tfull_bar[ab]);            // accumulator of this tile complete
+        umma_commit(tfull_bar + 8u * ab);            // accumulator of this tile complete
       }
     }
     __syncwarp();
@@ -494,8 +538,9 @@ static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
   if constexpr (BN == 128) {
     // enough 256-row tiles to fill the machine -> share each weight stage between two row sub-tiles
     // (only the sparse gather profits: dense layers lose more from the single-buffered accumulators, measured)
-    if (MODE == FF3D_GEMM_SPARSE && (long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms())
-      return launch_tc_cfg<MODE, BN, 2, 2>(p, n_tiles_n, st);
+    if constexpr (MODE == FF3D_GEMM_SPARSE) {
+      if ((long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms()) return launch_tc_cfg<MODE, BN, 2, 2>(p, n_tiles_n, st);
+    }
     return launch_tc_cfg<MODE, BN, 3, 1>(p, n_tiles_n, st);
   } else {
     return launch_tc_cfg<MODE, BN, 2, 1>(p, n_tiles_n, st);
@@ -545,8 +590,9 @@ extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn
                    (bn == 16 || bn == 32 || bn == 64 || bn == 128),
                "ff3d_tcgemm: shape cin=%d cout=%d (N tile %d) is not tensor-core tileable", d->cin, d->cout, bn);
   FF3D_REQUIRE(d->ldx % 4 == 0 && d->x && d->y && d->taps > 0, "ff3d_tcgemm: bad operands");
-  FF3D_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wimg) & 15) == 0,
-               "ff3d_tcgemm: x and wimg must be 16-byte aligned");
+  FF3D_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wimg) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0,
+               "ff3d_tcgemm: x, wimg and bias must be 16-byte aligned");
   if (d->M <= 0) return FF3D_OK;
   TcP p;
   p.mode = d->mode; p.M = d->M; p.m_dev = d->m_dev;
