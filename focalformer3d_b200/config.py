@@ -111,6 +111,15 @@ def scaled_camera_cfg(model_cfg, bev, img_hw, num_proposals=None):
     return _wrap(m)
 
 
+def scaled_fusion_cfg(model_cfg, bev, img_hw, num_proposals=None, max_voxels=None):
+    """Smaller variant of a LiDAR + camera config: scaled_model_cfg for the LiDAR tower / head plus the image size and
+    the Lift-Splat-Shoot BEV range of the neck."""
+    m = scaled_model_cfg(model_cfg, bev, num_proposals=num_proposals, max_voxels=max_voxels)
+    m["imgpts_neck"]["pc_range"] = list(m["pts_voxel_layer"]["point_cloud_range"])
+    m["imgpts_neck"]["img_scale"] = tuple(img_hw)
+    return m
+
+
 def scaled_model_cfg(model_cfg, bev, z_cells=None, num_proposals=None, max_voxels=None):
     """Derive a geometrically smaller variant of a LiDAR config (same layers, same voxel size, smaller
     range) for parity tests the CPU oracle finishes in seconds.  ``bev`` = BEV cells per side."""

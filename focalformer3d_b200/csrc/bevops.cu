@@ -74,6 +74,188 @@ __global__ void add_bcast_rows_kernel(const float4* __restrict__ a, const float4
   }
 }
 
+
+// Local-context attention (locatt_ops similar -> softmax -> weighting, encoder_utils.py:155-163) fused: one warp per
+// pixel, lane l owns channels 4l..4l+3 of every 128-channel block.  K*K <= 96 scores live three per lane; neighbours
+// outside the map score 0 and still take part in the soft-max (the reference pads the similarity with zeros), but
+// contribute no value.  q/k/v rows of neighbouring pixels are re-read from L1/L2 (81x reuse inside a CTA's 8-pixel row).
+template <int NV>
+__global__ void __launch_bounds__(256) local_attention_kernel(const float* __restrict__ q, int ldq,
+                                                              const float* __restrict__ k, int ldk,
+                                                              const float* __restrict__ v, int ldv, float* __restrict__ y,
+                                                              int ldy, int B, int H, int W, int K, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (pix >= (long long)B * H * W) return;
+  const int x0 = (int)(pix % W);
+  const long long r = pix / W;
+  const int y0 = (int)(r % H);
+  const long long b = r / H;
+  const int R = K >> 1, KK = K * K;
+  float4 qv[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) qv[u] = __ldg(reinterpret_cast<const float4*>(q + pix * ldq + u * 128 + lane * 4));
+  float sc[3] = {0.f, 0.f, 0.f};
+  for (int kk = 0; kk < KK; ++kk) {
+    const int ny = y0 + kk / K - R, nx = x0 + kk % K - R;
+    float s = 0.f;
+    if (ny >= 0 && ny < H && nx >= 0 && nx < W) {          // warp-uniform
+      const float* kp = k + ((b * H + ny) * W + nx) * ldk + lane * 4;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(kp + u * 128));
+        s = fmaf(qv[u].x, t.x, s); s = fmaf(qv[u].y, t.y, s); s = fmaf(qv[u].z, t.z, s); s = fmaf(qv[u].w, t.w, s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if ((kk & 31) == lane) {                               // static register indices (no local-memory array)
+      if (kk < 32) sc[0] = s * scale; else if (kk < 64) sc[1] = s * scale; else sc[2] = s * scale;
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) if (u * 32 + lane < KK) m = fmaxf(m, sc[u]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    sc[u] = (u * 32 + lane < KK) ? expf(sc[u] - m) : 0.f;
+    sum += sc[u];
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  float4 acc[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int kk = 0; kk < KK; ++kk) {
+    const float w0 = __shfl_sync(0xffffffffu, sc[0], kk & 31);
+    const float w1 = __shfl_sync(0xffffffffu, sc[1], kk & 31);
+    const float w2 = __shfl_sync(0xffffffffu, sc[2], kk & 31);
+    const float w = (kk < 32 ? w0 : (kk < 64 ? w1 : w2)) * inv;
+    const int ny = y0 + kk / K - R, nx = x0 + kk % K - R;
+    if (ny >= 0 && ny < H && nx >= 0 && nx < W) {
+      const float* vp = v + ((b * H + ny) * W + nx) * ldv + lane * 4;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(vp + u * 128));
+        acc[u].x = fmaf(w, t.x, acc[u].x); acc[u].y = fmaf(w, t.y, acc[u].y);
+        acc[u].z = fmaf(w, t.z, acc[u].z); acc[u].w = fmaf(w, t.w, acc[u].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NV; ++u) *reinterpret_cast<float4*>(y + pix * ldy + u * 128 + lane * 4) = acc[u];
+}
+
+// Tiled variant for C = 128 (the shipped configs): one CTA = 8x8 output pixels.  The (8+K-1)^2 key rows are staged once
+// in shared memory (row stride 132 floats, tile width 17: the lane <-> neighbour mapping below is then bank-conflict
+// free), zero-filled outside the map -- a zero key scores exactly 0, a zero value adds nothing, which IS the reference's
+// border rule, so the inner loops carry no bounds checks.  Scores: lane l owns neighbours l, l+32, l+64 and runs the whole
+// 128-channel dot product itself (q broadcast from shared memory; no shuffle reductions).  Then the same buffer is
+// re-filled with the value rows and the weighted sum runs with lanes over channels.  Global traffic drops from
+// 2*K*K rows per pixel to ~9 rows per pixel.
+constexpr int LA_T = 8, LA_C = 128, LA_LD = 132;
+__global__ void __launch_bounds__(512, 1) local_attention_tiled_kernel(const float* __restrict__ q, int ldq,
+                                                                    const float* __restrict__ k, int ldk,
+                                                                    const float* __restrict__ v, int ldv,
+                                                                    float* __restrict__ y, int ldy, int H, int W, int K,
+                                                                    float scale) {
+  extern __shared__ __align__(16) float la_smem[];
+  const int R = K >> 1, KK = K * K, HW = LA_T + K - 1, HWP = HW + 1;      // halo tile is HW x HWP (padded width)
+  float* qs = la_smem;                                                   // [64][128]
+  float* ks = la_smem + LA_T * LA_T * LA_C;                              // [HW * HWP][132]
+  const int tiles_x = (W + LA_T - 1) / LA_T, tiles_y = (H + LA_T - 1) / LA_T;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int trem = blockIdx.x - b * tiles_x * tiles_y;
+  const int y0 = (trem / tiles_x) * LA_T, x0 = (trem % tiles_x) * LA_T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long img = (long long)b * H * W;
+  auto stage_halo = [&](const float* src, int ld) {
+    for (int e = tid; e < HW * HW * (LA_C / 4); e += blockDim.x) {
+      const int c4 = e & (LA_C / 4 - 1), pix = e / (LA_C / 4);
+      const int hy = pix / HW, hx = pix - hy * HW;
+      const int gy = y0 + hy - R, gx = x0 + hx - R;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) t = __ldg(reinterpret_cast<const float4*>(src + (img + (long long)gy * W + gx) * ld + c4 * 4));
+      *reinterpret_cast<float4*>(ks + (hy * HWP + hx) * LA_LD + c4 * 4) = t;
+    }
+  };
+  for (int e = tid; e < LA_T * LA_T * (LA_C / 4); e += blockDim.x) {
+    const int c4 = e & (LA_C / 4 - 1), pix = e / (LA_C / 4);
+    const int gy = y0 + pix / LA_T, gx = x0 + pix % LA_T;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy < H && gx < W) t = __ldg(reinterpret_cast<const float4*>(q + (img + (long long)gy * W + gx) * ldq + c4 * 4));
+    *reinterpret_cast<float4*>(qs + pix * LA_C + c4 * 4) = t;
+  }
+  stage_halo(k, ldk);
+  __syncthreads();
+  // ---- scores + soft-max: 4 pixels per warp, 3 neighbours per lane
+  constexpr int PPW = LA_T * LA_T / 16;
+  float wgt[PPW][3];
+  int nb[3];                                                             // halo-row offset of my neighbour, minus the pixel's
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int kk = r * 32 + lane;
+    nb[r] = kk < KK ? ((kk / K) * HWP + kk % K) * LA_LD : 0;
+  }
+#pragma unroll
+  for (int pp = 0; pp < PPW; ++pp) {
+    const int p = warp * PPW + pp;
+    const float* qp = qs + p * LA_C;
+    const float* kp = ks + ((p / LA_T) * HWP + p % LA_T) * LA_LD;
+    float a[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < LA_C; c += 4) {
+      const float4 qv = *reinterpret_cast<const float4*>(qp + c);        // same address in every lane: broadcast
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp + nb[r] + c);
+        a[r][0] = fmaf(qv.x, kv.x, a[r][0]); a[r][1] = fmaf(qv.y, kv.y, a[r][1]);
+        a[r][2] = fmaf(qv.z, kv.z, a[r][2]); a[r][3] = fmaf(qv.w, kv.w, a[r][3]);
+      }
+    }
+    float s[3], m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      s[r] = (r * 32 + lane < KK) ? ((a[r][0] + a[r][1]) + (a[r][2] + a[r][3])) * scale : -INFINITY;
+      m = fmaxf(m, s[r]);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { s[r] = expf(s[r] - m); sum += s[r]; }   // expf(-inf) = 0 for the unused slots
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) wgt[pp][r] = s[r] * inv;
+  }
+  __syncthreads();
+  stage_halo(v, ldv);
+  __syncthreads();
+  // ---- weighted sum of the value rows: lane l owns channels 4l .. 4l+3
+#pragma unroll
+  for (int pp = 0; pp < PPW; ++pp) {
+    const int p = warp * PPW + pp;
+    const int gy = y0 + p / LA_T, gx = x0 + p % LA_T;
+    const float* vp = ks + ((p / LA_T) * HWP + p % LA_T) * LA_LD + lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int n = KK - r * 32 < 32 ? KK - r * 32 : 32;
+      for (int l = 0; l < n; ++l) {
+        const float w = __shfl_sync(0xffffffffu, wgt[pp][r], l);
+        const int kk = r * 32 + l;
+        const float4 t = *reinterpret_cast<const float4*>(vp + ((kk / K) * HWP + kk % K) * LA_LD);
+        acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y); acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
+      }
+    }
+    if (gy < H && gx < W) *reinterpret_cast<float4*>(y + (img + (long long)gy * W + gx) * ldy + lane * 4) = acc;
+  }
+}
+
 static inline int grid_for(long long work, int threads) {
   long long nb = (work + threads - 1) / threads;
   long long cap = (long long)num_sms() * 32;
@@ -115,4 +297,32 @@ extern "C" int ff3d_add_bcast_rows(const float* a, const float* p, float* y, int
   add_bcast_rows_kernel<<<grid_for(per4 * B, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(p), reinterpret_cast<float4*>(y), B, per4);
   return check_launch("ff3d_add_bcast_rows");
+}
+
+extern "C" int ff3d_local_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* y,
+                                    int ldy, int B, int H, int W, int C, int K, ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE((C == 128 || C == 256) && (K & 1) == 1 && K * K <= 96, "local_attention: C must be 128 or 256, K odd, K*K <= 96");
+  FF3D_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldy % 4 == 0, "local_attention: row strides must be multiples of 4");
+  long long pix = (long long)B * H * W;
+  if (pix == 0) return FF3D_OK;
+  float scale = 1.0f / sqrtf((float)C);
+  int blocks = cdiv(pix * 32, 256);
+  if (C == 128) {
+    const int hw = LA_T + K - 1;
+    const size_t smem = sizeof(float) * ((size_t)LA_T * LA_T * LA_C + (size_t)hw * (hw + 1) * LA_LD);
+    if (smem <= 227 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(local_attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+      }
+      const int tiles = cdiv(H, LA_T) * cdiv(W, LA_T);
+      local_attention_tiled_kernel<<<B * tiles, 512, smem, as_stream(stream)>>>(q, ldq, k, ldk, v, ldv, y, ldy, H, W, K, scale);
+      return check_launch("ff3d_local_attention");
+    }
+    local_attention_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(q, ldq, k, ldk, v, ldv, y, ldy, B, H, W, K, scale);
+  } else
+    local_attention_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(q, ldq, k, ldk, v, ldv, y, ldy, B, H, W, K, scale);
+  return check_launch("ff3d_local_attention");
 }

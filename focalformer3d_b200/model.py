@@ -495,11 +495,15 @@ class FocalEncoder(ParamTree):
                  input_pts=True, iterbev_wo_img=False, extra_feat=False, iter_bev_cam=False, cam_lss=False,
                  newbevpool=False, pc_range=None, img_scale=None, spec=None, **kw):
         super().__init__()
-        self.camera_only = bool(input_img and cam_lss and cam_lss != "proj" and not input_pts and not num_layers
-                                and not multistage_heatmap)
-        if not self.camera_only and (input_img or not input_pts or iterbev != "bevfusionmb2" or not iterbev_wo_img):
-            raise NotImplementedError("FocalEncoder: built paths are LiDAR-only bevfusionmb2 and camera-only "
-                                      "Lift-Splat-Shoot (SURVEY.md 8f: LiDAR+camera fusion is the next scope row)")
+        lss_ok = bool(input_img and cam_lss and cam_lss != "proj")
+        self.camera_only = bool(lss_ok and not input_pts and not num_layers and not multistage_heatmap)
+        # LiDAR + camera (FocalFormer3D_LC): camera BEV from cam_lss, 'bevfusion' blocks, iter_bev_cam (no I2P projection)
+        self.fusion = bool(lss_ok and input_pts and iterbev == "bevfusion" and iter_bev_cam and not iterbev_wo_img
+                           and multistage_heatmap and num_layers)
+        lidar_only = (not input_img) and input_pts and iterbev == "bevfusionmb2" and iterbev_wo_img
+        if not (self.camera_only or self.fusion or lidar_only):
+            raise NotImplementedError("FocalEncoder: built paths are LiDAR-only 'bevfusionmb2', camera-only Lift-Splat-Shoot "
+                                      "and LiDAR + camera 'bevfusion' with cam_lss / iter_bev_cam")
         self.pc_range, self.img_scale = pc_range, img_scale
         self.num_layers = num_layers or 0
         self.hidden = hidden_channel
@@ -513,6 +517,30 @@ class FocalEncoder(ParamTree):
             self.pk = {"lss": LiftSplatShoot(sd, "cam_lss", list(self.pc_range), 0.6, self.hidden, dev)}   # :129-131
             return
         pk = {"shared": (pack_conv2d(sd["shared_conv_pts.weight"], None, dev), vec(sd["shared_conv_pts.bias"], dev))}
+        if self.fusion:
+            pk["lss"] = LiftSplatShoot(sd, "cam_lss", list(self.pc_range), 0.6, self.hidden, dev)
+
+            def cbn(name):                                   # ConvBNReLU (encoder_utils.py:10-33), BN folded
+                s_, b_ = bn_scale_shift(sd, name + ".bn", 1e-5)
+                return sd[name + ".conv.weight"].double() * s_.view(-1, 1, 1, 1), b_
+            for i in range(self.num_layers):
+                q = f"fusion_blocks.{i}"
+                # first 1x1 of the query / key projections and the value projection read the same tensor: one GEMM
+                ws, bs = zip(*[cbn(f"{q}.P_IML.{n}") for n in ("query_project.0", "key_project.0", "value_project")])
+                blk = dict(qkv1=(pack_conv2d(torch.cat(ws, 0), None, dev), vec(torch.cat(bs), dev)))
+                for n, key in (("query_project.1", "q2"), ("key_project.1", "k2"), ("P_out_proj", "outp"), ("P_integration", "integ")):
+                    w_, b_ = cbn(f"{q}.{n}" if n.startswith("P_") else f"{q}.P_IML.{n}")
+                    blk[key] = (pack_conv2d(w_, None, dev), vec(b_, dev))
+                if i + 1 < self.num_layers:                  # the last block's camera-BEV update is never consumed
+                    for n in (1, 2):
+                        s_, b_ = bn_scale_shift(sd, f"{q}.iterimg_conv.0.bn{n}", 1e-5)
+                        blk[f"img{n}"] = (pack_conv2d(sd[f"{q}.iterimg_conv.0.conv{n}.weight"], s_, dev), vec(b_, dev))
+                pk[q] = blk
+            if self.extra_feat:
+                s, b = bn_scale_shift(sd, "extra_output.bn", 1e-5)
+                pk["extra"] = (pack_conv2d(sd["extra_output.conv.weight"], s, dev), vec(b, dev))
+            self.pk = pk
+            return
         for i in range(self.num_layers):
             q = f"fusion_blocks.{i}"
             pk[q] = (_IR(sd, q + ".P_IML", 2, dev), _IR(sd, q + ".P_out_proj", 1, dev), _IR(sd, q + ".P_integration", 1, dev))
@@ -536,6 +564,51 @@ class FocalEncoder(ParamTree):
         (focal_encoder.py:196-197: conv_feat and decoder feature are the same tensor)."""
         rots, trans = self.camera_rots_trans(img_metas, img_feat.device)
         return self.pk["lss"](img_feat, rots, trans, len(img_metas), out)
+
+    def forward_fusion(self, pts_feats, img_feat, img_metas, extra_out):
+        """focal_encoder.py:171-219 with both towers.  pts_feats [B,H,W,512] (SECONDFPN), img_feat [B*N,fH,fW,256] (FPN
+        level 0).  Concatenations are channel slices of two ping-pong buffers per layer: catA = [camera BEV | P2P],
+        catB = [P_Aug | LiDAR BEV]; every producer writes straight into its slice.
+        Returns (conv_feat, [stage features], extra, camera BEV of layer 0)."""
+        B, H, W, _ = pts_feats.shape
+        dev, hc, pk = pts_feats.device, self.hidden, self.pk
+        new = lambda c: torch.empty((B, H, W, c), dtype=torch.float32, device=dev)
+        catA, catB = new(2 * hc), new(2 * hc)
+        rots, trans = self.camera_rots_trans(img_metas, dev)
+        pk["lss"](img_feat, rots, trans, B, catA[..., :hc])                                        # :196 camera BEV
+        img_bev0 = catA[..., :hc]
+        conv_feat = new(hc)
+        ops.conv2d(pts_feats, *pk["shared"], conv_feat, 3, act=ACT_NONE)                           # :204
+        catB[..., hc:].copy_(conv_feat)                                                            # :207 (.clone())
+        stages = []
+        for i in range(self.num_layers):
+            blk = pk[f"fusion_blocks.{i}"]
+            lidar = catB[..., hc:]
+            qkv = new(3 * hc)
+            ops.conv2d(lidar, *blk["qkv1"], qkv, 1, act=ACT_RELU)                                  # encoder_utils.py:156-158
+            q2, k2 = new(hc), new(hc)
+            ops.conv2d(qkv[..., :hc], *blk["q2"], q2, 1, act=ACT_RELU)
+            ops.conv2d(qkv[..., hc:2 * hc], *blk["k2"], k2, 1, act=ACT_RELU)
+            ops.local_attention(q2, k2, qkv[..., 2 * hc:], catA[..., hc:], 9)                      # :160-162 -> P2P
+            ops.conv2d(catA, *blk["outp"], catB[..., :hc], 1, act=ACT_NONE)                        # focal_encoder.py:73
+            last = i == self.num_layers - 1
+            nxtB = new(hc) if last else new(2 * hc)
+            new_feat = nxtB if last else nxtB[..., hc:]
+            ops.conv2d(catB, *blk["integ"], new_feat, 1, act=ACT_NONE)                             # :74
+            stages.append(new_feat)
+            if not last:
+                nxtA = new(2 * hc)
+                t = new(hc)
+                ops.conv2d(catA[..., :hc], *blk["img1"], t, 3, act=ACT_RELU)                        # :85 BasicBlock
+                ops.conv2d(t, *blk["img2"], nxtA[..., :hc], 3, act=ACT_RELU, res=catA[..., :hc])
+                if i == 0:
+                    img_bev0 = catA[..., :hc]
+                catA, catB = nxtA, nxtB
+        extra = None
+        if self.extra_feat:
+            extra = extra_out if extra_out is not None else new(hc)
+            ops.conv2d(stages[-1], *pk["extra"], extra, 3, act=ACT_NONE)                           # :218-219
+        return conv_feat, stages, extra, img_bev0
 
     def forward(self, pts_feats, extra_out=None):
         """pts_feats [B,H,W,512] NHWC.  Returns (conv_feat view, [stage feature views...], extra view)."""
@@ -653,6 +726,10 @@ class FocalDecoder(ParamTree):
             pk["heat"] = [heat("heatmap_head"), heat("heatmap_head_img")]
         for i in range(self.stages):
             pk["heat"].append(heat("heatmap_head") if (i == 0 and self.reuse_first) else heat(f"heatmap_head_img.{i}"))
+        if not self.single_stage and not self.reuse_first:
+            # focal_decoder.py:588,663-664: heatmap_head(conv_feat) is still evaluated and returned as the first
+            # 'dense_heatmap' entry (a training-loss output; it feeds no proposal)
+            pk["heat_first"] = heat("heatmap_head")
         pk["cls_w"] = sd["class_encoding.weight"].reshape(hc, nc).t().contiguous().float().to(dev)      # [C, Cf]
         pk["cls_b"] = vec(sd["class_encoding.bias"], dev)
         for n in ("dconv", "dconv2"):
@@ -765,6 +842,8 @@ class FocalDecoder(ParamTree):
             ops.conv2d(t, w2, b2, lg, 3, act=ACT_NONE)
             return lg
 
+        if "heat_first" in pk:
+            dense_heatmaps.append(heat_logits(pk["heat_first"], conv_feat))
         for s in range(n_sel):
             logits2 = None
             if self.single_stage:      # heatmap = (sigmoid(heatmap_head(x)) + sigmoid(heatmap_head_img(x))) / 2   :547-549
@@ -881,8 +960,6 @@ class FocalFormer3D(nn.Module):
                  pts_neck=None, imgpts_neck=None, pts_bbox_head=None, train_cfg=None, test_cfg=None, input_img=True,
                  input_pts=True, img_backbone=None, img_neck=None, **unused):
         super().__init__()
-        if input_img and input_pts:
-            raise NotImplementedError("FocalFormer3D: LiDAR+camera fusion configs are the next scope row (SURVEY.md 8f)")
         self.input_img, self.input_pts = bool(input_img), bool(input_pts)
         cfg = dict(pts_voxel_layer=pts_voxel_layer, pts_voxel_encoder=pts_voxel_encoder,
                    pts_middle_encoder=pts_middle_encoder, pts_backbone=pts_backbone, pts_neck=pts_neck,
@@ -892,9 +969,10 @@ class FocalFormer3D(nn.Module):
         tcfg = test_cfg["pts"] if (test_cfg and "pts" in test_cfg) else test_cfg
         self._prepared_on = None
         if self.input_img:
-            # camera-only (DeformFormer3D_C_R50): focalformer3d.py:133-153 image tower, no LiDAR tower is built
+            # image tower (focalformer3d.py:133-153); camera-only (DeformFormer3D_C_R50) builds no LiDAR tower
             self.img_backbone = BACKBONES.build(img_backbone, spec=sub_spec(spec, "img_backbone"))
             self.img_neck = NECKS.build(img_neck, spec=sub_spec(spec, "img_neck"))
+        if self.input_img and not self.input_pts:
             self.imgpts_neck = NECKS.build(imgpts_neck, spec=sub_spec(spec, "imgpts_neck"), input_img=True)
             self.pts_bbox_head = HEADS.build(pts_bbox_head, spec=sub_spec(spec, "pts_bbox_head"), test_cfg=tcfg)
             return
@@ -966,7 +1044,8 @@ class FocalFormer3D(nn.Module):
         if self.input_img:
             if img is None or img_metas is None:
                 raise ValueError("camera config: forward_raw needs img [B,N,3,H,W] and img_metas with 'lidar2img'")
-            return self.forward_camera(img, img_metas, keep_stages)
+            if not self.input_pts:
+                return self.forward_camera(img, img_metas, keep_stages)
         dev = self._prepared_on
         B = len(points)
         offs = [0]
@@ -1000,7 +1079,19 @@ class FocalFormer3D(nn.Module):
         geom = ops.LevelGeom([(H >> l, W >> l) for l in range(head.n_levels)])
         ms_value = torch.empty((B, geom.n_tokens, head.hc), dtype=torch.float32, device=dev)
         extra_view = ms_value[:, :H * W].view(B, H, W, head.hc)
-        conv_feat, stage_feats, extra = self.imgpts_neck(neck, extra_out=extra_view)
+        cam = None
+        if self.input_img:
+            # LiDAR + camera (FocalFormer3D_LC): image tower (focalformer3d.py:133-153), then the fused encoder
+            Bi, N, Cc, Hi, Wi = img.shape
+            x = ops.nchw_to_nhwc(img.to(dev, torch.float32).reshape(Bi * N, Cc, Hi, Wi).contiguous(), 8)
+            feats = self.img_backbone(x)
+            ops.mark("img_backbone")
+            f0 = self.img_neck(feats)
+            ops.mark("img_neck")
+            conv_feat, stage_feats, extra, img_bev = self.imgpts_neck.forward_fusion(neck, f0, img_metas, extra_view)
+            cam = dict(img_backbone=feats, img_feat=f0, img_bev=img_bev)
+        else:
+            conv_feat, stage_feats, extra = self.imgpts_neck(neck, extra_out=extra_view)
         ops.mark("focal_encoder")
         res = head(conv_feat, stage_feats, ms_value, geom)
         det = head.get_bboxes()
@@ -1009,7 +1100,7 @@ class FocalFormer3D(nn.Module):
         stages = None
         if keep_stages:
             stages = dict(vox=vox, bev=bev, backbone=xs, neck=neck, conv_feat=conv_feat, stage_feats=stage_feats,
-                          extra=extra, ms_value=ms_value, overflow=overflow, level_sizes=me.level_sizes)
+                          extra=extra, ms_value=ms_value, overflow=overflow, level_sizes=me.level_sizes, cam=cam)
         return res, det, stages
 
     def simple_test(self, points, img_metas=None, img=None, rescale=False):

@@ -256,6 +256,22 @@ def layernorm(x, gamma, beta, out=None, eps=1e-5):
     return out
 
 
+def local_attention(q, k, v, out, ksize):
+    """9x9 local-context attention on NHWC views: out[b,y,x,:] = sum_k softmax_k(q.k_nb / sqrt(C)) v_nb."""
+    B, H, W, Cc, ldq, qbs = _nhwc_geom(q, "local_attention.q")
+    _, _, _, _, ldk, kbs = _nhwc_geom(k, "local_attention.k")
+    _, _, _, _, ldv, vbs = _nhwc_geom(v, "local_attention.v")
+    _, _, _, _, ldo, obs = _nhwc_geom(out, "local_attention.out")
+    if not (qbs == kbs == vbs == obs == H * W):
+        raise L.Ff3dError("local_attention: batch-dense views required")
+    t0 = prof.begin()
+    check(lib.ff3d_local_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), ldo, B, H, W, Cc, ksize, _stream()),
+          "ff3d_local_attention")
+    prof.end(t0, f"local_attention[k{ksize} C{Cc}@{H}]", 4.0 * B * H * W * ksize * ksize * Cc, 16.0 * B * H * W * Cc)
+    _count()
+    return out
+
+
 def add_bcast_rows(a, p, out):
     """out[b] = a[b] + p for a [B, rows, C] contiguous, p [rows, C]."""
     assert a.is_contiguous() and p.is_contiguous() and out.is_contiguous()

@@ -148,10 +148,26 @@ def _head_spec(model_cfg, s):
         return _decoder_spec(model_cfg, s)
     s["imgpts_neck.shared_conv_pts.weight"] = ((hc, ne["in_channels_pts"], 3, 3), ("w", ne["in_channels_pts"] * 9))
     s["imgpts_neck.shared_conv_pts.bias"] = ((hc,), "b")
+    fused = bool(model_cfg.get("input_img", False))               # LiDAR + camera (FocalFormer3D_LC): 'bevfusion' blocks
     for i in range(ne["num_layers"] or 0):
-        _inverted_residual(s, f"imgpts_neck.fusion_blocks.{i}.P_IML", hc, hc, 2)
-        _inverted_residual(s, f"imgpts_neck.fusion_blocks.{i}.P_out_proj", 2 * hc, hc, 1)
-        _inverted_residual(s, f"imgpts_neck.fusion_blocks.{i}.P_integration", 2 * hc, hc, 1)
+        q = f"imgpts_neck.fusion_blocks.{i}"
+        if ne.get("iterbev", "bevfusion") == "bevfusionmb2":
+            _inverted_residual(s, f"{q}.P_IML", hc, hc, 2)
+            _inverted_residual(s, f"{q}.P_out_proj", 2 * hc, hc, 1)
+            _inverted_residual(s, f"{q}.P_integration", 2 * hc, hc, 1)
+        else:
+            # focal_encoder.py:40-43: LocalContextAttentionBlock(k=9) + two 1x1 ConvBN (encoder_utils.py:109-163)
+            for proj in ("query_project.0", "query_project.1", "key_project.0", "key_project.1", "value_project"):
+                # query / key gains make q.k / sqrt(C) spread over a few units: a peaked, not a flat, 81-way soft-max
+                s[f"{q}.P_IML.{proj}.conv.weight"] = ((hc, hc, 1, 1), ("w" if proj == "value_project" else "w_att", hc))
+                _bn(s, f"{q}.P_IML.{proj}.bn", hc)
+            for nm in ("P_out_proj", "P_integration"):
+                s[f"{q}.{nm}.conv.weight"] = ((hc, 2 * hc, 1, 1), ("w", 2 * hc))
+                _bn(s, f"{q}.{nm}.bn", hc)
+        if fused and not ne.get("iterbev_wo_img", False):
+            for n in (1, 2):                                      # iterimg_conv = resnet.BasicBlock (focal_encoder.py:50-52)
+                s[f"{q}.iterimg_conv.0.conv{n}.weight"] = ((hc, hc, 3, 3), ("w" if n == 1 else "w_res", hc * 9))
+                _bn(s, f"{q}.iterimg_conv.0.bn{n}", hc)
     if ne.get("extra_feat"):
         s["imgpts_neck.extra_output.conv.weight"] = ((hc, hc, 3, 3), ("w", hc * 9))
         _bn(s, "imgpts_neck.extra_output.bn", hc)
@@ -261,7 +277,7 @@ def make_state_dict(model_cfg, seed=0):
         if isinstance(kind, tuple):
             k, fan = kind
             gain = {"w": 1.0, "w_small": 0.5, "spw": 1.2, "spw_in": 1.2, "w_in": 1.0, "w_img": 1.0, "w_res": 0.3,
-                    "w_bev": 4.0}[k]
+                    "w_bev": 4.0, "w_att": 6.0}[k]
             t = torch.randn(shape, generator=g) * (gain / math.sqrt(fan))
             if k == "w_in":              # HardVFE linear [C, F] on raw point features
                 t[:, :3] /= 20.0

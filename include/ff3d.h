@@ -239,6 +239,13 @@ int ff3d_lss_splat(const float* dn, int ld, const float* frustum, const float* r
                    int B, int cams, int D, int fH, int fW, const float* lo3, const float* dx3, int nx, int ny, int nz,
                    ff3d_stream_t stream);
 
+/* Local-context attention of the 'bevfusion' FocalEncoderLayer (LiDAR + camera configs): replaces the JIT extension
+ * locatt_ops (similar_forward -> softmax(. / sqrt(C)) -> weighting_forward; models/utils/ops/locatt_ops/kernels.cuh:4-80,
+ * encoder_utils.py:155-163) in one pass.  q/k/v/y NHWC [B,H,W,C] views (batch-dense), C in {128, 256}, K odd (9).
+ * Neighbours outside the map score 0 inside the soft-max and add no value, exactly like the reference's kernels. */
+int ff3d_local_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* y, int ldy,
+                         int B, int H, int W, int C, int K, ff3d_stream_t stream);
+
 /* Misc elementwise helpers used by the head glue (all fp32). */
 int ff3d_add_rows(const float* a, const float* b, float* y, long long n, ff3d_stream_t stream);
 /* y[b, r, :] = a[b, r, :] + p[r, :]   (value + cached BEV positional embedding, focal_decoder.py:886) */

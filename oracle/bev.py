@@ -6,6 +6,7 @@
 """
 import torch
 from torch import nn
+import torch.nn.functional as F
 import torchvision.models.mobilenetv2 as mobilenetv2
 
 
@@ -82,46 +83,115 @@ class ConvBNReLU(nn.Module):
         return x
 
 
-class FocalEncoderLayer(nn.Module):
-    """focal_encoder.py:15-87, LiDAR-only 'bevfusionmb2' branch (iterbev_wo_img=True)."""
+def local_similar(x_ori, x_loc, kH, kW):
+    """locatt_ops similar_forward (kernels.cuh:4-42 `cc2k`, float in / double accumulate): y[b,h,w,k] =
+    sum_c x_ori[b,c,h,w] * x_loc[b,c,h+dy,w+dx], 0 for neighbours outside the map; k = (dy+rH)*kW + (dx+rW)."""
+    B, C, H, W = x_loc.shape
+    nb = F.unfold(x_loc.double(), (kH, kW), padding=(kH // 2, kW // 2)).view(B, C, kH * kW, H, W)
+    return (x_ori.double().unsqueeze(2) * nb).sum(1).permute(0, 2, 3, 1).float().contiguous()
 
-    def __init__(self, hidden_channel, iterbev="bevfusionmb2", iterbev_wo_img=True, **kw):
+
+def local_weighting(x_loc, weight, kH, kW):
+    """locatt_ops weighting_forward (kernels.cuh:44-80 `ck2c_ori`): y[b,c,h,w] = sum_k x_loc[b,c,h+dy,w+dx] * weight[b,h,w,k]."""
+    B, C, H, W = x_loc.shape
+    nb = F.unfold(x_loc.double(), (kH, kW), padding=(kH // 2, kW // 2)).view(B, C, kH * kW, H, W)
+    return (nb * weight.double().permute(0, 3, 1, 2).unsqueeze(1)).sum(2).float()
+
+
+class LocalContextAttentionBlock(nn.Module):
+    """encoder_utils.py:109-163: 9x9 local attention with 1x1 ConvBNReLU projections."""
+
+    def __init__(self, cin, cout, kernel_size):
         super().__init__()
-        assert iterbev == "bevfusionmb2" and iterbev_wo_img, "oracle covers the LiDAR-only mb2 branch"
-        IR = mobilenetv2.InvertedResidual
-        self.P_IML = IR(hidden_channel, hidden_channel, stride=1, expand_ratio=2, norm_layer=nn.BatchNorm2d)
-        self.P_out_proj = IR(2 * hidden_channel, hidden_channel, stride=1, expand_ratio=1, norm_layer=nn.BatchNorm2d)
-        self.P_integration = IR(2 * hidden_channel, hidden_channel, stride=1, expand_ratio=1, norm_layer=nn.BatchNorm2d)
+        self.kernel_size = kernel_size
+        mk = lambda: ConvBNReLU(cin, cout, kernel_size=1, norm_layer=nn.BatchNorm2d, activation_layer=nn.ReLU)
+        mk2 = lambda: ConvBNReLU(cout, cout, kernel_size=1, norm_layer=nn.BatchNorm2d, activation_layer=nn.ReLU)
+        self.query_project = nn.Sequential(mk(), mk2())
+        self.key_project = nn.Sequential(mk(), mk2())
+        self.value_project = mk()
+
+    def forward(self, target_feats, source_feats):
+        import math
+        query, key, value = self.query_project(target_feats), self.key_project(source_feats), self.value_project(source_feats)
+        k = self.kernel_size
+        weight = local_similar(query, key, k, k)                                           # :160
+        weight = F.softmax(weight / math.sqrt(key.size(1)), -1)                            # :161 (zeros of the padding take part)
+        self.debug = dict(query=query, key=key, value=value, weight=weight)
+        return local_weighting(value, weight, k, k)                                        # :162
+
+
+class FocalEncoderLayer(nn.Module):
+    """focal_encoder.py:15-87: 'bevfusionmb2' (LiDAR-only, iterbev_wo_img) and 'bevfusion' (LiDAR + camera BEV with
+    iter_bev_cam and no I2P projection: cam_lss supplies the image BEV feature) branches."""
+
+    def __init__(self, hidden_channel, iterbev="bevfusionmb2", iterbev_wo_img=True, iter_bev_cam=None, need_projbev=True,
+                 layer_id=None, **kw):
+        super().__init__()
+        self.iterbev, self.iterbev_wo_img = iterbev, iterbev_wo_img
+        hc = hidden_channel
+        if iterbev == "bevfusionmb2":
+            assert iterbev_wo_img, "oracle covers the LiDAR-only mb2 branch"
+            IR = mobilenetv2.InvertedResidual
+            self.P_IML = IR(hc, hc, stride=1, expand_ratio=2, norm_layer=nn.BatchNorm2d)
+            self.P_out_proj = IR(2 * hc, hc, stride=1, expand_ratio=1, norm_layer=nn.BatchNorm2d)
+            self.P_integration = IR(2 * hc, hc, stride=1, expand_ratio=1, norm_layer=nn.BatchNorm2d)
+        else:
+            assert iterbev == "bevfusion" and (iterbev_wo_img or (iter_bev_cam and not need_projbev)), \
+                "oracle covers 'bevfusion' with the camera BEV feature from cam_lss (no I2P projection block)"
+            self.P_IML = LocalContextAttentionBlock(hc, hc, 9)                              # :40
+            self.P_out_proj = ConvBNReLU(2 * hc, hc, kernel_size=1, norm_layer=nn.BatchNorm2d, activation_layer=None)
+            self.P_integration = ConvBNReLU(2 * hc, hc, kernel_size=1, norm_layer=nn.BatchNorm2d, activation_layer=None)
+        self.iterimg_conv = None
+        if not iterbev_wo_img:
+            import torchvision.models.resnet as resnet
+            self.iterimg_conv = nn.Sequential(resnet.BasicBlock(hc, hc, norm_layer=nn.BatchNorm2d))   # :50-52
 
     def forward(self, img_feat, lidar_feat, img_metas=None, extra_args=None):
-        I2P_feat = lidar_feat                                          # :70 (iterbev_wo_img)
-        P2P_feat = self.P_IML(lidar_feat)                              # :76
-        P_Aug_feat = self.P_out_proj(torch.cat((I2P_feat, P2P_feat), dim=1))       # :77
-        new_lidar_feat = self.P_integration(torch.cat((P_Aug_feat, lidar_feat), dim=1))  # :78
-        return None, new_lidar_feat
+        I2P_feat = lidar_feat if self.iterbev_wo_img else img_feat     # :58-70 (iter_bev_cam, need_projbev=False)
+        if self.iterbev == "bevfusion":
+            P2P_feat = self.P_IML(lidar_feat, lidar_feat)              # :72
+        else:
+            P2P_feat = self.P_IML(lidar_feat)                          # :76
+        P_Aug_feat = self.P_out_proj(torch.cat((I2P_feat, P2P_feat), dim=1))       # :73,77
+        new_lidar_feat = self.P_integration(torch.cat((P_Aug_feat, lidar_feat), dim=1))  # :74,78
+        new_img_feat = self.iterimg_conv(img_feat) if self.iterimg_conv is not None else None   # :82-85
+        return new_img_feat, new_lidar_feat
 
 
 class FocalEncoder(nn.Module):
-    """focal_encoder.py:90-222, input_img=False path."""
+    """focal_encoder.py:90-222: LiDAR-only (input_img=False) and LiDAR + camera (cam_lss) paths."""
 
     def __init__(self, num_layers=2, in_channels_img=64, in_channels_pts=384, hidden_channel=128, bn_momentum=0.1,
                  bias="auto", iterbev="bevfusion", max_points_height=5, multistage_heatmap=False, input_img=True,
-                 input_pts=True, iterbev_wo_img=False, extra_feat=False, **kw):
+                 input_pts=True, iterbev_wo_img=False, extra_feat=False, iter_bev_cam=False, cam_lss=False, pc_range=None,
+                 img_scale=None, **kw):
         super().__init__()
-        assert not input_img and input_pts
+        assert input_pts and (not input_img or (cam_lss and cam_lss != "proj"))
         self.iterbev_wo_img = iterbev_wo_img
         self.multistage_heatmap = multistage_heatmap
         self.input_img = input_img
         self.shared_conv_pts = nn.Conv2d(in_channels_pts, hidden_channel, 3, padding=1, bias=bool(bias))  # :120
+        if input_img:
+            from .camera import LiftSplatShoot
+            self.cam_lss = LiftSplatShoot(grid=0.6, inputC=256, outputC=hidden_channel, camC=64, pc_range=pc_range,
+                                          img_scale=img_scale, downsample=4)                 # :129-131
         self.num_layers = num_layers if num_layers else 0
         self.fusion_blocks = nn.ModuleList(
-            [FocalEncoderLayer(hidden_channel, iterbev=iterbev, iterbev_wo_img=iterbev_wo_img) for _ in range(self.num_layers)])
+            [FocalEncoderLayer(hidden_channel, iterbev=iterbev, iterbev_wo_img=iterbev_wo_img, iter_bev_cam=iter_bev_cam,
+                               need_projbev=not cam_lss, layer_id=i) for i in range(self.num_layers)])
         self.extra_feat = extra_feat
         if extra_feat:
             self.extra_output = ConvBNReLU(hidden_channel, hidden_channel, 3, norm_layer=nn.BatchNorm2d, activation_layer=None)
 
     def forward(self, img_feats, pts_feats, img_metas=None):
         new_img_feat = None
+        if self.input_img:                                             # :173-197
+            from .camera import lidar2img_to_rots_trans
+            B = len(img_metas)
+            rots, trans = zip(*[lidar2img_to_rots_trans(m["lidar2img"]) for m in img_metas])
+            rots, trans = torch.stack(rots).to(img_feats), torch.stack(trans).to(img_feats)
+            new_img_feat, _ = self.cam_lss(img_feats.view(B, -1, *img_feats.shape[-3:]), rots, trans)
+            self.debug = dict(img_bev=new_img_feat)
         new_pts_feat = self.shared_conv_pts(pts_feats)                 # :204
         pts_feat_conv = new_pts_feat.clone()                           # :207
         if self.input_img or self.iterbev_wo_img:

@@ -27,14 +27,15 @@ class FocalFormer3D(nn.Module):
         head = _strip(pts_bbox_head)
         head["test_cfg"] = test_cfg["pts"] if test_cfg and "pts" in test_cfg else test_cfg
         if input_img:
-            # camera-only (DeformFormer3D_C_R50): focalformer3d.py:133-153 + focal_encoder.py:171-197
-            assert not input_pts, "oracle covers LiDAR-only and camera-only configs (fusion is the next scope row)"
+            # image tower (focalformer3d.py:133-153); camera-only (DeformFormer3D_C_R50) stops here, the fusion config
+            # (FocalFormer3D_LC) also builds the LiDAR tower below
             from .camera import ResNet50, FPN, CameraFocalEncoder
             self.img_backbone = ResNet50(**unused.get("img_backbone", {}))
             self.img_neck = FPN(**_strip(unused["img_neck"]))
-            self.imgpts_neck = CameraFocalEncoder(**_strip(imgpts_neck))
-            self.pts_bbox_head = FocalDecoder(**head)
-            return
+            if not input_pts:
+                self.imgpts_neck = CameraFocalEncoder(**_strip(imgpts_neck))
+                self.pts_bbox_head = FocalDecoder(**head)
+                return
         self.voxel_cfg = pts_voxel_layer
         ve = _strip(pts_voxel_encoder)
         if pts_voxel_encoder["type"] == "HardSimpleVFE":
@@ -44,7 +45,7 @@ class FocalFormer3D(nn.Module):
         self.pts_middle_encoder = SparseEncoder(**_strip(pts_middle_encoder))
         self.pts_backbone = SECOND(**_strip(pts_backbone))
         self.pts_neck = SECONDFPN(**_strip(pts_neck))
-        self.imgpts_neck = FocalEncoder(**_strip(imgpts_neck))
+        self.imgpts_neck = FocalEncoder(**_strip(imgpts_neck))      # the neck's own input_img default (True) applies
         self.pts_bbox_head = FocalDecoder(**head)
 
     def voxelize(self, points):
@@ -75,13 +76,18 @@ class FocalFormer3D(nn.Module):
     def forward_raw(self, points, stages=None, img=None, img_metas=None):
         """points: list[B] of [Ni, F] (or None for camera-only) -> (head output dict, list of per-scene result dicts).
         img: [B, N, 3, H, W]; img_metas: list[B] of dict(lidar2img=[N, 4, 4])."""
+        feats = [None]
         if self.input_img:
             B, N, C, H, W = img.shape
             c = self.img_backbone(img.view(B * N, C, H, W).float())                          # focalformer3d.py:133-153
             feats = self.img_neck(c)
             if stages is not None:
                 stages["img_backbone"], stages["img_feat"] = c, feats[0]
+        if self.input_img and not self.input_pts:
             _, new_pts = self.imgpts_neck(feats[0], None, img_metas)                          # only level 0 (:186)
+        elif self.input_img:
+            pts_feats = self.extract_pts_feat(points, stages)
+            _, new_pts = self.imgpts_neck(feats[0], pts_feats[0], img_metas)                  # :177-187
         else:
             pts_feats = self.extract_pts_feat(points, stages)
             _, new_pts = self.imgpts_neck(None, pts_feats[0], None)

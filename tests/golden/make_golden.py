@@ -127,7 +127,12 @@ def install_stubs():
     _pkg("projects.mmdet3d_plugin", base)
     for sub in ("models", "models/utils", "models/dense_heads", "models/necks", "core", "core/bbox", "core/bbox/coders"):
         _pkg("projects.mmdet3d_plugin." + sub.replace("/", "."), os.path.join(base, sub))
-    _mod("projects.mmdet3d_plugin.models.utils.ops", locatt_ops=None)          # JIT CUDA extension, LC configs only
+    # locatt_ops is a JIT-compiled CUDA extension (needs a GPU + nvcc at import): its two forward entry points are
+    # served by the oracle's restatement of kernels.cuh (oracle/bev.py local_similar / local_weighting)
+    from oracle import bev as obev
+    locatt = types.SimpleNamespace(localattention=types.SimpleNamespace(
+        similar_forward=obev.local_similar, weighting_forward=obev.local_weighting))
+    _mod("projects.mmdet3d_plugin.models.utils.ops", locatt_ops=locatt)
     # the copied-from-mmdet transformer.py is star-imported by focal_decoder.py but nothing of it is used
     _mod("projects.mmdet3d_plugin.models.utils.transformer")
     return LiDARInstance3DBoxes
@@ -202,6 +207,35 @@ def main():
     n = sum(t.numel() for t in _tensors(out))
     print(f"wrote {os.path.join(OUT, 'focalformer3d_l_intree.pt')} ({n} values)")
     camera_golden(fe)
+    fusion_golden(fe)
+
+
+def fusion_golden(fe):
+    """Real FocalEncoder, LiDAR + camera path of FocalFormer3D_LC (focal_encoder.py:171-219: cam_lss camera BEV,
+    shared_conv_pts, two 'bevfusion' FocalEncoderLayers = LocalContextAttentionBlock + 1x1 ConvBN fusion + BasicBlock on
+    the camera BEV, extra_output) on a reduced size.  The locatt CUDA extension is served by the oracle restatement."""
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_fusion_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_cameras
+    img_hw, bev = (32, 64), 16
+    cfg = scaled_fusion_cfg(load_config(default_config_path("focalformer3d_lc"))["model"], bev=bev, img_hw=img_hw, num_proposals=12)
+    sd = make_state_dict(cfg, seed=8)
+    g = torch.Generator().manual_seed(13)
+    ne = dict(cfg["imgpts_neck"]); ne.pop("type")
+    with no_cuda_device():
+        enc = fe.FocalEncoder(**ne).eval()
+        enc.load_state_dict({k[len("imgpts_neck."):]: v for k, v in sd.items() if k.startswith("imgpts_neck.")}, strict=True)
+        B, N = 2, 6
+        feat = torch.randn(B * N, 256, img_hw[0] // 4, img_hw[1] // 4, generator=g) * 0.7
+        neck = torch.randn(B, 512, bev, bev, generator=g) * 0.3
+        metas = [dict(lidar2img=synth_cameras(N, img_hw, seed=60 + b)) for b in range(B)]
+        with torch.no_grad():
+            new_img, (conv_feat, stage_list) = enc(feat, neck, metas)
+    out = dict(img_hw=img_hw, bev=bev, weights_seed=8, feat=feat, neck=neck,
+               lidar2img=torch.stack([torch.as_tensor(m["lidar2img"]) for m in metas]), conv_feat=conv_feat.clone(),
+               stage_feats=[t.clone() for t in stage_list], new_img_feat=new_img.clone())
+    path = os.path.join(OUT, "focalformer3d_lc_encoder.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({sum(t.numel() for t in _tensors(out))} values)")
 
 
 def camera_golden(fe):

@@ -229,3 +229,26 @@ def test_cuda_lss_matches_reference_golden():
     assert torch.equal(ours != 0, ref != 0), "voxel indices differ from the reference's"
     assert (ours - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
     _close(_nchw(out), gold["bev_out"], "bevencode output vs reference")
+
+
+def test_cuda_fusion_encoder_matches_reference_golden():
+    """CUDA FocalEncoder fusion path (Lift-Splat-Shoot + 9x9 local attention + 1x1 fusion convs + BasicBlock) against the
+    fixture produced by the REAL reference FocalEncoder."""
+    import os
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_fusion_cfg
+    from focalformer3d_b200.synth import make_state_dict
+    from focalformer3d_b200.model import build_model
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "focalformer3d_lc_encoder.pt")
+    gold = torch.load(path, map_location="cpu")
+    cfg = scaled_fusion_cfg(load_config(default_config_path("focalformer3d_lc"))["model"], bev=gold["bev"],
+                            img_hw=gold["img_hw"], num_proposals=12)
+    model = build_model(cfg)
+    model.load_state_dict(make_state_dict(cfg, seed=gold["weights_seed"]), strict=True)
+    model.prepare("cuda")
+    metas = [dict(lidar2img=m.numpy()) for m in gold["lidar2img"]]
+    feat = gold["feat"].permute(0, 2, 3, 1).contiguous().cuda()
+    neck = gold["neck"].permute(0, 2, 3, 1).contiguous().cuda()
+    conv_feat, stages, extra, img_bev = model.imgpts_neck.forward_fusion(neck, feat, metas, None)
+    _close(_nchw(conv_feat), gold["conv_feat"], "shared conv")
+    for i, (a, b) in enumerate(zip(stages + [extra], gold["stage_feats"])):
+        _close(_nchw(a), b, f"fused stage feature {i}")

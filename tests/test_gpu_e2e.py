@@ -39,7 +39,20 @@ def _deform_tiny():
     return cfg, make_state_dict(cfg, 2), pts
 
 
-@pytest.fixture(scope="module", params=["nuscenes_l", "waymo_l", "deformformer_l"])
+def _fusion_tiny():
+    """FocalFormer3D_LC: LiDAR tower + image tower + Lift-Splat-Shoot + two 'bevfusion' layers (9x9 local attention)."""
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_fusion_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_points, synth_cameras
+    hw = (64, 96)
+    cfg = scaled_fusion_cfg(load_config(default_config_path("focalformer3d_lc"))["model"], bev=24, img_hw=hw, num_proposals=16)
+    pts = [torch.from_numpy(synth_points(n, cfg["pts_voxel_layer"]["point_cloud_range"], seed=30 + s))
+           for s, n in enumerate((6000, 5000))]
+    img = torch.randn(2, 6, 3, *hw, generator=torch.Generator().manual_seed(7))
+    metas = [dict(lidar2img=synth_cameras(6, hw, seed=50 + b)) for b in range(2)]
+    return cfg, make_state_dict(cfg, 4), pts, img, metas
+
+
+@pytest.fixture(scope="module", params=["nuscenes_l", "waymo_l", "deformformer_l", "fusion_lc"])
 def pair(request, tiny_cfg, tiny_sd, tiny_points):
     from focalformer3d_b200.model import build_model
     from oracle.detector import build_oracle
@@ -47,17 +60,21 @@ def pair(request, tiny_cfg, tiny_sd, tiny_points):
         tiny_cfg, tiny_sd, tiny_points = _waymo_tiny()
     if request.param == "deformformer_l":    # no HIP: single averaged heatmap, one decoder stage, no ROI, no fusion layers
         tiny_cfg, tiny_sd, tiny_points = _deform_tiny()
+    kw, okw = {}, {}
+    if request.param == "fusion_lc":
+        tiny_cfg, tiny_sd, tiny_points, img, metas = _fusion_tiny()
+        kw, okw = dict(img=img.cuda(), img_metas=metas), dict(img=img, img_metas=metas)
     model = build_model(tiny_cfg)
     model.load_state_dict(tiny_sd, strict=True)
-    model.cuda().prepare("cuda")
-    res, det, st = model.forward_raw([p.cuda() for p in tiny_points], keep_stages=True)
+    model.prepare("cuda")
+    res, det, st = model.forward_raw([p.cuda() for p in tiny_points], keep_stages=True, **kw)
     torch.cuda.synchronize()
     oracle = build_oracle(tiny_cfg)
     oracle.load_state_dict(tiny_sd, strict=True)
     ost = {}
-    ref, rdet = oracle.forward_raw(tiny_points, ost)
+    ref, rdet = oracle.forward_raw(tiny_points, ost, **okw)
     return dict(model=model, res=res, det=det, st=st, oracle=oracle, ref=ref, rdet=rdet, ost=ost, points=tiny_points,
-                name=request.param)
+                name=request.param, kw=kw)
 
 
 def test_voxel_stage(pair):
@@ -91,10 +108,16 @@ def test_bev_stages(pair):
     for a, b in zip(st["stage_feats"], feats[:-1]):
         _close(_nchw(a), b, "FocalEncoder stage feature")
     _close(_nchw(st["extra"]), feats[-1], "FocalEncoder extra feature")
+    if pair["name"] == "fusion_lc":
+        for i, (a, b) in enumerate(zip(st["cam"]["img_backbone"], ost["img_backbone"])):
+            _close(_nchw(a), b, f"ResNet-50 stage {i}")
+        _close(_nchw(st["cam"]["img_feat"]), ost["img_feat"], "FPN level 0")
+        _close(_nchw(st["cam"]["img_bev"]), pair["oracle"].imgpts_neck.debug["img_bev"], "camera BEV (Lift-Splat-Shoot)")
 
 
 def test_hip_stage_outputs(pair):
     res, dbg = pair["res"], pair["oracle"].pts_bbox_head.debug
+    assert len(res["dense_heatmap"]) == len(pair["ref"]["dense_heatmap"])
     for a, b in zip(res["dense_heatmap"], pair["ref"]["dense_heatmap"]):
         assert (a.cpu() - b).abs().max().item() < TOL
         assert (a.cpu().sigmoid() - b.sigmoid()).abs().max().item() < TOL
@@ -156,7 +179,7 @@ def test_final_boxes(pair):
 
 def test_simple_test_signature(pair):
     tiny_points = pair["points"]
-    out = pair["model"].simple_test([p.cuda() for p in tiny_points])
+    out = pair["model"].simple_test([p.cuda() for p in tiny_points], **pair["kw"])
     assert len(out) == len(tiny_points)
     for o in out:
         d = o["pts_bbox"]
@@ -168,11 +191,16 @@ def test_determinism_and_batch_independence(pair):
     """Size-independent properties: same inputs -> bit-identical outputs; a scene's result does not depend on its
     batch neighbours (scenes never exchange data: the basis of scene-level data parallelism)."""
     model, tiny_points = pair["model"], pair["points"]
-    r1, d1, _ = model.forward_raw([p.cuda() for p in tiny_points])
-    r2, d2, _ = model.forward_raw([p.cuda() for p in tiny_points])
+    kw = pair["kw"]
+    r1, d1, _ = model.forward_raw([p.cuda() for p in tiny_points], **kw)
+    r2, d2, _ = model.forward_raw([p.cuda() for p in tiny_points], **kw)
     for k in ("center", "dim", "heatmap"):
-        assert torch.equal(r1[k], r2[k])
-    r3, d3, _ = model.forward_raw([tiny_points[1].cuda()])
+        if kw:      # camera BEV pooling sums with atomics: the addition order (last bits) is not fixed run to run
+            assert (r1[k] - r2[k]).abs().max().item() < 1e-4
+        else:
+            assert torch.equal(r1[k], r2[k])
+    kw1 = dict(img=kw["img"][1:2], img_metas=kw["img_metas"][1:2]) if kw else {}
+    r3, d3, _ = model.forward_raw([tiny_points[1].cuda()], **kw1)
     assert torch.equal(r3["_top_proposals"][0][0], r1["_top_proposals"][0][1])
     assert (r3["center"][0] - r1["center"][1]).abs().max().item() < 1e-4
 

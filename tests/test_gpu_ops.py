@@ -490,3 +490,25 @@ def test_tcgemm_conv_small_cin_taps_share_a_kstep(ops):
         assert pw.img is not None
         ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), pw, None, out, 3)
         assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 13, 17, 128), (1, 24, 24, 128), (1, 5, 4, 256)])
+def test_local_attention(shape):
+    """ff3d_local_attention vs the oracle's restatement of locatt_ops (similar -> softmax -> weighting), incl. the
+    zero-scored out-of-map neighbours that take part in the soft-max."""
+    from focalformer3d_b200 import ops
+    from oracle.bev import local_similar, local_weighting
+    import math
+    B, H, W, C = shape
+    g = torch.Generator().manual_seed(H * 100 + W)
+    q, k, v = (torch.randn(B, C, H, W, generator=g) * s for s in (1.3, 1.3, 1.0))
+    w = torch.softmax(local_similar(q, k, 9, 9) / math.sqrt(C), -1)
+    ref = local_weighting(v, w, 9, 9)
+    assert w.max().item() > 0.3                      # peaked soft-max: the test is sensitive to the scores
+    # operands as channel slices of a wider buffer (how the encoder feeds them)
+    buf = torch.zeros(B, H, W, 3 * C + 4, device="cuda")
+    buf[..., :C], buf[..., C:2 * C], buf[..., 2 * C:3 * C] = (t.permute(0, 2, 3, 1).cuda() for t in (q, k, v))
+    out = torch.empty(B, H, W, 2 * C, device="cuda")
+    ops.local_attention(buf[..., :C], buf[..., C:2 * C], buf[..., 2 * C:3 * C], out[..., C:], 9)
+    err = (out[..., C:].permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
+    assert err < 2e-5, err
