@@ -216,6 +216,27 @@ __global__ void head_update_kernel(float* __restrict__ pred, int ldp, float* __r
   }
 }
 
+
+// class-aware regression (focal_decoder.py:940-943): the heads emit one (centre, height, dim, rot) set per class,
+// channel = class * k + d; every query keeps the set of its own class.  full rows = [g0: nc*k0 | g1: nc*k1 | ... | tail],
+// out rows = [k0 | k1 | ... | tail].  One thread per (row, output column).
+struct ClsSelP { int n_groups, k[8], tail, nc, ld_full, ld_out; };
+__global__ void class_select_kernel(const float* __restrict__ full, const int* __restrict__ label, ClsSelP p,
+                                    float* __restrict__ out, int rows, int out_cols) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)rows * out_cols) return;
+  int r = (int)(e / out_cols), c = (int)(e - (long long)r * out_cols);
+  int lab = min(max(label[r], 0), p.nc - 1);
+  int src = 0, c0 = 0;
+  bool done = false;
+  for (int g = 0; g < p.n_groups; ++g) {
+    if (!done && c < c0 + p.k[g]) { src += lab * p.k[g] + (c - c0); done = true; }
+    if (!done) { src += p.nc * p.k[g]; c0 += p.k[g]; }
+  }
+  if (!done) src += c - c0;                                // tail (class logits): copied through
+  out[(size_t)r * p.ld_out + c] = full[(size_t)r * p.ld_full + src];
+}
+
 struct DecP {
   int C, has_vel, cls_col, ldp;
   float cell_x, cell_y, origin_x, origin_y, pr[6];
@@ -335,4 +356,18 @@ extern "C" int ff3d_box_decode(const float* pred, int ldp, int cls_col, int has_
   box_decode_kernel<<<cdiv(rows, 128), 128, 0, as_stream(stream)>>>(pred, query_score, query_label, p, boxes, scores,
                                                                     labels, keep, rows);
   return check_launch("ff3d_box_decode");
+}
+
+extern "C" int ff3d_class_select(const float* full, int ld_full, const int* label, const int* group_k, int n_groups, int tail,
+                                 int num_classes, float* out, int ld_out, int rows, ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(n_groups > 0 && n_groups <= 8 && num_classes > 0 && tail >= 0, "class_select: bad group description");
+  if (rows <= 0) return FF3D_OK;
+  ClsSelP p;
+  p.n_groups = n_groups; p.tail = tail; p.nc = num_classes; p.ld_full = ld_full; p.ld_out = ld_out;
+  int out_cols = tail;
+  for (int g = 0; g < 8; ++g) { p.k[g] = g < n_groups ? group_k[g] : 0; out_cols += p.k[g]; }
+  FF3D_REQUIRE(out_cols <= ld_out, "class_select: output row too narrow");
+  class_select_kernel<<<cdiv((long long)rows * out_cols, 256), 256, 0, as_stream(stream)>>>(full, label, p, out, rows, out_cols);
+  return check_launch("ff3d_class_select");
 }

@@ -215,6 +215,49 @@ __global__ void vox_gather_kernel(const float* __restrict__ pts, const int* __re
   }
 }
 
+
+// Dynamic voxelisation + DynamicSimpleVFE ([upstream] mmdet3d v0.17.1 Voxelization(max_num_points=-1) + DynamicScatter
+// mean, DeformFormer3D_L_dynamic.py): no per-voxel point cap, no voxel cap; the voxel feature is the mean of ALL its
+// points.  Sums are accumulated in fp64 atomics (the addition order then only matters below fp32 resolution).
+__global__ void vox_assign_dynamic_kernel(const float* __restrict__ pts, const int* __restrict__ pt_slot,
+                                          const int* __restrict__ hfirst, const uint32_t* __restrict__ hkeys,
+                                          const int* __restrict__ rank, const int* __restrict__ meta, VoxP p,
+                                          double* sums, int* num_points, int* coors) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_total) return;
+  int s = pt_slot[i];
+  if (s < 0) return;
+  int f = hfirst[s];
+  int b = sample_of(p, i);
+  int local = rank[f] - meta[b];
+  if (local >= p.max_voxels) return;
+  int vid = meta[p.batch + b] + local;
+  if (f == i) {
+    uint32_t key = hkeys[s];
+    int x = key % p.g[0];
+    uint32_t r = key / p.g[0];
+    int y = r % p.g[1];
+    r /= p.g[1];
+    int z = r % p.g[2];
+    coors[vid * 4 + 0] = b;
+    coors[vid * 4 + 1] = z;
+    coors[vid * 4 + 2] = y;
+    coors[vid * 4 + 3] = x;
+  }
+  atomicAdd(&num_points[vid], 1);
+  const float* q = pts + (size_t)i * p.n_feat;
+  for (int c = 0; c < p.n_feat; ++c) atomicAdd(&sums[(size_t)vid * 8 + c], (double)q[c]);
+}
+
+__global__ void vox_dynamic_mean_kernel(const double* __restrict__ sums, const int* __restrict__ num_points,
+                                        const int* __restrict__ n_voxels_dev, int n_feat, float* mean_feats, int mean_ld) {
+  int vid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vid >= n_voxels_dev[0]) return;
+  double inv = 1.0 / (double)num_points[vid];
+  for (int c = 0; c < mean_ld; ++c)
+    mean_feats[(size_t)vid * mean_ld + c] = (c < n_feat && c < 8) ? (float)(sums[(size_t)vid * 8 + c] * inv) : 0.f;
+}
+
 // HardVFE (single VFELayer, max-pool): out[v, c] = max_k relu( sum_f x[v,k,f] * w[f,c] + b[c] ) over ALL max_points
 // slots, padded slots contributing relu(b[c]) (their features are masked to zero first) -- [upstream] mmdet3d v0.17.1
 // HardVFE/VFELayer as configured at projects/configs/focalformer3d/FocalFormer3D_Waymo_L.py:141-152.  BN folded into w, b.
@@ -261,7 +304,9 @@ static VoxWs vox_layout(int n_total, int batch, int max_voxels, int max_points) 
   w.rank = take(sizeof(int) * ((size_t)n_total + 1));
   w.bsum = take(sizeof(int) * (cdiv(n_total, SCAN_ELEMS) + 2));
   w.meta = take(sizeof(int) * 2 * FF3D_MAX_BATCH);
-  w.slots = take(sizeof(int) * (size_t)batch * max_voxels * max_points);
+  // hard mode: per-voxel point slots; dynamic mode (max_points <= 0): fp64 feature sums [cap][8]
+  w.slots = max_points > 0 ? take(sizeof(int) * (size_t)batch * max_voxels * max_points)
+                           : take(sizeof(double) * (size_t)batch * max_voxels * 8);
   w.total = o;
   return w;
 }
@@ -281,7 +326,9 @@ extern "C" int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, 
   FF3D_REQUIRE(batch >= 1 && batch <= FF3D_MAX_BATCH, "voxelize: batch=%d out of range", batch);
   FF3D_REQUIRE(n_feat >= 3 && n_feat <= 8, "voxelize: n_feat=%d (3..8 supported)", n_feat);
   FF3D_REQUIRE(points && coors && num_points && n_voxels_dev && workspace, "voxelize: null pointer");
-  FF3D_REQUIRE(max_points >= 1 && max_voxels >= 1, "voxelize: bad caps");
+  const bool dynamic = max_points <= 0;        // mmdet3d Voxelization(max_num_points=-1): no point cap, mean of all points
+  FF3D_REQUIRE(max_voxels >= 1, "voxelize: bad caps (dynamic mode: pass the largest per-sample point count as max_voxels)");
+  FF3D_REQUIRE(!dynamic || (voxels == nullptr && mean_feats != nullptr), "voxelize: dynamic mode returns means only");
   VoxP p;
   p.n_total = n_total; p.n_feat = n_feat; p.batch = batch;
   for (int b = 0; b <= batch; ++b) p.off[b] = batch_offsets_host[b];
@@ -312,7 +359,12 @@ extern "C" int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, 
   int* slots = reinterpret_cast<int*>(base + w.slots);
   cudaMemsetAsync(hkeys, 0xFF, sizeof(uint32_t) * w.hsize, st);
   cudaMemsetAsync(hfirst, 0x7f, sizeof(int) * w.hsize, st);
-  cudaMemsetAsync(slots, 0x7f, sizeof(int) * (size_t)batch * max_voxels * max_points, st);
+  if (dynamic) {
+    cudaMemsetAsync(slots, 0, sizeof(double) * (size_t)batch * max_voxels * 8, st);
+    cudaMemsetAsync(num_points, 0, sizeof(int) * (size_t)batch * max_voxels, st);
+  } else {
+    cudaMemsetAsync(slots, 0x7f, sizeof(int) * (size_t)batch * max_voxels * max_points, st);
+  }
   if (n_total == 0) {
     cudaMemsetAsync(n_voxels_dev, 0, sizeof(int) * (1 + batch), st);
     return check_launch("voxelize(empty)");
@@ -323,6 +375,13 @@ extern "C" int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, 
   int rc = exclusive_scan_i32(flag, rank, n_total, bsum, st);
   if (rc) return rc;
   vox_meta_kernel<<<1, 32, 0, st>>>(rank, p, meta, n_voxels_dev);
+  if (dynamic) {
+    double* sums = reinterpret_cast<double*>(base + w.slots);
+    vox_assign_dynamic_kernel<<<nb, 256, 0, st>>>(points, pt_slot, hfirst, hkeys, rank, meta, p, sums, num_points, coors);
+    vox_dynamic_mean_kernel<<<cdiv((long long)batch * max_voxels, 128), 128, 0, st>>>(sums, num_points, n_voxels_dev, n_feat,
+                                                                                    mean_feats, mean_ld);
+    return check_launch("ff3d_voxelize_hard(dynamic)");
+  }
   vox_assign_kernel<<<nb, 256, 0, st>>>(pt_slot, hfirst, hkeys, rank, meta, p, slots, coors);
   vox_gather_kernel<<<cdiv((long long)batch * max_voxels, 128), 128, 0, st>>>(points, slots, n_voxels_dev, p, voxels,
                                                                              num_points, mean_feats, mean_ld);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ff3d_box_decode": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _F, _F, _F, _F, _FP, _P, _P, _P, _P, _P]),
     "ff3d_add_rows": (_I, [_P, _P, _P, _LL, _P]),
     "ff3d_add_bcast_rows": (_I, [_P, _P, _P, _I, _LL, _I, _P]),
+    "ff3d_class_select": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P]),
     "ff3d_local_attention": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ff3d_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ff3d_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _P]),

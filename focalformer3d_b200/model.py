@@ -102,6 +102,15 @@ class HardSimpleVFE(ParamTree):
 
 
 @VOXEL_ENCODERS.register_module()
+class DynamicSimpleVFE(ParamTree):
+    """[upstream] mmdet3d v0.17.1 DynamicSimpleVFE (DynamicScatter mean over ALL points of a voxel) as configured at
+    DeformFormer3D_L_dynamic.py; computed inside the dynamic mode of the voxeliser (fp64 atomic sums)."""
+
+    def __init__(self, voxel_size=None, point_cloud_range=None, spec=None, **kw):
+        super().__init__()
+
+
+@VOXEL_ENCODERS.register_module()
 class HardVFE(ParamTree):
     """[upstream] mmdet3d v0.17.1 HardVFE as configured by the Waymo configs (FocalFormer3D_Waymo_L.py:141-152):
     no distance / cluster-centre / voxel-centre features, one VFELayer (Linear no-bias + BN1d + ReLU), max over points."""
@@ -673,8 +682,9 @@ class FocalDecoder(ParamTree):
                  **unused):
         super().__init__()
         if not (initialize_by_heatmap and multiscale and bevpos and mask_heatmap_mode == "poscls") \
-                or heatmap_box or classaware_reg or boxpos is not None:
+                or heatmap_box or boxpos is not None:
             raise NotImplementedError("FocalDecoder: only the shipped LiDAR head variants are built")
+        self.classaware_reg = bool(classaware_reg)
         if not loss_cls.get("use_sigmoid", False):
             # focal_decoder.py:164-166 appends a background class in that case; no shipped config uses it
             raise NotImplementedError("FocalDecoder: only loss_cls.use_sigmoid=True heads are built")
@@ -776,7 +786,8 @@ class FocalDecoder(ParamTree):
             st["vproj"] = (pack_linear(torch.cat(vw), None, dev), vec(torch.cat(vb), dev))   # 3 layers batched: N = 3*hc
             # prediction heads: 6 x (Conv1d hc->64 + BN + ReLU, Conv1d 64->k): one GEMM + one block-diagonal GEMM
             names = list(self.common_heads.keys()) + ["heatmap"]
-            ks = [self.common_heads[n][0] for n in self.common_heads] + [nc]
+            mult = nc if self.classaware_reg else 1                 # :317-319 one regression set per class
+            ks = [self.common_heads[n][0] * mult for n in self.common_heads] + [nc]
             w1, b1 = [], []
             w2 = torch.zeros((sum(ks), 64 * len(names)), dtype=torch.float64)
             b2, r0 = [], 0
@@ -907,6 +918,9 @@ class FocalDecoder(ParamTree):
                 x = ops.layernorm(y, *lay["ln"][2])
             hh = ops.linear(x, st["head1"][0], st["head1"][1], act=ACT_RELU)               # :939
             pred = ops.linear(hh, st["head2"][0], st["head2"][1], cout=st["pred_dim"])
+            if self.classaware_reg:                                                        # :940-943
+                gk = [self.common_heads[n][0] for n in self.common_heads]
+                pred = ops.class_select(pred, q_label, gk, nc, nc, _pad4(sum(gk) + nc))
             q_pos = q_pos.clone()
             ops.head_update(pred, q_pos, prev if (self.roi_based_reg and prev is not None) else None)   # :945-957
             preds.append(pred)
@@ -1055,11 +1069,14 @@ class FocalFormer3D(nn.Module):
         vc = self.voxel_cfg
         mv = vc["max_voxels"]
         mv = mv[1] if isinstance(mv, (tuple, list)) else mv
-        mv = min(mv, max(int(p.shape[0]) for p in points))
+        n_max = max(max(int(p.shape[0]) for p in points), 1)
+        # focalformer3d.py:80,159-163: a 'Dynamic*' voxel encoder switches to dynamic voxelisation (no caps)
+        dynamic = isinstance(self.pts_voxel_encoder, DynamicSimpleVFE)
+        mv = n_max if (dynamic or mv <= 0) else min(mv, n_max)
         ops.mark("start")
         hard_vfe = isinstance(self.pts_voxel_encoder, HardVFE)
-        vox = ops.voxelize(allp, offs, vc["voxel_size"], vc["point_cloud_range"], vc["max_num_points"], mv,
-                           mean_ld=8, want_voxels=keep_stages or hard_vfe)
+        vox = ops.voxelize(allp, offs, vc["voxel_size"], vc["point_cloud_range"], -1 if dynamic else vc["max_num_points"], mv,
+                           mean_ld=8, want_voxels=(keep_stages and not dynamic) or hard_vfe)
         if hard_vfe:
             vox["mean"] = self.pts_voxel_encoder(vox, vc["max_num_points"])      # [cap, 64] learned voxel features
         ops.mark("voxelize+vfe")

@@ -351,6 +351,8 @@ def voxelize(points, batch_offsets, voxel_size, pc_range, max_points, max_voxels
     nump = torch.empty((cap,), dtype=torch.int32, device=dev)
     mean = torch.empty((cap, mean_ld), dtype=torch.float32, device=dev)
     n_dev = torch.empty((1 + B,), dtype=torch.int32, device=dev)
+    if max_points <= 0 and want_voxels:
+        raise L.Ff3dError("voxelize: dynamic mode (max_points <= 0) returns per-voxel means only")
     voxels = torch.empty((cap, max_points, F), dtype=torch.float32, device=dev) if want_voxels else None
     check(lib.ff3d_voxelize_hard(_ptr(points), N, F, L.int_array(batch_offsets), B, L.float_array(voxel_size),
                                  L.float_array(pc_range), max_points, max_voxels, _ptr(voxels), _ptr(coors),
@@ -503,6 +505,17 @@ def head_update(pred, query_pos, prev):
     check(lib.ff3d_head_update(_ptr(pred), pred.stride(0), _ptr(query_pos), _ptr(prev),
                                prev.stride(0) if prev is not None else 0, pred.shape[0], _stream()), "ff3d_head_update")
     _count()
+
+
+def class_select(full, label, group_k, tail, num_classes, out_cols_ld):
+    """full [rows, ld] = [nc*k0 | nc*k1 | ... | tail] -> [rows, out_cols_ld] keeping each row's own class set."""
+    rows = full.shape[0]
+    out = torch.zeros((rows, out_cols_ld), dtype=torch.float32, device=full.device)
+    gk = (C.c_int * len(group_k))(*group_k)
+    check(lib.ff3d_class_select(_ptr(full), full.stride(0), _ptr(label), gk, len(group_k), tail, num_classes, _ptr(out),
+                                out.stride(0), rows, _stream()), "ff3d_class_select")
+    _count()
+    return out
 
 
 def box_decode(pred, cls_col, has_vel, query_score, query_label, Cc, cell, origin, post_range, boxes, scores, labels,

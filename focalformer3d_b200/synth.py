@@ -99,7 +99,7 @@ def param_spec(model_cfg):
     taps = (3.0, 10.0, 16.0, 21.0)        # measured mean active taps per SubM level on LiDAR-like clouds
     # raw point statistics reach conv_input only with the mean VFE; HardVFE hands it O(1) learned features
     s[f"{p}.conv_input.0.weight"] = ((3, 3, 3, me["in_channels"], base),
-                                     ("spw_in" if ve["type"] == "HardSimpleVFE" else "spw", me["in_channels"] * taps[0]))
+                                     ("spw_in" if ve["type"] in ("HardSimpleVFE", "DynamicSimpleVFE") else "spw", me["in_channels"] * taps[0]))
     _bn(s, f"{p}.conv_input.1", base)
     cin = base
     enc = me["encoder_channels"]
@@ -241,6 +241,8 @@ def _decoder_spec(model_cfg, s):
                 s[f"{q}.norms.{n}.weight"] = ((hc,), "ln_w")
                 s[f"{q}.norms.{n}.bias"] = ((hc,), "b")
         heads = dict(hd["common_heads"])
+        if hd.get("classaware_reg"):                      # focal_decoder.py:317-319: one regression set per class
+            heads = {k_: (v_[0] * nc, v_[1]) for k_, v_ in heads.items()}
         heads["heatmap"] = (nc, hd.get("num_heatmap_convs", 2))
         for name, (k, nconv) in heads.items():
             assert nconv == 2

@@ -211,6 +211,12 @@ int ff3d_roi_sample(const float* query_box, int box_ld, const float* value, int 
 int ff3d_head_update(float* pred, int ldp, float* query_pos, const float* prev, int ldprev, int rows,
                      ff3d_stream_t stream);
 
+/* Class-aware regression select (focal_decoder.py:940-943, `classaware_reg=True`, FocalFormer3D_Waymo15_L): the
+ * prediction heads emit num_classes regression sets per query (channel = class * k + d for each of the n_groups heads of
+ * widths group_k[]), followed by `tail` pass-through columns (class logits); out keeps the set of label[row]. */
+int ff3d_class_select(const float* full, int ld_full, const int* label, const int* group_k, int n_groups, int tail,
+                      int num_classes, float* out, int ld_out, int rows, ff3d_stream_t stream);
+
 /* Final scoring + box decode (focal_decoder.py:1313-1321 + transfusion_bbox_coder.py:71-158, nms_type=None):
  * pred as above (class logits at column cls_col); boxes [rows, 9|7] = (x,y,z_bottom,w,l,h,yaw[,vx,vy]),
  * scores [rows], labels [rows] int32, keep [rows] uint8 (post_center_range test). */

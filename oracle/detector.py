@@ -8,7 +8,7 @@ state dict drives both this oracle and the CUDA product.
 import torch
 from torch import nn
 
-from .voxelize import voxelize_batch, HardSimpleVFE, HardVFE
+from .voxelize import voxelize_batch, dynamic_voxelize_mean, HardSimpleVFE, HardVFE
 from .sparse import SparseEncoder
 from .bev import SECOND, SECONDFPN, FocalEncoder
 from .head import FocalDecoder
@@ -38,7 +38,11 @@ class FocalFormer3D(nn.Module):
                 return
         self.voxel_cfg = pts_voxel_layer
         ve = _strip(pts_voxel_encoder)
-        if pts_voxel_encoder["type"] == "HardSimpleVFE":
+        self.dynamic = "Dynamic" in pts_voxel_encoder["type"]             # focalformer3d.py:80
+        if self.dynamic:
+            assert pts_voxel_encoder["type"] == "DynamicSimpleVFE"
+            self.pts_voxel_encoder = None                                 # no parameters; see dynamic_voxelize_mean
+        elif pts_voxel_encoder["type"] == "HardSimpleVFE":
             self.pts_voxel_encoder = HardSimpleVFE(**ve)
         else:
             self.pts_voxel_encoder = HardVFE(in_channels=ve["in_channels"], feat_channels=ve["feat_channels"])
@@ -56,10 +60,15 @@ class FocalFormer3D(nn.Module):
 
     @torch.no_grad()
     def extract_pts_feat(self, points, stages=None):
-        voxels, num_points, coors = self.voxelize(points)
         dev = next(self.parameters()).device           # .cuda() turns the oracle into the stock-PyTorch GPU stand-in
-        voxels, num_points, coors = voxels.to(dev), num_points.to(dev), coors.to(dev)
-        vf = self.pts_voxel_encoder(voxels, num_points, coors)
+        if self.dynamic:                               # focalformer3d.py:159-163
+            vf, coors = dynamic_voxelize_mean(points, self.voxel_cfg["voxel_size"], self.voxel_cfg["point_cloud_range"])
+            vf, coors = vf.to(dev), coors.to(dev)
+            voxels = num_points = None
+        else:
+            voxels, num_points, coors = self.voxelize(points)
+            voxels, num_points, coors = voxels.to(dev), num_points.to(dev), coors.to(dev)
+            vf = self.pts_voxel_encoder(voxels, num_points, coors)
         batch_size = int(coors[-1, 0]) + 1
         x = self.pts_middle_encoder(vf, coors, batch_size)
         if stages is not None:

@@ -148,7 +148,8 @@ class FocalDecoder(nn.Module):
                  roi_based_reg=False, classaware_reg=False, boxpos=None, decoder_cfg=None,
                  loss_cls=dict(type='GaussianFocalLoss', reduction='mean'), **unused):
         super().__init__()
-        assert initialize_by_heatmap and not heatmap_box and not classaware_reg and boxpos is None
+        assert initialize_by_heatmap and not heatmap_box and boxpos is None
+        self.classaware_reg = classaware_reg
         # focal_decoder.py:164-166: a background class is appended unless loss_cls.use_sigmoid; every shipped config
         # sets use_sigmoid=True (the softmax variant would break class_encoding's channel count in the reference)
         assert loss_cls.get('use_sigmoid', False), 'only the use_sigmoid=True classification head is restated'
@@ -201,6 +202,8 @@ class FocalDecoder(nn.Module):
         self.prediction_heads = nn.ModuleList()
         for _ in range(num_decoder_layers):
             heads = copy.deepcopy(common_heads)
+            if self.classaware_reg:                                              # :317-319
+                heads = {k: [v[0] * num_classes, v[1]] for k, v in heads.items()}
             heads.update(dict(heatmap=(num_classes, num_heatmap_convs)))
             self.prediction_heads.append(PredFFN(hc, heads))
         xs = test_cfg["grid_size"][0] // test_cfg["out_size_factor"]
@@ -386,6 +389,12 @@ class FocalDecoder(nn.Module):
             dbg["stage_query_feat"].append(query_feat)
             query_pos = reference_points * WH
             res = self.prediction_heads[i](query_feat)                           # :939
+            if self.classaware_reg:                                              # :940-943: keep the query's own class
+                P = res["center"].shape[-1]
+                lab = self.query_labels[:, None, None, :].clip(0, self.num_classes - 1)
+                for k in ("center", "height", "dim", "rot"):
+                    t = res[k].view(B, self.num_classes, -1, P)
+                    res[k] = t.gather(index=lab.expand(-1, -1, t.shape[2], -1), dim=1)[:, 0]
             res["center"] = res["center"] + query_pos.permute(0, 2, 1)           # :945
             query_pos = res["center"].detach().clone().permute(0, 2, 1)
             if self.roi_based_reg and query_box is not None:                     # :949-951

@@ -101,6 +101,31 @@ def voxelize_batch(points_list, voxel_size, pc_range, max_points, max_voxels):
             torch.from_numpy(np.concatenate(coo)))
 
 
+def dynamic_voxelize_mean(points_list, voxel_size, pc_range):
+    """[upstream] mmdet3d v0.17.1 dynamic voxelisation (Voxelization(max_num_points=-1): one (z, y, x) per point, -1 when
+    outside the grid) + DynamicSimpleVFE (DynamicScatter, mean of ALL points of a voxel) as used at
+    focalformer3d.py:159-163,213-238.  Returns (features [M, F] float32, coors [M, 4] (b, z, y, x)); voxels are listed in
+    key order -- the order is implementation-defined in the reference and irrelevant after SparseConvTensor.dense()."""
+    feats, coors = [], []
+    r = np.asarray(pc_range, dtype=np.float32)
+    v = np.asarray(voxel_size, dtype=np.float32)
+    g = grid_size_of(voxel_size, pc_range)
+    for b, pts in enumerate(points_list):
+        p = np.ascontiguousarray(pts.detach().cpu().numpy() if torch.is_tensor(pts) else pts, dtype=np.float32)
+        c = np.floor((p[:, :3] - r[None, :3]) / v[None, :]).astype(np.int64)
+        ok = np.all((c >= 0) & (c < g[None, :]), axis=1)
+        p, c = p[ok], c[ok]
+        key = (c[:, 2] * g[1] + c[:, 1]) * g[0] + c[:, 0]
+        uniq, inv = np.unique(key, return_inverse=True)
+        sums = np.zeros((uniq.size, p.shape[1]), np.float64)
+        np.add.at(sums, inv, p.astype(np.float64))
+        cnt = np.bincount(inv, minlength=uniq.size).astype(np.float64)
+        feats.append((sums / cnt[:, None]).astype(np.float32))
+        z, rem = uniq // (g[1] * g[0]), uniq % (g[1] * g[0])
+        coors.append(np.stack([np.full_like(uniq, b), z, rem // g[0], rem % g[0]], 1).astype(np.int32))
+    return torch.from_numpy(np.concatenate(feats)), torch.from_numpy(np.concatenate(coors))
+
+
 class HardSimpleVFE(torch.nn.Module):
     """[upstream] mmdet3d v0.17.1 HardSimpleVFE: mean of the (<= max_points) points of a voxel."""
 

@@ -39,6 +39,31 @@ def _deform_tiny():
     return cfg, make_state_dict(cfg, 2), pts
 
 
+def _waymo15_tiny():
+    """FocalFormer3D_Waymo15_L: 14x14 ROI grids (roi_mlp K = 75264) and class-aware regression heads."""
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_points
+    cfg = scaled_model_cfg(load_config(default_config_path("focalformer3d_waymo15_l"))["model"], bev=24, num_proposals=16)
+    pts = [torch.from_numpy(synth_points(n, cfg["pts_voxel_layer"]["point_cloud_range"], seed=40 + s, n_beams=64))
+           for s, n in enumerate((7000, 5000))]
+    return cfg, make_state_dict(cfg, 5), pts
+
+
+def _dynamic_tiny():
+    """DeformFormer3D_L_dynamic: dynamic voxelisation (no point / voxel caps) + DynamicSimpleVFE (mean of all points)."""
+    import copy
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_points
+    base = copy.deepcopy(load_config(default_config_path("deformformer3d_l"))["model"])
+    base["pts_voxel_layer"].update(max_num_points=-1, max_voxels=(-1, -1))      # DeformFormer3D_L_dynamic.py:189-196
+    base["pts_voxel_encoder"] = dict(type="DynamicSimpleVFE", voxel_size=base["pts_voxel_layer"]["voxel_size"],
+                                     point_cloud_range=base["pts_voxel_layer"]["point_cloud_range"])
+    cfg = scaled_model_cfg(base, bev=24, num_proposals=20)
+    pts = [torch.from_numpy(synth_points(n, cfg["pts_voxel_layer"]["point_cloud_range"], seed=60 + s))
+           for s, n in enumerate((9000, 6500))]
+    return cfg, make_state_dict(cfg, 6), pts
+
+
 def _fusion_tiny():
     """FocalFormer3D_LC: LiDAR tower + image tower + Lift-Splat-Shoot + two 'bevfusion' layers (9x9 local attention)."""
     from focalformer3d_b200.config import load_config, default_config_path, scaled_fusion_cfg
@@ -52,7 +77,8 @@ def _fusion_tiny():
     return cfg, make_state_dict(cfg, 4), pts, img, metas
 
 
-@pytest.fixture(scope="module", params=["nuscenes_l", "waymo_l", "deformformer_l", "fusion_lc"])
+@pytest.fixture(scope="module", params=["nuscenes_l", "waymo_l", "deformformer_l", "fusion_lc", "waymo15_l",
+                                        "deformformer_l_dynamic"])
 def pair(request, tiny_cfg, tiny_sd, tiny_points):
     from focalformer3d_b200.model import build_model
     from oracle.detector import build_oracle
@@ -61,6 +87,10 @@ def pair(request, tiny_cfg, tiny_sd, tiny_points):
     if request.param == "deformformer_l":    # no HIP: single averaged heatmap, one decoder stage, no ROI, no fusion layers
         tiny_cfg, tiny_sd, tiny_points = _deform_tiny()
     kw, okw = {}, {}
+    if request.param == "waymo15_l":
+        tiny_cfg, tiny_sd, tiny_points = _waymo15_tiny()
+    if request.param == "deformformer_l_dynamic":
+        tiny_cfg, tiny_sd, tiny_points = _dynamic_tiny()
     if request.param == "fusion_lc":
         tiny_cfg, tiny_sd, tiny_points, img, metas = _fusion_tiny()
         kw, okw = dict(img=img.cuda(), img_metas=metas), dict(img=img, img_metas=metas)
@@ -81,6 +111,17 @@ def test_voxel_stage(pair):
     st, ost = pair["st"], pair["ost"]
     n = int(st["vox"]["n_dev"][0].item())
     assert n == ost["coors"].shape[0]
+    if pair["name"] == "deformformer_l_dynamic":
+        # dynamic voxelisation: same voxel SET (order is implementation-defined), every voxel = mean of ALL its points
+        def keyed(c):
+            c = c.long()
+            return ((c[:, 0] * 64 + c[:, 1]) * 4096 + c[:, 2]) * 4096 + c[:, 3]
+        ka, kb = keyed(st["vox"]["coors"][:n].cpu()), keyed(ost["coors"])
+        ia, ib = ka.argsort(), kb.argsort()
+        assert torch.equal(ka[ia], kb[ib])
+        assert (st["vox"]["mean"][:n, :5].cpu()[ia] - ost["voxel_features"][ib]).abs().max().item() < 1e-5
+        assert int(st["vox"]["num_points"][:n].max().item()) > 10           # the 10-point cap of the hard voxeliser is gone
+        return
     assert torch.equal(st["vox"]["coors"][:n].cpu(), ost["coors"].int())
     assert torch.equal(st["vox"]["num_points"][:n].cpu(), ost["num_points"].int())
     assert torch.equal(st["vox"]["voxels"][:n].cpu(), ost["voxels"])
@@ -183,7 +224,7 @@ def test_simple_test_signature(pair):
     assert len(out) == len(tiny_points)
     for o in out:
         d = o["pts_bbox"]
-        assert d["boxes_3d"].shape[1] == (7 if pair["name"] == "waymo_l" else 9) and d["boxes_3d"].shape[0] == d["scores_3d"].shape[0] == d["labels_3d"].shape[0]
+        assert d["boxes_3d"].shape[1] == (7 if pair["name"].startswith("waymo") else 9) and d["boxes_3d"].shape[0] == d["scores_3d"].shape[0] == d["labels_3d"].shape[0]
         assert d["boxes_3d"].device.type == "cpu" and d["boxes_3d"].shape[0] <= 200
 
 

@@ -512,3 +512,21 @@ def test_local_attention(shape):
     ops.local_attention(buf[..., :C], buf[..., C:2 * C], buf[..., 2 * C:3 * C], out[..., C:], 9)
     err = (out[..., C:].permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
     assert err < 2e-5, err
+
+
+def test_class_select():
+    """class-aware regression heads (focal_decoder.py:940-943): keep the regression set of each query's own class."""
+    from focalformer3d_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    rows, nc, gk = 37, 3, [2, 1, 3, 2]
+    full = torch.randn(rows, 28, generator=g)                      # 3 * 8 = 24 regression columns + 3 class logits (+ pad)
+    lab = torch.randint(0, nc, (rows,), generator=g).int()
+    out = ops.class_select(full.cuda(), lab.cuda(), gk, nc, nc, 12).cpu()
+    c_full, c_out = 0, 0
+    for k in gk:
+        blk = full[:, c_full:c_full + nc * k].view(rows, nc, k)
+        ref = blk[torch.arange(rows), lab.long()]
+        assert torch.equal(out[:, c_out:c_out + k], ref)
+        c_full += nc * k
+        c_out += k
+    assert torch.equal(out[:, c_out:c_out + nc], full[:, c_full:c_full + nc])
