@@ -50,6 +50,10 @@ int ff3d_version(void);
  *   mean_feats [cap, mean_ld] (may be NULL; columns >= n_feat are written as 0),
  *   n_voxels_dev [1 + batch] int32: total, then per-sample counts.
  * Voxel order = sample-major, first-appearance order inside a sample (the reference's order).
+ * Dynamic mode (max_points <= 0; [upstream] Voxelization(max_num_points=-1) + DynamicSimpleVFE as used at
+ *   focalformer3d.py:159-163,213-238 by DeformFormer3D_L_dynamic): no per-voxel point cap -- pass the largest
+ *   per-sample point count as max_voxels --, voxels must be NULL, num_points = all points of the voxel, mean_feats =
+ *   their mean (fp64 atomic sums); same voxel order as above.
  */
 size_t ff3d_voxelize_workspace_bytes(int n_total, int batch, int max_voxels, int max_points);
 int ff3d_voxelize_hard(const float* points, int n_total, int n_feat, const int* batch_offsets_host, int batch,
