@@ -295,7 +295,12 @@ extern "C" int ff3d_mha_core(const float* q, int ldq, const float* k, int ldk, c
   FF3D_REQUIRE(Nq >= 1 && Nq <= MHA_MAXQ, "mha_core: Nq=%d unsupported (<= %d)", Nq, MHA_MAXQ);
   size_t smem = (size_t)2 * Nq * (d + 1) * sizeof(float);
   FF3D_REQUIRE(smem <= 220 * 1024, "mha_core: K/V tile does not fit shared memory");
-  dim3 grid(B * heads, cdiv(Nq, 64));
+  // query chunks per (batch, head): ~64 queries each, but never more CTAs than fit in ONE wave (two 81 KB CTAs per SM)
+  // -- 4 x 8 x 10 = 320 CTAs on 296 slots ran a nearly empty second wave
+  int ny = cdiv(Nq, 64);
+  const int one_wave = (2 * num_sms()) / (B * heads);
+  if (ny > one_wave && one_wave >= 1) ny = one_wave;
+  dim3 grid(B * heads, ny);
   cudaStream_t st = as_stream(stream);
   if (d == 16) {
     cudaFuncSetAttribute(mha_core_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
