@@ -458,11 +458,13 @@ class LiftSplatShoot:
         nx, ny, nz = self.nxyz
         bev = torch.empty((B, ny, nx, nz * self.CAM_C), dtype=torch.float32, device=dev)
         ops.lss_splat(dn, self.frustum, rots, trans, bev, n_img // B, self.D, self.lo, self.dx)
+        ops.mark("lss_lift_splat")
         x = bev
         for i, (w, b, co) in enumerate(self.bevenc):
             y = out if i == 3 else torch.empty((B, ny, nx, w.shape[-1]), dtype=torch.float32, device=dev)
             ops.conv2d(x, w, b, y, 3, act=ACT_RELU)
             x = y[..., :co]
+        ops.mark("lss_bevencode")
         return out, dn, bev
 
 
@@ -599,6 +601,7 @@ class FocalEncoder(ParamTree):
             ops.conv2d(qkv[..., :hc], *blk["q2"], q2, 1, act=ACT_RELU)
             ops.conv2d(qkv[..., hc:2 * hc], *blk["k2"], k2, 1, act=ACT_RELU)
             ops.local_attention(q2, k2, qkv[..., 2 * hc:], catA[..., hc:], 9)                      # :160-162 -> P2P
+            ops.mark("locatt")
             ops.conv2d(catA, *blk["outp"], catB[..., :hc], 1, act=ACT_NONE)                        # focal_encoder.py:73
             last = i == self.num_layers - 1
             nxtB = new(hc) if last else new(2 * hc)
