@@ -39,6 +39,34 @@ def test_gemm_desc_rejects_bad_arguments_without_a_gpu():
     assert lib.ff3d_voxelize_workspace_bytes(1000, 2, 100, 10) > 2 * 100 * 10 * 4
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks run before any CUDA call: bad shapes return FF3D_EINVAL (-1) with a message, like the reference's
+    asserts raise (bev_pool_op.py:84, localAttention.cpp CHECK_* macros)."""
+    _ensure_built()
+    import ctypes as C
+    from focalformer3d_b200.lib import lib
+    nul = C.c_void_p(0)
+    one = C.c_void_p(16)                                           # never dereferenced: validation fails first
+    assert lib.ff3d_local_attention(one, 128, one, 128, one, 128, one, 128, 1, 8, 8, 96, 9, nul) == -1     # C not 128/256
+    assert b"local_attention" in lib.ff3d_last_error()
+    assert lib.ff3d_local_attention(one, 128, one, 128, one, 128, one, 128, 1, 8, 8, 128, 8, nul) == -1    # even window
+    gk = (C.c_int * 4)(2, 1, 3, 2)
+    assert lib.ff3d_class_select(one, 28, one, gk, 9, 3, 3, one, 12, 4, nul) == -1                         # > 8 groups
+    assert lib.ff3d_class_select(one, 28, one, gk, 4, 3, 3, one, 8, 4, nul) == -1                          # out row too narrow
+    assert b"class_select" in lib.ff3d_last_error()
+    f3 = (C.c_float * 3)(0.6, 0.6, 0.6)
+    assert lib.ff3d_lss_splat(one, 100, one, one, one, one, 1, 6, 41, 8, 8, f3, f3, 16, 16, 13, nul) == -1 # ld < 64 + D
+    assert b"lss_splat" in lib.ff3d_last_error()
+    assert lib.ff3d_nchw_to_nhwc(one, one, 1, 3, 8, 8, 6, nul) == -1                                       # ld % 4
+    assert lib.ff3d_maxpool3x3s2(one, one, 1, 8, 8, 6, nul) == -1
+    # dynamic voxelisation returns means only
+    off = (C.c_int * 2)(0, 10)
+    f6 = (C.c_float * 6)(-1, -1, -1, 1, 1, 1)
+    assert lib.ff3d_voxelize_hard(one, 10, 5, off, 1, f3, f6, -1, 10, one, one, one, one, 8, one, one, 1 << 20, nul) == -1
+    assert b"dynamic" in lib.ff3d_last_error()
+    assert lib.ff3d_voxelize_workspace_bytes(1000, 2, 500, -1) >= 2 * 500 * 8 * 8   # fp64 sums [cap][8]
+
+
 def test_repo_config_and_param_contract():
     from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
     from focalformer3d_b200.synth import param_spec, make_state_dict
