@@ -10,19 +10,21 @@
 // accumulation step costs up to 1 ulp of the running sum; keeping the 2/3 of the steps that carry 2^-11-sized terms
 // out of the main accumulator cuts that bias 3x for free (measured: K=1024 error 3.1e-5 -> see tests).
 //
-// CTA = one 128 x BN output tile, 320 threads:
-//   warps 0-3, 4-7  two A-producer groups (even / odd pipeline stages): each thread owns one of the 128 tile rows;
-//              per stage it gathers the row's 32 fp32 (128 B: one conv tap x 32 channels, or 32/cin taps when
-//              cin < 32) with 8 LDG.128, splits hi/lo in registers and stores both into the 128B-swizzled K-major
-//              smem tiles (generic proxy) -> fence.proxy.async -> mbarrier arrive.  Two groups (and 2 CTAs/SM for
-//              BN <= 64) keep several 16 KB gathers in flight per SM: the gather is latency-bound otherwise.
-//              After the main loop both groups run the epilogue, half the columns each
-//              (tcgen05.ld 32x32b: thread <-> TMEM lane <-> tile row).
-//   warp 8     B producer: one cp.async.bulk (UBLKCP) per stage of the host-pre-swizzled [hi | lo] weight image.
-//   warp 9     TMEM alloc/dealloc + single-thread tcgen05.mma issue (per K=8 step: one 128 x 2BN and one 128 x BN MMA),
+// Persistent CTAs (one per SM for BN = 128, two for BN <= 64) loop over (128*MT) x BN output tiles; 128*G + 64 threads:
+//   warps 0 .. 4G-1  G A-producer groups of 128 threads (G = number of smem slots; group g owns slot g and the pipeline
+//              stages g, g+G, ...).  One gather UNIT = the 32 K-values (128 B: one tap x 32 channels, or 32/cin taps when
+//              cin < 32) of a 128-row sub-tile: a quarter-warp reads one row (full 128-byte line per request), 8 LDG.128
+//              per thread.  Units are double-buffered in registers (ping-pong, BN = 128): the next unit's loads are in
+//              flight while this one is split into hi / lo TF32 and stored (STS.128) into the 128B-swizzled K-major smem
+//              tiles -> fence.proxy.async -> mbarrier arrive.  The same warps run the epilogue of the PREVIOUS tile after
+//              issuing this tile's gathers (double-buffered TMEM accumulators): tcgen05.ld 32x32b (thread <-> TMEM lane
+//              <-> tile row), bias / residual / activation, 64-byte row segments to global memory.
+//   warp 4G    B producer: one cp.async.bulk (UBLKCP) per stage of the host-pre-swizzled [hi | lo] weight image.
+//   warp 4G+1  TMEM alloc/dealloc + single-thread tcgen05.mma issue (per K=8 step: one 128 x 2BN and one 128 x BN MMA),
 //              tcgen05.commit releases smem stages / signals the epilogue.
-// Sparse mode stages the tile's whole neighbour map (taps x 128 int32) in shared memory up front, so the gather's
-// dependent index load is off the per-stage critical path.
+// All shared-memory accesses use 32-bit shared-space addresses (LDS / STS / mbarrier on shared::cta), never generic
+// pointers.  Sparse mode stages the tile's whole neighbour map (taps x rows int32), conv mode one int4 of row geometry per
+// row, in shared memory up front, so the gather's dependent index load is off the per-stage critical path.
 #include "common.cuh"
 
 namespace ff3d {

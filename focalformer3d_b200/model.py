@@ -4,7 +4,7 @@ Registered ``type`` strings (same as the reference registry): ``FocalFormer3D``
 (projects/mmdet3d_plugin/models/detectors/focalformer3d.py:26), ``FocalEncoder`` (models/necks/focal_encoder.py:89),
 ``FocalDecoder`` (models/dense_heads/focal_decoder.py:33), ``TransFusionBBoxCoder``
 (core/bbox/coders/transfusion_bbox_coder.py:7) plus stand-ins for the upstream types the shipped configs name
-(``HardSimpleVFE``, ``SparseEncoder``, ``SECOND``, ``SECONDFPN``).  Every module is an ``nn.Module`` whose parameter
+(``HardSimpleVFE``, ``HardVFE``, ``DynamicSimpleVFE``, ``SparseEncoder``, ``SECOND``, ``SECONDFPN``, ``ResNet``, ``FPN``).  Every module is an ``nn.Module`` whose parameter
 names reproduce the reference checkpoint keys, so ``load_state_dict`` / ``load_checkpoint`` work unchanged; the
 arithmetic runs in libff3d.so (no PyTorch compute fallback: without the library the import of ``.ops`` fails).
 """
@@ -499,7 +499,9 @@ class _IR:
 
 @NECKS.register_module()
 class FocalEncoder(ParamTree):
-    """models/necks/focal_encoder.py:90-222, LiDAR-only 'bevfusionmb2' path (input_img=False, iterbev_wo_img=True)."""
+    """models/necks/focal_encoder.py:90-222.  Three built paths: LiDAR-only 'bevfusionmb2' (input_img=False,
+    iterbev_wo_img=True; `forward`), camera-only Lift-Splat-Shoot (`forward_camera`), LiDAR + camera 'bevfusion' with
+    cam_lss / iter_bev_cam (`forward_fusion`)."""
 
     def __init__(self, num_layers=2, in_channels_img=64, in_channels_pts=384, hidden_channel=128, bn_momentum=0.1,
                  bias="auto", iterbev="bevfusion", max_points_height=5, multistage_heatmap=False, input_img=True,
@@ -971,7 +973,8 @@ class FocalDecoder(ParamTree):
 
 @DETECTORS.register_module()
 class FocalFormer3D(nn.Module):
-    """models/detectors/focalformer3d.py:27 -- inference forward (simple_test :321-332) on libff3d.so."""
+    """models/detectors/focalformer3d.py:27 -- inference forward (simple_test :321-332) on libff3d.so: LiDAR-only,
+    camera-only (input_pts=False) and LiDAR + camera configs."""
 
     def __init__(self, pts_voxel_layer=None, pts_voxel_encoder=None, pts_middle_encoder=None, pts_backbone=None,
                  pts_neck=None, imgpts_neck=None, pts_bbox_head=None, train_cfg=None, test_cfg=None, input_img=True,
