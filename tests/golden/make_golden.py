@@ -208,6 +208,45 @@ def main():
     print(f"wrote {os.path.join(OUT, 'focalformer3d_l_intree.pt')} ({n} values)")
     camera_golden(fe)
     fusion_golden(fe)
+    head_variants_golden(fd, box_cls)
+
+
+def head_variants_golden(fd, box_cls):
+    """Real FocalDecoder.forward / get_bboxes for the head branches the flagship fixture does not reach:
+    single-stage DeformFormer3D_L (focal_decoder.py:539-586), HIP without heatmap re-use (FocalFormer3D_LC, :588-664) and
+    class-aware regression heads with 14x14 ROI grids (FocalFormer3D_Waymo15_L, :317-319,940-943)."""
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict
+    out = {}
+    for name, cfg_name, n_stage_feats, seed in (("deformformer_l", "deformformer3d_l", 0, 21),
+                                                ("fusion_lc", "focalformer3d_lc", 3, 22),
+                                                ("waymo15_l", "focalformer3d_waymo15_l", 3, 23)):
+        full = load_config(default_config_path(cfg_name))["model"]
+        cfg = scaled_model_cfg(full, bev=16, num_proposals=10)
+        sd = make_state_dict(cfg, seed=seed)
+        g = torch.Generator().manual_seed(100 + seed)
+        hd = dict(cfg["pts_bbox_head"]); hd.pop("type")
+        head = fd.FocalDecoder(**hd, test_cfg=dict(cfg["test_cfg"]["pts"])).eval()
+        head.load_state_dict({k[len("pts_bbox_head."):]: v for k, v in sd.items() if k.startswith("pts_bbox_head.")}, strict=True)
+        rec = dict(weights_seed=seed, cfg_name=cfg_name)
+        for B, tag in ((2, "b2"), (1, "b1")):
+            conv = torch.randn(B, 128, 16, 16, generator=g) * 0.5
+            stage = [torch.randn(B, 128, 16, 16, generator=g) * 0.5 for _ in range(n_stage_feats)]
+            second = [t.clone() for t in stage] if n_stage_feats else conv.clone()      # DeformFormer: the same tensor twice
+            with torch.no_grad(), no_cuda_device():
+                res = head([conv.clone(), second], None, [dict()] * B)
+                r = res[0][0]
+                rec[f"{tag}_in"] = dict(conv=conv, stage=stage)
+                rec[f"{tag}_out"] = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v])
+                                     for k, v in r.items() if k != "multistage_masks"}
+                rec[f"{tag}_query_labels"] = head.query_labels.clone()
+                if B == 1:
+                    boxes, scores, labels = head.get_bboxes(res, [dict(box_type_3d=box_cls)])[0]
+                    rec["bboxes_b1"] = dict(boxes=boxes.tensor.clone(), scores=scores.clone(), labels=labels.clone())
+        out[name] = rec
+    path = os.path.join(OUT, "head_variants.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({sum(t.numel() for t in _tensors(out))} values)")
 
 
 def fusion_golden(fe):

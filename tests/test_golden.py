@@ -95,3 +95,48 @@ def test_get_bboxes_matches_reference(gold, setup):
     assert (det["boxes_3d"] - ref["boxes"]).abs().max().item() < 1e-4
     assert (det["scores_3d"] - ref["scores"]).abs().max().item() < 1e-5
     assert torch.equal(det["labels_3d"].int(), ref["labels"].int())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# head branches the flagship fixture does not reach: single-stage (DeformFormer3D_L), HIP without heatmap re-use
+# (FocalFormer3D_LC), class-aware regression + 14x14 ROI (FocalFormer3D_Waymo15_L) -- REAL reference head outputs
+VARIANTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "head_variants.pt")
+
+
+@pytest.fixture(scope="module")
+def variants():
+    if not os.path.exists(VARIANTS):
+        pytest.skip("golden fixture missing")
+    return torch.load(VARIANTS, map_location="cpu")
+
+
+@pytest.mark.parametrize("name", ["deformformer_l", "fusion_lc", "waymo15_l"])
+def test_head_variants_match_reference(variants, name):
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict
+    rec = variants[name]
+    cfg = scaled_model_cfg(load_config(default_config_path(rec["cfg_name"]))["model"], bev=16, num_proposals=10)
+    head = _head(cfg, make_state_dict(cfg, seed=rec["weights_seed"]))
+    keys = [k for k in ("center", "height", "dim", "rot", "vel", "heatmap", "query_heatmap_score") if k in rec["b2_out"]]
+    for tag in ("b2", "b1"):
+        conv, stage = rec[f"{tag}_in"]["conv"], rec[f"{tag}_in"]["stage"]
+        second = [t.clone() for t in stage] if stage else conv.clone()
+        with torch.no_grad():
+            outs = head([conv.clone(), second], None, None, topk_fn=_ref_topk)
+        out, ref = outs[0][0], rec[f"{tag}_out"]
+        assert torch.equal(head.query_labels, rec[f"{tag}_query_labels"])             # class ids bit-exact
+        for k in keys:
+            assert out[k].shape == ref[k].shape, k
+            assert (out[k] - ref[k]).abs().max().item() < 1e-4, (name, tag, k)
+        dh, rh = out["dense_heatmap"], ref["dense_heatmap"]
+        dh, rh = (dh, rh) if isinstance(rh, (list, tuple)) else ([dh], [rh])
+        assert len(dh) == len(rh)
+        for a, b in zip(dh, rh):
+            assert (a - b).abs().max().item() < 1e-5
+        if tag == "b1":
+            det = head.get_bboxes(outs)[0]
+            gb = rec["bboxes_b1"]
+            assert det["boxes_3d"].shape == gb["boxes"].shape
+            assert (det["boxes_3d"] - gb["boxes"]).abs().max().item() < 1e-4
+            assert (det["scores_3d"] - gb["scores"]).abs().max().item() < 1e-5
+            assert torch.equal(det["labels_3d"].int(), gb["labels"].int())
