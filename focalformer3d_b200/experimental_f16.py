@@ -76,3 +76,46 @@ def unpack_images_f16(imgs, taps, cin, cout):
         else:
             parts.append(kmat.reshape(-1, cin, cout)[:taps])
     return parts[0], parts[1]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Opt-in test harness (round 2): route every tensor-core GEMM of focalformer3d_b200.ops through the experimental fp16
+# kernel, so that the WHOLE existing GPU test suite (kernel parity + end to end) validates it:
+#     make -C focalformer3d_b200/csrc experimental && FF3D_EXPERIMENTAL_F16=1 python -m pytest tests -m gpu
+# Never active by default; nothing in the product path imports this.
+def enable(ops_module=None):
+    import ctypes as C
+    import os
+    from . import lib as L
+    ops = ops_module
+    if ops is None:
+        from . import ops
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libff3d_x.so")
+    if not os.path.exists(path):
+        raise RuntimeError("libff3d_x.so missing: make -C focalformer3d_b200/csrc experimental")
+    xlib = C.CDLL(path)
+    xlib.ff3d_x_tcgemm_f16.restype = C.c_int
+    xlib.ff3d_x_tcgemm_f16.argtypes = [C.POINTER(L.GemmDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    xlib.ff3d_last_error.restype = C.c_char_p
+    state = {"overflow": None, "calls": 0, "fallbacks": 0}
+    orig = ops._gemm
+
+    def gemm_f16(d, w, what):
+        taps, cin, cout = w.w.shape
+        if f16_ntile(cin, cout) <= 0 or w.img is None:
+            state["fallbacks"] += 1
+            return orig(d, w, what)
+        if getattr(w, "img16", None) is None:
+            bn = w.bn if (w.bn and cout % w.bn == 0) else None
+            img, w.bn16 = tc_weight_images_f16(w.w.detach().float().cpu(), bn)
+            w.img16 = img.to(w.w.device)
+        if state["overflow"] is None:
+            state["overflow"] = torch.zeros(1, dtype=torch.int32, device=w.w.device)
+        rc = xlib.ff3d_x_tcgemm_f16(C.byref(d), C.c_void_p(w.img16.data_ptr()), w.bn16,
+                                    C.c_void_p(state["overflow"].data_ptr()), ops._stream())
+        if rc != 0:
+            raise L.Ff3dError(f"ff3d_x_tcgemm_f16({what}): {xlib.ff3d_last_error().decode()}")
+        state["calls"] += 1
+
+    ops._gemm = gemm_f16
+    return state

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    if os.environ.get("FF3D_EXPERIMENTAL_F16") == "1":
+        # round-2 harness (never set by default): run the whole GPU suite on the experimental fp16 hi/lo GEMM kernel
+        from focalformer3d_b200 import experimental_f16
+        experimental_f16.enable()
 
 
 @pytest.fixture(scope="session")
