@@ -149,6 +149,18 @@ def _head_spec(model_cfg, s):
     s["imgpts_neck.shared_conv_pts.weight"] = ((hc, ne["in_channels_pts"], 3, 3), ("w", ne["in_channels_pts"] * 9))
     s["imgpts_neck.shared_conv_pts.bias"] = ((hc,), "b")
     fused = bool(model_cfg.get("input_img", False))               # LiDAR + camera (FocalFormer3D_LC): 'bevfusion' blocks
+    if fused and not ne.get("cam_lss"):
+        # 'proj' variant (FocalFormer3D_LC_Proj): image-plane 3x3 conv, then the layer-0 I2P projection block
+        # (focal_encoder.py:134-141,28-31; encoder_utils.py:184-193: one single-head nn.MultiheadAttention)
+        ci = ne["in_channels_img"]
+        s["imgpts_neck.shared_conv_img.weight"] = ((hc, ci, 3, 3), ("w", ci * 9))
+        s["imgpts_neck.shared_conv_img.bias"] = ((hc,), "b")
+        if ne.get("num_layers") and not ne.get("iterbev_wo_img", False):
+            q0 = "imgpts_neck.fusion_blocks.0.I2P_block.learnedAlign"
+            s[f"{q0}.in_proj_weight"] = ((3 * hc, hc), ("w_att", hc))
+            s[f"{q0}.in_proj_bias"] = ((3 * hc,), "b")
+            s[f"{q0}.out_proj.weight"] = ((hc, hc), ("w", hc))
+            s[f"{q0}.out_proj.bias"] = ((hc,), "b")
     for i in range(ne["num_layers"] or 0):
         q = f"imgpts_neck.fusion_blocks.{i}"
         if ne.get("iterbev", "bevfusion") == "bevfusionmb2":

@@ -4,6 +4,7 @@
 ``focalformer3d.py:169-171``); in-tree ``models/necks/focal_encoder.py:15-222`` and
 ``models/utils/encoder_utils.py:10-33``.
 """
+import numpy as np
 import torch
 from torch import nn
 import torch.nn.functional as F
@@ -120,14 +121,71 @@ class LocalContextAttentionBlock(nn.Module):
         return local_weighting(value, weight, k, k)                                        # :162
 
 
+class I2P(nn.Module):
+    """encoder_utils.py:184-262: image -> BEV projection of the 'proj' fusion variant (FocalFormer3D_LC_Proj).  Every BEV
+    cell owns `max_points_height` sample points along z (cell centres of a W x H x P grid over the HARD-CODED range
+    +-54 m, [-5, 3] m, :208); each point is projected into every camera with `lidar2img`, the image feature is sampled
+    bilinearly (grid_sample, zeros outside), averaged over the cameras that see the point, and one single-head attention
+    (query = the cell's LiDAR feature, keys = values = its P sampled features, unseen points masked) yields the cell's
+    decorated feature; cells no camera sees stay zero."""
+
+    def __init__(self, pts_channels, img_channels, dropout, max_points_height=5):
+        super().__init__()
+        self.pts_channels, self.img_channels, self.max_points_height = pts_channels, img_channels, max_points_height
+        self.learnedAlign = nn.MultiheadAttention(pts_channels, 1, dropout=dropout, kdim=img_channels, vdim=img_channels,
+                                                  batch_first=True)
+
+    def sample_points(self, ref):
+        """[P*H*W, 3] sample points, height-major (index = (p*H + h)*W + w), :209-212 + create_3D_grid :174-182."""
+        P = self.max_points_height
+        W, H = ref.shape[-1], ref.shape[-2]
+        pz, py, px = torch.meshgrid(torch.linspace(0, P - 1, P), torch.linspace(0, H - 1, H), torch.linspace(0, W - 1, W),
+                                    indexing="ij")
+        cell = torch.stack([px + 0.5, py + 0.5, pz + 0.5], 0).view(3, -1).t().to(ref)
+        rng = ref.new_tensor([-54.0, -54.0, -5.0, 54.0, 54.0, 3.0])
+        return cell / ref.new_tensor([W, H, P]) * (rng[3:] - rng[:3]) + rng[:3]
+
+    def forward(self, lidar_feat, img_feat, img_metas):
+        """lidar_feat [B, C, H, W]; img_feat [B, N, C, fH, fW]; returns [B, C, H, W]."""
+        B, C, H, W = lidar_feat.shape
+        P = self.max_points_height
+        out = torch.zeros_like(lidar_feat)
+        pts = self.sample_points(lidar_feat)
+        homo = torch.cat([pts, torch.ones_like(pts[:, :1])], 1)                             # [V, 4]
+        for b in range(B):
+            l2i = lidar_feat.new_tensor(np.asarray(img_metas[b]["lidar2img"]))              # [N, 4, 4]
+            cam = torch.matmul(l2i.unsqueeze(1), homo[None, :, :, None]).squeeze(-1)        # [N, V, 4]   :224
+            eps = 1e-5
+            seen = cam[..., 2:3] > eps
+            uv = cam[..., 0:2] / torch.maximum(cam[..., 2:3], torch.ones_like(cam[..., 2:3]) * eps)
+            ih, iw = img_metas[b]["input_shape"]
+            uv = torch.stack([uv[..., 0] / iw, uv[..., 1] / ih], -1)
+            uv = (uv - 0.5) * 2                                                              # :236
+            seen = seen & (uv[..., 0:1] > -1.0) & (uv[..., 0:1] < 1.0) & (uv[..., 1:2] > -1.0) & (uv[..., 1:2] < 1.0)
+            samp = F.grid_sample(img_feat[b], uv.unsqueeze(-2), align_corners=False).squeeze(-1)   # [N, C, V]   :243 (torch default)
+            N = samp.shape[0]
+            seen = seen.view(N, 1, P, H, W)
+            samp = samp.view(N, self.img_channels, P, H, W)
+            mean = (samp * seen).sum(0) / (seen.sum(0) + 1e-10)                              # over cameras :249
+            kv = mean.flatten(2, 3).transpose(0, 2)                                         # [H*W, P, C]
+            vis = (seen[:, 0].sum(0) > 0).view(P, H * W).t()                                 # [H*W, P]
+            q = lidar_feat[b].flatten(1, 2).t().unsqueeze(1)                                 # [H*W, 1, C]
+            valid = vis.sum(1) > 0
+            att = lidar_feat.new_zeros(H * W, 1, self.pts_channels)
+            att[valid] = self.learnedAlign(q[valid], kv[valid], kv[valid], attn_mask=(~vis[valid]).unsqueeze(1))[0]
+            out[b] = att.squeeze(1).t().view(self.pts_channels, H, W)
+        return out
+
+
 class FocalEncoderLayer(nn.Module):
     """focal_encoder.py:15-87: 'bevfusionmb2' (LiDAR-only, iterbev_wo_img) and 'bevfusion' (LiDAR + camera BEV with
     iter_bev_cam and no I2P projection: cam_lss supplies the image BEV feature) branches."""
 
     def __init__(self, hidden_channel, iterbev="bevfusionmb2", iterbev_wo_img=True, iter_bev_cam=None, need_projbev=True,
-                 layer_id=None, **kw):
+                 layer_id=None, max_points_height=5, **kw):
         super().__init__()
         self.iterbev, self.iterbev_wo_img = iterbev, iterbev_wo_img
+        self.project = bool(need_projbev and not iterbev_wo_img and iter_bev_cam and layer_id == 0)   # :28-31
         hc = hidden_channel
         if iterbev == "bevfusionmb2":
             assert iterbev_wo_img, "oracle covers the LiDAR-only mb2 branch"
@@ -136,8 +194,10 @@ class FocalEncoderLayer(nn.Module):
             self.P_out_proj = IR(2 * hc, hc, stride=1, expand_ratio=1, norm_layer=nn.BatchNorm2d)
             self.P_integration = IR(2 * hc, hc, stride=1, expand_ratio=1, norm_layer=nn.BatchNorm2d)
         else:
-            assert iterbev == "bevfusion" and (iterbev_wo_img or (iter_bev_cam and not need_projbev)), \
-                "oracle covers 'bevfusion' with the camera BEV feature from cam_lss (no I2P projection block)"
+            assert iterbev == "bevfusion" and (iterbev_wo_img or iter_bev_cam), \
+                "oracle covers 'bevfusion' with iter_bev_cam (camera BEV from cam_lss, or the layer-0 I2P projection)"
+            if self.project:
+                self.I2P_block = I2P(hc, hc, 0.1, max_points_height=max_points_height)        # :31
             self.P_IML = LocalContextAttentionBlock(hc, hc, 9)                              # :40
             self.P_out_proj = ConvBNReLU(2 * hc, hc, kernel_size=1, norm_layer=nn.BatchNorm2d, activation_layer=None)
             self.P_integration = ConvBNReLU(2 * hc, hc, kernel_size=1, norm_layer=nn.BatchNorm2d, activation_layer=None)
@@ -147,7 +207,11 @@ class FocalEncoderLayer(nn.Module):
             self.iterimg_conv = nn.Sequential(resnet.BasicBlock(hc, hc, norm_layer=nn.BatchNorm2d))   # :50-52
 
     def forward(self, img_feat, lidar_feat, img_metas=None, extra_args=None):
-        I2P_feat = lidar_feat if self.iterbev_wo_img else img_feat     # :58-70 (iter_bev_cam, need_projbev=False)
+        I2P_feat = lidar_feat if self.iterbev_wo_img else img_feat     # :58-70 (iter_bev_cam)
+        if self.project:                                               # :62-64: layer 0 lifts the image-plane feature
+            B = lidar_feat.shape[0]
+            I2P_feat = self.I2P_block(lidar_feat, img_feat.view(B, -1, *img_feat.shape[1:]), img_metas)
+            img_feat = I2P_feat
         if self.iterbev == "bevfusion":
             P2P_feat = self.P_IML(lidar_feat, lidar_feat)              # :72
         else:
@@ -166,26 +230,32 @@ class FocalEncoder(nn.Module):
                  input_pts=True, iterbev_wo_img=False, extra_feat=False, iter_bev_cam=False, cam_lss=False, pc_range=None,
                  img_scale=None, **kw):
         super().__init__()
-        assert input_pts and (not input_img or (cam_lss and cam_lss != "proj"))
+        assert input_pts and cam_lss != "proj"
+        self.use_lss = bool(input_img and cam_lss)
         self.iterbev_wo_img = iterbev_wo_img
         self.multistage_heatmap = multistage_heatmap
         self.input_img = input_img
         self.shared_conv_pts = nn.Conv2d(in_channels_pts, hidden_channel, 3, padding=1, bias=bool(bias))  # :120
-        if input_img:
+        if self.use_lss:
             from .camera import LiftSplatShoot
             self.cam_lss = LiftSplatShoot(grid=0.6, inputC=256, outputC=hidden_channel, camC=64, pc_range=pc_range,
                                           img_scale=img_scale, downsample=4)                 # :129-131
+        elif input_img:
+            self.shared_conv_img = nn.Conv2d(in_channels_img, hidden_channel, 3, padding=1, bias=bool(bias))   # :134-141
         self.num_layers = num_layers if num_layers else 0
         self.fusion_blocks = nn.ModuleList(
             [FocalEncoderLayer(hidden_channel, iterbev=iterbev, iterbev_wo_img=iterbev_wo_img, iter_bev_cam=iter_bev_cam,
-                               need_projbev=not cam_lss, layer_id=i) for i in range(self.num_layers)])
+                               need_projbev=not cam_lss, layer_id=i, max_points_height=max_points_height)
+             for i in range(self.num_layers)])
         self.extra_feat = extra_feat
         if extra_feat:
             self.extra_output = ConvBNReLU(hidden_channel, hidden_channel, 3, norm_layer=nn.BatchNorm2d, activation_layer=None)
 
     def forward(self, img_feats, pts_feats, img_metas=None):
         new_img_feat = None
-        if self.input_img:                                             # :173-197
+        if self.input_img and not self.use_lss:
+            new_img_feat = self.shared_conv_img(img_feats)             # :199 (image-plane feature; I2P lifts it in layer 0)
+        elif self.input_img:                                           # :173-197
             from .camera import lidar2img_to_rots_trans
             B = len(img_metas)
             rots, trans = zip(*[lidar2img_to_rots_trans(m["lidar2img"]) for m in img_metas])

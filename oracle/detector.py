@@ -88,6 +88,8 @@ class FocalFormer3D(nn.Module):
         feats = [None]
         if self.input_img:
             B, N, C, H, W = img.shape
+            for m in img_metas:
+                m.update(input_shape=(H, W))                                                  # focalformer3d.py:136-139
             c = self.img_backbone(img.view(B * N, C, H, W).float())                          # focalformer3d.py:133-153
             feats = self.img_neck(c)
             if stages is not None:

@@ -209,6 +209,7 @@ def main():
     camera_golden(fe)
     fusion_golden(fe)
     head_variants_golden(fd, box_cls)
+    proj_golden(fe)
 
 
 def head_variants_golden(fd, box_cls):
@@ -275,6 +276,37 @@ def fusion_golden(fe):
     path = os.path.join(OUT, "focalformer3d_lc_encoder.pt")
     torch.save(out, path)
     print(f"wrote {path} ({sum(t.numel() for t in _tensors(out))} values)")
+
+
+def proj_golden(fe):
+    """Real FocalEncoder of FocalFormer3D_LC_Proj (no Lift-Splat-Shoot): shared_conv_img on the image-plane feature, the
+    layer-0 I2P projection block (encoder_utils.py:184-262: pillar sample points -> lidar2img -> grid_sample -> camera
+    average -> single-head attention), then the same 'bevfusion' layers as FocalFormer3D_LC."""
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict, synth_cameras
+    img_hw, bev = (32, 64), 16
+    cfg = scaled_model_cfg(load_config(default_config_path("focalformer3d_lc_proj"))["model"], bev=bev, num_proposals=12)
+    sd = make_state_dict(cfg, seed=9)
+    g = torch.Generator().manual_seed(14)
+    ne = dict(cfg["imgpts_neck"]); ne.pop("type")
+    with no_cuda_device():
+        enc = fe.FocalEncoder(**ne).eval()
+        enc.load_state_dict({k[len("imgpts_neck."):]: v for k, v in sd.items() if k.startswith("imgpts_neck.")}, strict=True)
+        B, N = 2, 6
+        feat = torch.randn(B * N, 256, img_hw[0] // 4, img_hw[1] // 4, generator=g) * 0.7
+        neck = torch.randn(B, 512, bev, bev, generator=g) * 0.3
+        # cameras 20 m behind the rig centre so that a good part of the hard-coded +-54 m pillar grid projects into them
+        metas = [dict(lidar2img=synth_cameras(N, img_hw, seed=80 + b), input_shape=img_hw) for b in range(B)]
+        with torch.no_grad():
+            new_img, (conv_feat, stage_list) = enc(feat, neck, metas)
+            i2p = enc.fusion_blocks[0].I2P_block(conv_feat, enc.shared_conv_img(feat).view(B, N, 128, img_hw[0] // 4, img_hw[1] // 4), metas)
+    out = dict(img_hw=img_hw, bev=bev, weights_seed=9, feat=feat, neck=neck,
+               lidar2img=torch.stack([torch.as_tensor(m["lidar2img"]) for m in metas]), conv_feat=conv_feat.clone(),
+               stage_feats=[t.clone() for t in stage_list], new_img_feat=new_img.clone(), i2p=i2p.clone())
+    path = os.path.join(OUT, "focalformer3d_lc_proj_encoder.pt")
+    torch.save(out, path)
+    seen = (i2p.abs().sum(1) > 0).float().mean().item()
+    print(f"wrote {path} ({sum(t.numel() for t in _tensors(out))} values; {100 * seen:.0f} % of the BEV cells see a camera)")
 
 
 def camera_golden(fe):

@@ -106,3 +106,51 @@ def test_lc_state_dict_contract_and_packing(gold):
     assert "img1" in blk and "img1" not in model.imgpts_neck.pk["fusion_blocks.1"]
     with pytest.raises(ValueError):
         model.forward_raw([torch.zeros(4, 5)])                           # fusion config without images: loud failure
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FocalFormer3D_LC_Proj ('proj' variant: I2P projection block instead of Lift-Splat-Shoot) -- oracle side only
+PROJ = os.path.join(ROOT, "tests", "golden", "focalformer3d_lc_proj_encoder.pt")
+REF_PROJ_CFG = "/root/reference/projects/configs/focalformer3d/FocalFormer3D_LC_Proj.py"
+
+
+def test_oracle_proj_encoder_matches_reference():
+    """oracle/bev.py I2P + FocalEncoder against the REAL FocalEncoder / I2P of the reference (golden fixture)."""
+    if not os.path.exists(PROJ):
+        pytest.skip("golden fixture missing")
+    from focalformer3d_b200.config import load_config, default_config_path, scaled_model_cfg
+    from focalformer3d_b200.synth import make_state_dict
+    from oracle.bev import FocalEncoder
+    gold = torch.load(PROJ, map_location="cpu")
+    cfg = scaled_model_cfg(load_config(default_config_path("focalformer3d_lc_proj"))["model"], bev=gold["bev"], num_proposals=12)
+    sd = make_state_dict(cfg, seed=gold["weights_seed"])
+    ne = {k: v for k, v in cfg["imgpts_neck"].items() if k != "type"}
+    enc = FocalEncoder(**ne).eval()
+    enc.load_state_dict({k[len("imgpts_neck."):]: v for k, v in sd.items() if k.startswith("imgpts_neck.")}, strict=True)
+    metas = [dict(lidar2img=m.numpy(), input_shape=tuple(gold["img_hw"])) for m in gold["lidar2img"]]
+    B, N = len(metas), gold["lidar2img"].shape[1]
+    with torch.no_grad():
+        new_img, (conv_feat, stages) = enc(gold["feat"], gold["neck"], metas)
+        img_plane = enc.shared_conv_img(gold["feat"])
+        i2p = enc.fusion_blocks[0].I2P_block(conv_feat, img_plane.view(B, N, *img_plane.shape[1:]), metas)
+    close = lambda a, b: ((a - b).abs() / (1 + b.abs())).max().item()
+    assert close(conv_feat, gold["conv_feat"]) < 1e-5
+    assert close(i2p, gold["i2p"]) < 1e-4                       # the projection block on its own
+    assert (gold["i2p"].abs().sum(1) > 0).float().mean().item() > 0.5
+    for a, b in zip(stages, gold["stage_feats"]):
+        assert close(a, b) < 1e-4
+    assert close(new_img, gold["new_img_feat"]) < 1e-4
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PROJ_CFG), reason="reference tree not present on this box")
+def test_lc_proj_config_mirrors_reference_and_product_refuses_it():
+    from focalformer3d_b200.config import load_config, default_config_path
+    from focalformer3d_b200.synth import param_spec
+    from focalformer3d_b200.model import build_model
+    ref, mine = load_config(REF_PROJ_CFG)["model"], load_config(default_config_path("focalformer3d_lc_proj"))["model"]
+    for part in ("img_backbone", "img_neck", "pts_middle_encoder", "pts_backbone", "pts_neck", "imgpts_neck"):
+        assert dict(ref[part]) == dict(mine[part]), part
+    assert set(param_spec(ref)) == set(param_spec(mine))
+    assert "imgpts_neck.fusion_blocks.0.I2P_block.learnedAlign.in_proj_weight" in param_spec(mine)
+    with pytest.raises(NotImplementedError):                     # no silent fallback: the CUDA product does not build it yet
+        build_model(mine)
