@@ -10,7 +10,8 @@
 namespace ff3d {
 
 __device__ __forceinline__ uint32_t lin_key(int b, int z, int y, int x, int D, int H, int W) {
-  return (uint32_t)(((b * D + z) * H + y) * W + x);
+  // unsigned arithmetic (callers guarantee batch * D * H * W < 2^32, which can exceed a signed int)
+  return (((uint32_t)b * (uint32_t)D + (uint32_t)z) * (uint32_t)H + (uint32_t)y) * (uint32_t)W + (uint32_t)x;
 }
 
 __global__ void sp_hash_build_kernel(const int* __restrict__ coors, const int* __restrict__ n_dev, int cap, int D,

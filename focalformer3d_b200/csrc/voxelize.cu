@@ -45,7 +45,8 @@ __global__ void vox_hash_kernel(const float* __restrict__ pts, VoxP p, uint32_t*
   int slot = -1;
   if (cx >= 0 && cx < p.g[0] && cy >= 0 && cy < p.g[1] && cz >= 0 && cz < p.g[2]) {
     int b = sample_of(p, i);
-    uint32_t key = (uint32_t)(((b * p.g[2] + cz) * p.g[1] + cy) * p.g[0] + cx);
+    // unsigned arithmetic: the guard only bounds batch * cells below 2^32, which overflows a signed int product
+    uint32_t key = (((uint32_t)b * (uint32_t)p.g[2] + (uint32_t)cz) * (uint32_t)p.g[1] + (uint32_t)cy) * (uint32_t)p.g[0] + (uint32_t)cx;
     bool ins;
     slot = hash_insert(hkeys, hmask, key, &ins);   // table holds 2x the point count: never full
     if (slot >= 0) atomicMin(&hfirst[slot], i);

@@ -566,11 +566,38 @@ class FocalEncoder(ParamTree):
     def camera_rots_trans(img_metas, dev):
         """focal_encoder.py:178-194: per camera inverse(lidar2img) -> rotation [B*N, 9] and translation [B*N, 3].
         36 4x4 inverses: done on the host (LAPACK), uploaded once per call."""
+        for m in img_metas:
+            FocalEncoder._check_identity_metas(m)
         mats = torch.stack([torch.as_tensor(m["lidar2img"], dtype=torch.float32).reshape(-1, 4, 4) for m in img_metas])
         inv = torch.inverse(mats.cpu())
         rots = inv[..., :3, :3].reshape(-1, 9).contiguous().to(dev)
         trans = inv[..., :3, 3].reshape(-1, 3).contiguous().to(dev)
         return rots, trans
+
+    @staticmethod
+    def _check_identity_metas(m):
+        """lss.py:239-267 get_geometry also un-applies img_metas['img_aug_matrix'] (post_rots / post_trans) and runs
+        apply_3d_transformation (pcd_rotation, pcd_scale_factor, pcd_trans, flips) on the frustum points.  The shipped
+        non-TTA test pipeline emits identities; anything else would silently give wrong camera-BEV features here."""
+        import numpy as np
+
+        def ident(v, ref):
+            return v is None or np.allclose(np.asarray(v, dtype=np.float64), ref)
+        bad = []
+        if not ident(m.get("img_aug_matrix"), np.eye(4)):
+            bad.append("img_aug_matrix")
+        if not ident(m.get("pcd_rotation"), np.eye(3)):
+            bad.append("pcd_rotation")
+        if not ident(m.get("pcd_scale_factor"), 1.0):
+            bad.append("pcd_scale_factor")
+        if not ident(m.get("pcd_trans"), 0.0):
+            bad.append("pcd_trans")
+        for k in ("pcd_horizontal_flip", "pcd_vertical_flip", "flip"):
+            if m.get(k):
+                bad.append(k)
+        if bad:
+            raise NotImplementedError("Lift-Splat-Shoot geometry: non-identity augmentation metas %s are not applied "
+                                      "(lss.py:239-267); only the shipped non-TTA test pipeline is built" % bad)
 
     def forward_camera(self, img_feat, img_metas, out):
         """img_feat [B*N, fH, fW, 256] (FPN level 0) -> out [B, ny, nx, hidden]; returned twice by the reference
@@ -690,6 +717,10 @@ class FocalDecoder(ParamTree):
                 or heatmap_box or boxpos is not None:
             raise NotImplementedError("FocalDecoder: only the shipped LiDAR head variants are built")
         self.classaware_reg = bool(classaware_reg)
+        if self.classaware_reg and "vel" in common_heads:
+            # focal_decoder.py:317-319 widens every head by num_classes but :940-943 class-selects only
+            # center/height/dim/rot: a class-aware 'vel' head keeps nc*2 channels in the reference.  Not reproduced.
+            raise NotImplementedError("FocalDecoder: classaware_reg with a 'vel' head is not built (no shipped config)")
         if not loss_cls.get("use_sigmoid", False):
             # focal_decoder.py:164-166 appends a background class in that case; no shipped config uses it
             raise NotImplementedError("FocalDecoder: only loss_cls.use_sigmoid=True heads are built")
@@ -702,6 +733,9 @@ class FocalDecoder(ParamTree):
         self.num_classes, self.num_proposals, self.hc = num_classes, num_proposals, hidden_channel
         self.num_decoder_layers, self.num_heads = num_decoder_layers, num_heads
         self.nms_kernel_size, self.test_cfg = nms_kernel_size, test_cfg
+        self.nms_type = (test_cfg or {}).get("nms_type")
+        if self.nms_type not in (None, "circle", "rotate"):
+            raise NotImplementedError(f"FocalDecoder: test_cfg.nms_type={self.nms_type!r} (focal_decoder.py:1352-1385)")
         self.stages, self.reuse_first = stages, reuse_first_heatmap
         self.roi_feats, self.roi_based_reg = roi_feats, roi_based_reg
         self.roi_expand_ratio = [roi_expand_ratio] * num_decoder_layers if isinstance(roi_expand_ratio, float) else list(roi_expand_ratio)
