@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("x_bstride", C.c_longlong), ("y_bstride", C.c_longlong), ("y_row0", C.c_longlong),
         ("ux", C.c_int), ("uy", C.c_int), ("dx", C.c_int), ("dy", C.c_int),
         ("nbr", C.c_void_p), ("nbr_stride", C.c_int), ("y_off", C.c_void_p), ("res_after_act", C.c_int),
+        ("tile_mask", C.c_void_p),
     ]
 
 
@@ -47,6 +48,13 @@ SIGNATURES = {
     "ff3d_sp_subm_map": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "ff3d_sp_down_build": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P, _I, _I, _I, _I, _P, _P,
                                 _I, _P, _P, _P]),
+    "ff3d_sp_down_sites": (_I, [_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _IP, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "ff3d_sp_tap_keys": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P]),
+    "ff3d_sort_workspace_bytes": (_SZ, [_I]),
+    "ff3d_sort_pairs": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _SZ, _P]),
+    "ff3d_sp_level_permute": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "ff3d_sp_nbr_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ff3d_sp_gather_rows": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _P]),
     "ff3d_sp_bev_offsets": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ff3d_igemm": (_I, [C.POINTER(GemmDesc), _P]),
     "ff3d_tcgemm": (_I, [C.POINTER(GemmDesc), _P, _P]),

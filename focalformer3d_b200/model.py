@@ -175,14 +175,19 @@ class SparseEncoder(ParamTree):
         self.pk = pk
 
     def forward(self, vox, batch, bev_out, overflow):
-        """vox: dict from ops.voxelize; bev_out [B,H,W,2*C] zero-initialised NHWC buffer (channel = d*C + c)."""
+        """vox: dict from ops.voxelize; bev_out [B,H,W,2*C] zero-initialised NHWC buffer (channel = d*C + c).
+        Every level is stored in tap-mask order (ops.SparseLevel.sort_by_mask): the voxeliser's first-appearance order
+        (the reference's, checked by the parity tests) stays untouched in ``vox``; row order inside the sparse encoder is
+        implementation-defined in spconv too and vanishes in the dense BEV scatter."""
         dev = vox["mean"].device
         cap1 = vox["coors"].shape[0]
         lvl = ops.SparseLevel(vox["coors"], vox["n_dev"][:1], cap1, batch, self.sparse_shape)
         lvl.build_hash()
+        perm = lvl.sort_by_mask()
+        feats = ops.gather_rows(vox["mean"], perm, lvl.n_dev, vox["mean"].shape[1])
         w, b = self.pk["conv_input"]
         x = torch.empty((cap1, w.shape[-1]), dtype=torch.float32, device=dev)
-        ops.sparse_conv(vox["mean"], lvl.subm_map(), lvl.n_dev, w, b, x, act=ACT_RELU)
+        ops.sparse_conv(feats, lvl.subm_map(), lvl.n_dev, w, b, x, act=ACT_RELU)
         self.level_sizes = [lvl.n_dev]
         for i, blocks in enumerate(self.encoder_channels):
             for j, cout in enumerate(blocks):
@@ -191,29 +196,30 @@ class SparseEncoder(ParamTree):
                     pad = self.encoder_paddings[i][j]
                     p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
                     cap_out = int(lvl.cap * self.cap_growth[i])
-                    nl, nbr = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow)
+                    nl, rb = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow, ldy=cout)
                     w, b = self.pk[q]
                     y = torch.empty((nl.cap, cout), dtype=torch.float32, device=dev)
-                    ops.sparse_conv(x, nbr, nl.n_dev, w, b, y, act=ACT_RELU)
+                    ops.sparse_conv(x, rb, nl.n_dev, w, b, y, act=ACT_RELU)
                     lvl, x = nl, y
                     self.level_sizes.append(lvl.n_dev)
                 else:
-                    nbr = lvl.subm_map()
+                    rb = lvl.subm_map()
                     w1, b1 = self.pk[q + ".1"]
                     w2, b2 = self.pk[q + ".2"]
                     t = torch.empty_like(x)
-                    ops.sparse_conv(x, nbr, lvl.n_dev, w1, b1, t, act=ACT_RELU)
+                    ops.sparse_conv(x, rb, lvl.n_dev, w1, b1, t, act=ACT_RELU)
                     y = torch.empty_like(x)
-                    ops.sparse_conv(t, nbr, lvl.n_dev, w2, b2, y, act=ACT_RELU, res=x)
+                    ops.sparse_conv(t, rb, lvl.n_dev, w2, b2, y, act=ACT_RELU, res=x)
                     x = y
         # conv_out: SparseConv3d k(3,1,1) s(2,1,1) p0 + BN + ReLU, scattered straight into the NHWC BEV grid
-        nl, nbr = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), lvl.cap, overflow)
-        self.level_sizes.append(nl.n_dev)
         Cc = self.output_channels
-        assert bev_out.shape[-1] == nl.shape[0] * Cc and bev_out.is_contiguous()
-        off = nl.bev_offsets(bev_out.shape[-1], Cc)
+        assert bev_out.is_contiguous()
+        Hb, Wb, ld = bev_out.shape[1], bev_out.shape[2], bev_out.shape[3]
+        nl, rb = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), lvl.cap, overflow, ldy=ld, sort_level=False, bev=(Hb, Wb, Cc))
+        self.level_sizes.append(nl.n_dev)
+        assert ld == nl.shape[0] * Cc and (Hb, Wb) == tuple(nl.shape[1:])
         w, b = self.pk["conv_out"]
-        ops.sparse_conv(x, nbr, nl.n_dev, w, b, bev_out, act=ACT_RELU, y_off=off, cout=Cc)
+        ops.sparse_conv(x, rb, nl.n_dev, w, b, bev_out, act=ACT_RELU, cout=Cc)
         return bev_out
 
 

@@ -212,10 +212,11 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     return out
 
 
-def sparse_conv(x, nbr, n_dev, w, bias, out, act=ACT_RELU, res=None, y_off=None, cout=None):
-    """Rulebook gather-GEMM: x [cap_in, cin] rows, nbr [taps, cap_out] int32, out [cap_out, cout] rows
-    (or an arbitrary buffer when ``y_off`` gives per-row element offsets)."""
+def sparse_conv(x, rb, n_dev, w, bias, out, act=ACT_RELU, res=None, cout=None):
+    """Rulebook gather-GEMM: x [cap_in, cin] rows, rb a Rulebook (nbr [taps, cap_out], per-tile tap masks, optional row
+    map), out [cap_out, cout] rows (or an arbitrary buffer when the rulebook carries element offsets)."""
     _chk_f32(x, "sparse_conv.x")
+    nbr, y_off = rb.nbr, rb.y_off
     taps, cap = nbr.shape
     cin = x.shape[1]
     cout = cout or w.shape[-1]
@@ -227,10 +228,11 @@ def sparse_conv(x, nbr, n_dev, w, bias, out, act=ACT_RELU, res=None, y_off=None,
     d.y, d.ldy, d.act = out.data_ptr(), (out.stride(0) if y_off is None else 0), act
     d.nbr, d.nbr_stride = nbr.data_ptr(), nbr.stride(0)
     d.y_off = y_off.data_ptr() if y_off is not None else None
+    d.tile_mask = rb.tile_mask.data_ptr() if rb.tile_mask is not None else None
     t0 = prof.begin()
     _gemm(d, w, "sparse")
     prof.end(t0, f"spconv[{taps}t {cin}->{cout}]", None, None, n_dev, dict(nbr=nbr, cin=cin, cout=cout, taps=taps,
-                                                                            x_rows=x.shape[0]))
+                                                                            x_rows=x.shape[0], tile_mask=rb.tile_mask))
     _count()
     return out
 
@@ -379,8 +381,21 @@ def next_pow2(v):
     return p
 
 
+class Rulebook:
+    """Output-stationary rulebook of one sparse conv in mask-sorted tile order: ``nbr`` [taps, cap] (input row feeding
+    tile position j through tap t, -1 = none), ``tile_mask`` [ceil(cap/128)] (OR of the tap masks of each 128-row tile:
+    the gather-GEMM skips the other taps), ``y_off`` (element offset of tile position j's output row; None when the
+    rows are stored in tile order)."""
+
+    def __init__(self, nbr, tile_mask, y_off=None):
+        self.nbr, self.tile_mask, self.y_off = nbr, tile_mask, y_off
+
+
+SUBM_K, SUBM_S, SUBM_P = (3, 3, 3), (1, 1, 1), (1, 1, 1)
+
+
 class SparseLevel:
-    """One resolution level of the sparse encoder: coordinates, device row count, hash."""
+    """One resolution level of the sparse encoder: coordinates, device row count, hash (coordinate -> row)."""
 
     def __init__(self, coors, n_dev, cap, batch, shape):
         self.coors, self.n_dev, self.cap, self.batch, self.shape = coors, n_dev, cap, batch, tuple(shape)
@@ -395,18 +410,62 @@ class SparseLevel:
                                      _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _stream()), "ff3d_sp_hash_build")
         _count(2)
 
+    def _sorted_perm(self, out_coors, n_out, cap_out, k3, s3, p3):
+        """perm[j] = row (of out_coors) at sorted tile position j, ordered by the tap mask of the conv (k3, s3, p3)
+        whose INPUT level is self."""
+        D, H, W = self.shape
+        dev = out_coors.device
+        keys = torch.empty((cap_out,), dtype=torch.int32, device=dev)
+        check(lib.ff3d_sp_tap_keys(_ptr(out_coors), _ptr(n_out), cap_out, D, H, W, _ptr(self.hkeys), _ptr(self.hvals),
+                                   self.hsize, L.int_array(k3), L.int_array(s3), L.int_array(p3), _ptr(keys), _stream()),
+              "ff3d_sp_tap_keys")
+        ws_bytes = lib.ff3d_sort_workspace_bytes(cap_out)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        skeys = torch.empty_like(keys)
+        perm = torch.empty((cap_out,), dtype=torch.int32, device=dev)
+        kvol = k3[0] * k3[1] * k3[2]
+        check(lib.ff3d_sort_pairs(_ptr(keys), None, _ptr(n_out), cap_out, kvol, _ptr(skeys), _ptr(perm), _ptr(ws), ws_bytes,
+                                  _stream()), "ff3d_sort_pairs")
+        _count(1 + 3 * ((kvol + 8) // 9))
+        return perm
+
+    def _rulebook(self, out_coors, perm, n_out, cap_out, k3, s3, p3, y_mode=0, ldy=0, bev=(0, 0, 0)):
+        D, H, W = self.shape
+        dev = out_coors.device
+        kvol = k3[0] * k3[1] * k3[2]
+        nbr = torch.empty((kvol, cap_out), dtype=torch.int32, device=dev)
+        tile_mask = torch.empty(((cap_out + 127) // 128,), dtype=torch.int32, device=dev)
+        y_off = torch.empty((cap_out,), dtype=torch.int32, device=dev) if y_mode else None
+        check(lib.ff3d_sp_nbr_build(_ptr(out_coors), _ptr(perm), _ptr(n_out), cap_out, D, H, W, _ptr(self.hkeys),
+                                    _ptr(self.hvals), self.hsize, L.int_array(k3), L.int_array(s3), L.int_array(p3),
+                                    _ptr(nbr), _ptr(tile_mask), _ptr(y_off), y_mode, ldy, bev[0], bev[1], bev[2], _stream()),
+              "ff3d_sp_nbr_build")
+        _count()
+        return Rulebook(nbr, tile_mask, y_off)
+
+    def sort_by_mask(self):
+        """Re-store the level in SubM tap-mask order (all SubM convs of the level then run on homogeneous tiles).
+        Returns perm (new row i <- old row perm[i]) so that the caller can move row data stored in the old order."""
+        D, H, W = self.shape
+        perm = self._sorted_perm(self.coors, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
+        coors = torch.empty_like(self.coors)
+        check(lib.ff3d_sp_level_permute(_ptr(self.coors), _ptr(perm), _ptr(self.n_dev), self.cap, D, H, W, _ptr(coors),
+                                        _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _stream()), "ff3d_sp_level_permute")
+        _count()
+        self.coors = coors
+        self.subm = None
+        return perm
+
     def subm_map(self):
+        """SubM k=3 rulebook of the level (rows already in mask order: no row map)."""
         if self.subm is None:
-            D, H, W = self.shape
-            self.subm = torch.empty((27, self.cap), dtype=torch.int32, device=self.coors.device)
-            check(lib.ff3d_sp_subm_map(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W,
-                                       _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _ptr(self.subm), _stream()),
-                  "ff3d_sp_subm_map")
-            _count()
+            self.subm = self._rulebook(self.coors, None, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
         return self.subm
 
-    def downsample(self, k3, s3, p3, cap_out, overflow):
-        """Returns (new level with its hash built, nbr [kvol, cap_out])."""
+    def downsample(self, k3, s3, p3, cap_out, overflow, ldy, sort_level=True, bev=None):
+        """SparseConv3d (k3, s3, p3): creates the output level and the conv's rulebook.  The new level is stored in ITS
+        SubM mask order (``sort_level``); the conv runs over its own mask order and writes through ``y_off``
+        (row * ldy, or -- ``bev=(H, W, C)`` -- straight into the NHWC BEV grid).  Returns (level, Rulebook)."""
         D, H, W = self.shape
         oshape = tuple((self.shape[i] + 2 * p3[i] - k3[i]) // s3[i] + 1 for i in range(3))
         cells = self.batch * oshape[0] * oshape[1] * oshape[2]
@@ -415,23 +474,30 @@ class SparseLevel:
         coors_o = torch.empty((cap_out, 4), dtype=torch.int32, device=dev)
         n_o = torch.empty((1,), dtype=torch.int32, device=dev)
         lvl = SparseLevel(coors_o, n_o, cap_out, self.batch, oshape)
-        kvol = k3[0] * k3[1] * k3[2]
-        nbr = torch.empty((kvol, cap_out), dtype=torch.int32, device=dev)
-        check(lib.ff3d_sp_down_build(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W,
-                                     _ptr(self.hkeys), _ptr(self.hvals), self.hsize, L.int_array(k3), L.int_array(s3),
-                                     L.int_array(p3), _ptr(coors_o), _ptr(n_o), cap_out, oshape[0], oshape[1], oshape[2],
-                                     _ptr(lvl.hkeys), _ptr(lvl.hvals), lvl.hsize, _ptr(nbr), _ptr(overflow), _stream()),
-              "ff3d_sp_down_build")
-        _count(5)
-        return lvl, nbr
+        check(lib.ff3d_sp_down_sites(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W, L.int_array(k3),
+                                     L.int_array(s3), L.int_array(p3), _ptr(coors_o), _ptr(n_o), cap_out, oshape[0],
+                                     oshape[1], oshape[2], _ptr(lvl.hkeys), _ptr(lvl.hvals), lvl.hsize, _ptr(overflow),
+                                     _stream()), "ff3d_sp_down_sites")
+        _count(4)
+        if sort_level:
+            lvl.sort_by_mask()
+        perm = self._sorted_perm(lvl.coors, n_o, cap_out, k3, s3, p3)
+        if bev is not None:
+            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=2, ldy=ldy, bev=bev)
+        else:
+            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=1, ldy=ldy)
+        return lvl, rb
 
-    def bev_offsets(self, ld, Cc):
-        D, H, W = self.shape
-        off = torch.empty((self.cap,), dtype=torch.int32, device=self.coors.device)
-        check(lib.ff3d_sp_bev_offsets(_ptr(self.coors), _ptr(self.n_dev), self.cap, H, W, ld, Cc, _ptr(off), _stream()),
-              "ff3d_sp_bev_offsets")
-        _count()
-        return off
+
+def gather_rows(src, perm, n_dev, cols):
+    """dst[i, :cols] = src[perm[i], :cols] for the first *n_dev rows."""
+    _chk_f32(src, "gather_rows.src")
+    cap = perm.shape[0]
+    dst = torch.empty((cap, src.shape[1]), dtype=torch.float32, device=src.device)
+    check(lib.ff3d_sp_gather_rows(_ptr(src), src.stride(0), _ptr(perm), _ptr(n_dev), cap, _ptr(dst), dst.stride(0), cols,
+                                  _stream()), "ff3d_sp_gather_rows")
+    _count()
+    return dst
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -90,6 +90,37 @@ int ff3d_sp_down_build(const int* coors_in, const int* n_in_dev, int cap_in, int
                        int* coors_out, int* n_out_dev, int cap_out, int Do, int Ho, int Wo,
                        uint32_t* hkeys_out, int* hvals_out, int hsize_out, int* nbr_out, int* overflow_dev,
                        ff3d_stream_t stream);
+/* ---- mask-sorted rulebooks (round 2): the output rows of every sparse conv are ordered by their tap-presence mask so
+ * that the 128-row tiles of the gather-GEMM are homogeneous and the kernel skips, per tile, every tap no row of the tile
+ * uses (ff3d_gemm_desc.tile_mask).  Same [upstream] get_indice_pairs semantics as above (i = o*s - p + k); only the ROW
+ * ORDER -- implementation-defined in spconv -- changes.
+ *   ff3d_sp_down_sites   the site-creation half of ff3d_sp_down_build (output coordinates + hash, allocation order)
+ *   ff3d_sp_tap_keys     keys[o] = tap mask of output row o (probing the INPUT level's hash) with the bits permuted into
+ *                        rarity order (corner taps most significant); kvol = k0*k1*k2 <= 27 key bits
+ *   ff3d_sort_pairs      stable LSD radix sort of (key, value) with a device-side count; vals_in NULL -> 0..n-1
+ *   ff3d_sp_level_permute  store a level in sorted order: coors_out[i] = coors_in[perm[i]], hash values := new rows
+ *   ff3d_sp_nbr_build    nbr[t][j] for tile position j (source row o = perm ? perm[j] : j), tile_mask[j/128] = OR of
+ *                        the natural-order tap masks of the tile's rows, and the row map y_off (y_mode 1: o*ldy;
+ *                        y_mode 2: NHWC BEV element offset ((b*bev_h + y)*bev_w + x)*ldy + z*bev_c; 0: none)
+ *   ff3d_sp_gather_rows  dst[i,:cols] = src[perm[i],:cols] (voxel features into the sorted level-1 order) */
+int ff3d_sp_down_sites(const int* coors_in, const int* n_in_dev, int cap_in, int batch, int D, int H, int W,
+                       const int* k3, const int* s3, const int* p3, int* coors_out, int* n_out_dev, int cap_out,
+                       int Do, int Ho, int Wo, uint32_t* hkeys_out, int* hvals_out, int hsize_out, int* overflow_dev,
+                       ff3d_stream_t stream);
+int ff3d_sp_tap_keys(const int* coors_out, const int* n_out_dev, int cap_out, int D, int H, int W,
+                     const uint32_t* hkeys_in, const int* hvals_in, int hsize_in, const int* k3, const int* s3,
+                     const int* p3, uint32_t* keys, ff3d_stream_t stream);
+size_t ff3d_sort_workspace_bytes(int cap);
+int ff3d_sort_pairs(const uint32_t* keys_in, const int* vals_in, const int* n_dev, int cap, int key_bits,
+                    uint32_t* keys_out, int* vals_out, void* workspace, size_t workspace_bytes, ff3d_stream_t stream);
+int ff3d_sp_level_permute(const int* coors_in, const int* perm, const int* n_dev, int cap, int D, int H, int W,
+                          int* coors_out, const uint32_t* hkeys, int* hvals, int hsize, ff3d_stream_t stream);
+int ff3d_sp_nbr_build(const int* coors_out, const int* perm, const int* n_out_dev, int cap_out, int D, int H, int W,
+                      const uint32_t* hkeys_in, const int* hvals_in, int hsize_in, const int* k3, const int* s3,
+                      const int* p3, int* nbr, uint32_t* tile_mask, int* y_off, int y_mode, int ldy, int bev_h, int bev_w,
+                      int bev_c, ff3d_stream_t stream);
+int ff3d_sp_gather_rows(const float* src, int ld_src, const int* perm, const int* n_dev, int cap, float* dst, int ld_dst,
+                        int cols, ff3d_stream_t stream);
 /* element offsets for scattering the last sparse level straight into the NHWC BEV grid:
  * off[o] = ((b*H + y)*W + x)*ld + z*C   (replaces SparseConvTensor.dense() + view, [upstream]) */
 int ff3d_sp_bev_offsets(const int* coors, const int* n_dev, int cap, int H, int W, int ld, int C, int* off,
@@ -131,6 +162,9 @@ typedef struct ff3d_gemm_desc {
   const int* nbr; int nbr_stride;  /* [taps, nbr_stride] */
   const int* y_off;                /* optional per-row ELEMENT offset into y (replaces m*ldy) */
   int res_after_act;               /* 0: act(acc+bias+res) (residual blocks); 1: act(acc+bias)+res (query_feat += roi_feat) */
+  const uint32_t* tile_mask;       /* SPARSE, optional: [ceil(M/128)] OR of the tap masks (bit t = tap t) of each 128-row
+                                      tile (ff3d_sp_nbr_build); taps whose bit is clear are skipped for the tile.  Every
+                                      (row, tap) with nbr >= 0 must have its bit set.  NULL = all taps. */
 } ff3d_gemm_desc;
 
 int ff3d_igemm(const ff3d_gemm_desc* desc, ff3d_stream_t stream);

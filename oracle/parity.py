@@ -96,26 +96,35 @@ def head_report(res, det, oracle_head, ref, rdet):
     b = ref["query_heatmap_score"][idx].gather(2, po_s[:, None].expand(-1, nc, -1))
     out["max_abs"]["query_heatmap_score"] = (a - b).abs().max().item()
     out["max_abs_heads"] = worst
-    # final boxes (get_bboxes + coder decode): keep mask exact, boxes / scores within TOL
+    # final boxes (get_bboxes + coder decode): keep mask exact; then the reference's own output list (score-truncated to
+    # 200 boxes, focal_decoder.py:1395-1400) against ours truncated the same way, matched box by box
     if det is not None and rdet is not None:
         boxes, scores, labels, keep = (_cpu(t) for t in det)
-        keep_equal, box_err, score_err, labels_ok = True, 0.0, 0.0, True
+        keep_equal, box_err, score_err, labels_ok, n_boxes = True, 0.0, 0.0, True, 0
         for b in sel:
             r = rdet[b]
             ok = r["keep"]
             km = keep[b][pm[b]].bool()
             keep_equal &= bool(torch.equal(km, ok[po[b]]))
-            if r["boxes_3d"].shape[0] != int(ok.sum()) or not keep_equal:
-                continue                                     # > 200 kept boxes: the oracle list is score-truncated
-            ref_boxes = torch.zeros(ok.shape[0], r["boxes_3d"].shape[1]); ref_boxes[ok] = r["boxes_3d"]
-            ref_scores = torch.zeros(ok.shape[0]); ref_scores[ok] = r["scores_3d"]
-            ref_labels = torch.zeros(ok.shape[0], dtype=torch.int32); ref_labels[ok] = r["labels_3d"].int()
-            sel_m, sel_o = pm[b][km], po[b][ok[po[b]]]
-            if sel_m.numel():
-                box_err = max(box_err, (boxes[b][sel_m] - ref_boxes[sel_o]).abs().max().item())
-                score_err = max(score_err, (scores[b][sel_m] - ref_scores[sel_o]).abs().max().item())
-                labels_ok &= bool(torch.equal(labels[b][sel_m].int(), ref_labels[sel_o]))
-        out["keep_equal"], out["box_labels_equal"] = bool(keep_equal), bool(labels_ok)
+            m = keep[b].bool()
+            bx, sc, lb = boxes[b][m], scores[b][m], labels[b][m]
+            if bx.shape[0] > 200:
+                inds = sc.argsort(descending=True, stable=True)[:200]
+                bx, sc, lb = bx[inds], sc[inds], lb[inds]
+            rb_, rs_, rl_ = r["boxes_3d"], r["scores_3d"], r["labels_3d"].int()
+            if bx.shape[0] != rb_.shape[0]:
+                keep_equal = False
+                continue
+            if rb_.shape[0] == 0:
+                continue
+            # nearest match in (box, score) space: the 200-cut and the order may differ only between equal scores
+            d = torch.cdist(torch.cat([rb_, rs_[:, None]], 1).double(), torch.cat([bx, sc[:, None]], 1).double(), p=float("inf"))
+            best, arg = d.min(1)
+            box_err = max(box_err, best.max().item())
+            score_err = max(score_err, (rs_ - sc[arg]).abs().max().item())
+            labels_ok &= bool(torch.equal(rl_, lb[arg].int()))
+            n_boxes += int(rb_.shape[0])
+        out["keep_equal"], out["box_labels_equal"], out["boxes_compared"] = bool(keep_equal), bool(labels_ok), n_boxes
         out["max_abs"]["boxes"], out["max_abs"]["scores"] = box_err, score_err
     return out
 

@@ -180,9 +180,12 @@ def _to_dense(feat, coors, n, shape, B):
     return out
 
 
+@pytest.mark.parametrize("sort_rows", [False, True])
 @pytest.mark.parametrize("k,s,p", [(None, None, None), ((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1)),
                                    ((3, 1, 1), (2, 1, 1), (0, 0, 0))])
-def test_sparse_conv_matches_oracle(ops, k, s, p):
+def test_sparse_conv_matches_oracle(ops, k, s, p, sort_rows):
+    """SubM and strided sparse convs vs the oracle; ``sort_rows`` stores the input level in tap-mask order first (what the
+    sparse encoder does), so both homogeneous (mask-sorted, sparse tile masks) and random (full tile masks) tiles run."""
     from oracle import sparse as osp
     from focalformer3d_b200.model import pack_taps
     B, shape, n, Ci, Co = 2, (9, 20, 20), 900, 16, 32
@@ -204,17 +207,26 @@ def test_sparse_conv_matches_oracle(ops, k, s, p):
     with torch.no_grad():
         ref = oconv(osp.SparseTensor(feat, idx, shape, B))
     wpk = pack_taps(wt.reshape(-1, Ci, Co), "cuda")
+    xg, resg = x.cuda(), res.cuda()
+    if sort_rows:
+        perm = lvl.sort_by_mask()
+        pl = perm[:n].long()
+        assert torch.equal(pl.sort().values.cpu(), torch.arange(n))                  # a permutation of the active rows
+        assert torch.equal(lvl.coors[:n].cpu(), coors[pl.cpu()])
+        xg = ops.gather_rows(xg, perm, n_dev, Ci)
+        resg = ops.gather_rows(resg, perm, n_dev, Co)
     if subm:
         out = torch.zeros((cap, Co), device="cuda")
-        ops.sparse_conv(x.cuda(), lvl.subm_map(), lvl.n_dev, wpk, bias.cuda(), out, act=1, res=res.cuda())
-        got = _to_dense(out.cpu(), coors, n, shape, B)
+        rb = lvl.subm_map()
+        ops.sparse_conv(xg, rb, lvl.n_dev, wpk, bias.cuda(), out, act=1, res=resg)
+        got = _to_dense(out.cpu(), lvl.coors.cpu(), n, shape, B)
         r = torch.relu(ref.features + bias + res[:n])               # oracle rows are in input order for SubM
         want = _to_dense(r, idx, n, shape, B)
     else:
         overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
-        nl, nbr = lvl.downsample(k, s, p, 4 * cap, overflow)
+        nl, rb = lvl.downsample(k, s, p, 4 * cap, overflow, ldy=Co)
         out = torch.zeros((nl.cap, Co), device="cuda")
-        ops.sparse_conv(x.cuda(), nbr, nl.n_dev, wpk, bias.cuda(), out, act=0)
+        ops.sparse_conv(xg, rb, nl.n_dev, wpk, bias.cuda(), out, act=0)
         no = int(nl.n_dev.item())
         assert int(overflow.item()) == 0 and no == ref.indices.shape[0]          # same output-site set size
         assert nl.shape == tuple(ref.spatial_shape)
@@ -223,7 +235,82 @@ def test_sparse_conv_matches_oracle(ops, k, s, p):
         occ_g = _to_dense(torch.ones(nl.cap, 1), nl.coors.cpu(), no, nl.shape, B)
         occ_w = _to_dense(torch.ones(no, 1), ref.indices, no, ref.spatial_shape, B)
         assert torch.equal(occ_g, occ_w)                                         # identical active sites
+    # the tile masks cover every (row, tap) pair of the rulebook and nothing outside the kernel volume
+    no = int((nl if not subm else lvl).n_dev.item())
+    nbr = rb.nbr[:, :no].cpu()
+    tm = rb.tile_mask.cpu().long() & 0xFFFFFFFF
+    for t in range(nbr.shape[0]):
+        rows = (nbr[t] >= 0).nonzero().flatten()
+        assert bool(((tm[rows // 128] >> t) & 1).all())
+    assert int(tm.max()) < (1 << nbr.shape[0])
     assert (got - want).abs().max().item() < 2e-4
+
+
+def test_mask_sort_makes_tiles_homogeneous(ops):
+    """A clustered (LiDAR-like: thin horizontal sheets) level: after sort_by_mask the per-tile OR masks must select far
+    fewer (tile, tap) pairs than the 27 of unsorted tiles, and the SubM conv result must not depend on the order."""
+    from oracle import sparse as osp
+    from focalformer3d_b200.model import pack_taps
+    g = torch.Generator().manual_seed(5)
+    B, shape, Ci, Co = 2, (11, 120, 120), 32, 32
+    cells = []
+    for b in range(B):
+        yx = torch.randint(0, 120, (9000, 2), generator=g)
+        z = torch.randint(3, 5, (9000, 1), generator=g)                   # two z slabs -> kz = 0 / 2 taps mostly absent
+        cells.append(torch.cat([torch.full((9000, 1), b), z, yx], 1))
+    idx = torch.unique(torch.cat(cells), dim=0).int()
+    idx = idx[torch.randperm(idx.shape[0], generator=g)]
+    n = idx.shape[0]
+    feat = torch.randn(n, Ci, generator=g)
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    wt = torch.randn(3, 3, 3, Ci, Co, generator=g) / 16
+    wpk = pack_taps(wt.reshape(-1, Ci, Co), "cuda")
+    outs, pairs = [], []
+    for sort_rows in (False, True):
+        lvl = ops.SparseLevel(idx.cuda(), n_dev, n, B, shape)
+        lvl.build_hash()
+        x = feat.cuda()
+        if sort_rows:
+            x = ops.gather_rows(x, lvl.sort_by_mask(), n_dev, Ci)
+        rb = lvl.subm_map()
+        out = torch.zeros((n, Co), device="cuda")
+        ops.sparse_conv(x, rb, n_dev, wpk, None, out, act=0)
+        outs.append(_to_dense(out.cpu(), lvl.coors.cpu(), n, shape, B))
+        tm = rb.tile_mask.cpu().long() & 0xFFFFFFFF
+        pairs.append(sum(bin(int(v)).count("1") for v in tm[:(n + 127) // 128]) * 128)
+        valid = int((rb.nbr[:, :n] >= 0).sum().item())
+    assert torch.equal(outs[0], outs[1])             # bit-identical: skipped taps only ever added exact zeros
+    assert pairs[1] < 0.6 * pairs[0] and pairs[1] < 1.6 * valid, (pairs, valid)
+    oconv = osp.SpConv3d(Ci, Co, 3, 1, 1, subm=True)
+    oconv.weight.data.copy_(wt)
+    with torch.no_grad():
+        ref = oconv(osp.SparseTensor(feat, idx, shape, B))
+    assert (outs[1] - _to_dense(ref.features, idx, n, shape, B)).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("n,bits", [(1, 27), (31, 3), (4096, 9), (4097, 18), (100000, 27), (300000, 27)])
+def test_radix_sort_pairs_matches_stable_sort(ops, n, bits):
+    """ff3d_sort_pairs == torch.sort(stable=True) on the low `bits` key bits, with a device-side count < capacity."""
+    import ctypes as C
+    from focalformer3d_b200.lib import lib, check
+    g = torch.Generator().manual_seed(n)
+    cap = n + 77
+    keys = torch.randint(0, 1 << bits, (cap,), generator=g, dtype=torch.int64)
+    if n > 1000:
+        keys[: n // 2] = keys[: n // 2] & 0x1C7                                   # heavy duplicates: stability matters
+    k32 = keys.to(torch.int32).cuda()
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    ws_bytes = lib.ff3d_sort_workspace_bytes(cap)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    ko = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
+    vo = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.ff3d_sort_pairs(C.c_void_p(k32.data_ptr()), None, C.c_void_p(n_dev.data_ptr()), cap, bits,
+                              C.c_void_p(ko.data_ptr()), C.c_void_p(vo.data_ptr()), C.c_void_p(ws.data_ptr()), ws_bytes, st),
+          "ff3d_sort_pairs")
+    ref_k, ref_v = torch.sort(keys[:n], stable=True)
+    assert torch.equal(ko[:n].cpu().long(), ref_k) and torch.equal(vo[:n].cpu().long(), ref_v)
+    assert bool((vo[n:] == -1).all())                                             # nothing written past the count
 
 
 def test_sparse_conv_many_tiles_256_row_path(ops):
@@ -233,30 +320,42 @@ def test_sparse_conv_many_tiles_256_row_path(ops):
     B, shape, n, Ci, Co = 2, (9, 90, 90), 42000, 32, 128
     idx, feat = _rand_level(B, shape, n, Ci, 21)
     n_dev = torch.tensor([n], dtype=torch.int32).cuda()
-    lvl = ops.SparseLevel(idx.cuda(), n_dev, n, B, shape)
-    lvl.build_hash()
     wt = torch.randn(3, 3, 3, Ci, Co, generator=torch.Generator().manual_seed(5)) / 12
     oconv = osp.SpConv3d(Ci, Co, 3, 1, 1, subm=True)
     oconv.weight.data.copy_(wt)
     with torch.no_grad():
         ref = oconv(osp.SparseTensor(feat, idx, shape, B))
-    out = torch.zeros((n, Co), device="cuda")
-    ops.sparse_conv(feat.cuda(), lvl.subm_map(), lvl.n_dev, pack_taps(wt.reshape(-1, Ci, Co), "cuda"), None, out, act=0)
-    assert (out.cpu() - ref.features).abs().max().item() < 1e-4
+    want = _to_dense(ref.features, idx, n, shape, B)
+    for sort_rows in (False, True):
+        lvl = ops.SparseLevel(idx.cuda(), n_dev, n, B, shape)
+        lvl.build_hash()
+        x = feat.cuda()
+        if sort_rows:
+            x = ops.gather_rows(x, lvl.sort_by_mask(), n_dev, Ci)
+        out = torch.zeros((n, Co), device="cuda")
+        ops.sparse_conv(x, lvl.subm_map(), lvl.n_dev, pack_taps(wt.reshape(-1, Ci, Co), "cuda"), None, out, act=0)
+        assert (_to_dense(out.cpu(), lvl.coors.cpu(), n, shape, B) - want).abs().max().item() < 1e-4
 
 
 def test_sparse_to_bev_scatter(ops):
-    B, shape, n, C = 2, (2, 6, 5), 40, 8
+    """conv_out's row map (y_mode 2 of ff3d_sp_nbr_build): NHWC BEV element offsets == SparseConvTensor.dense() + view."""
+    from focalformer3d_b200.model import pack_taps
+    B, shape, n, C = 2, (5, 6, 5), 60, 8
     idx, feat = _rand_level(B, shape, n, C, 4)
     n_dev = torch.tensor([n], dtype=torch.int32).cuda()
     lvl = ops.SparseLevel(idx.cuda(), n_dev, n, B, shape)
-    off = lvl.bev_offsets(shape[0] * C, C).cpu().long()
-    bev = torch.zeros(B * shape[1] * shape[2] * shape[0] * C)
-    for i in range(n):
-        bev[off[i]:off[i] + C] = feat[i]
-    bev = bev.view(B, shape[1], shape[2], shape[0], C)                            # [B,H,W,D,C]
-    dense = _to_dense(feat, idx, n, shape, B)                                     # [B,D,H,W,C]
-    assert torch.equal(bev.permute(0, 3, 1, 2, 4), dense)
+    lvl.build_hash()
+    overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+    D2 = (shape[0] - 3) // 2 + 1
+    bev = torch.zeros((B, shape[1], shape[2], D2 * C), device="cuda")
+    nl, rb = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), n, overflow, ldy=D2 * C, sort_level=False,
+                            bev=(shape[1], shape[2], C))
+    w = torch.zeros(3, 1, 1, C, C)
+    w[0, 0, 0] = torch.eye(C)                                      # out(o) = in(2*o_z) (tap 0 only): a pure scatter
+    ops.sparse_conv(feat.cuda(), rb, nl.n_dev, pack_taps(w.reshape(-1, C, C), "cuda"), None, bev, act=0, cout=C)
+    dense = _to_dense(feat, idx, n, shape, B)                      # [B,D,H,W,C]
+    want = dense[:, 0:2 * D2:2].permute(0, 2, 3, 1, 4).reshape(B, shape[1], shape[2], D2 * C)
+    assert torch.equal(bev.cpu(), want)
 
 
 def test_down_build_overflow_flag(ops):
@@ -265,7 +364,7 @@ def test_down_build_overflow_flag(ops):
     lvl = ops.SparseLevel(idx.cuda(), torch.tensor([n], dtype=torch.int32).cuda(), n, B, shape)
     lvl.build_hash()
     overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
-    nl, _ = lvl.downsample((3, 3, 3), (2, 2, 2), (1, 1, 1), 16, overflow)
+    nl, _ = lvl.downsample((3, 3, 3), (2, 2, 2), (1, 1, 1), 16, overflow, ldy=4)
     assert int(overflow.item()) == 1 and int(nl.n_dev.item()) == 16
 
 
