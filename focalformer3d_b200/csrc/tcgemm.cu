@@ -25,7 +25,18 @@
 // All shared-memory accesses use 32-bit shared-space addresses (LDS / STS / mbarrier on shared::cta), never generic
 // pointers.  Sparse mode stages the tile's whole neighbour map (taps x rows int32), conv mode one int4 of row geometry per
 // row, in shared memory up front, so the gather's dependent index load is off the per-stage critical path.
+//
+// Round 2:
+//  * F16 = true: fp16 hi/lo operand split instead of TF32 hi/lo:  a = hi + 2^-11 lo, hi = rn_f16(a), lo = rn_f16((a-hi) 2^11)
+//    (saturating; a device flag is raised beyond +-65504).  Same 22-bit products, but kind::f16 MMAs run at twice the TF32
+//    rate and a 128-byte shared-memory row covers 64 K-values instead of 32: half the tensor time AND half the
+//    shared-memory bytes per product (the TF32 kernel's limiter).  y = D_main + 2^-11 D_cross.
+//  * Sparse mode takes a per-128-row-tile tap mask (ff3d_sp_nbr_build): rows are mask-sorted by the rulebook builder, and
+//    all three warp roles walk only the taps (cin >= K-step) / multi-tap stages (cin < K-step) whose bit is set, so the
+//    (row, tap) pairs that exist in no row of the tile are neither gathered, split, copied nor multiplied.
+//  * Row offsets are 64-bit (row index * ld), the one-time kernel attribute setup is a thread-safe static initialiser.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace ff3d {
 
@@ -35,7 +46,7 @@ struct TcP {
   int cin, cout, taps;
   const float* x; int ldx;
   const float* x2;
-  const float* wimg;        // [n_tiles][n_stages][2][BN*32] pre-swizzled hi/lo images
+  const void* wimg;         // [n_tiles][n_stages][2][BN*128 bytes] pre-swizzled hi/lo images (tf32 words or fp16 halves)
   const float* bias;
   const float* res; int ldres;
   float* y; int ldy;
@@ -45,7 +56,10 @@ struct TcP {
   int ux, uy, dx, dy;
   const int* nbr; int nbr_stride;
   const int* y_off;
-  int n_stages, tps, cpt;   // pipeline K-steps; taps per stage (cin < 32); 32-channel chunks per tap (cin >= 32)
+  const uint32_t* tile_mask;   // SPARSE, optional: per 128-row tile the OR of its rows' tap masks
+  int* overflow;            // F16: device flag raised when an activation saturates the fp16 range
+  int n_stages, tps, cpt;   // pipeline K-steps; taps per stage (cin < KS); KS-channel chunks per tap (cin >= KS)
+  int n_units;              // skippable units of a tile: taps (cin >= KS) or multi-tap stages (cin < KS)
 };
 
 constexpr int TC_BM = 128;
@@ -88,6 +102,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
 __device__ __forceinline__ void sts128i(uint32_t addr, int4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t addr, int v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -117,15 +134,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major A and B,
 // N>>3 at [17,23), M>>4 at [24,29)
+// (A = B = F16: format code 0 instead of 2)
+template <bool F16>
 __device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  const uint32_t fmt = F16 ? 0u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if constexpr (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -160,6 +189,33 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = v - hi;
 }
 
+// fp16 hi/lo split of four fp32 values -> two packed half2 words each.  Saturating: beyond +-65504 the hi part clamps
+// (and the caller's overflow flag is raised); lo = (v - hi) * 2^11 cannot overflow unless hi already did.
+constexpr float F16_MAX = 65504.f;
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_f16x4(const float4& v, uint32_t& h01, uint32_t& h23, uint32_t& l01, uint32_t& l23,
+                                            bool& ovf) {
+  float c0 = fminf(fmaxf(v.x, -F16_MAX), F16_MAX), c1 = fminf(fmaxf(v.y, -F16_MAX), F16_MAX);
+  float c2 = fminf(fmaxf(v.z, -F16_MAX), F16_MAX), c3 = fminf(fmaxf(v.w, -F16_MAX), F16_MAX);
+  ovf = ovf || c0 != v.x || c1 != v.y || c2 != v.z || c3 != v.w;      // also true for NaN
+  __half2 ha = __floats2half2_rn(c0, c1), hb = __floats2half2_rn(c2, c3);
+  float2 fa = __half22float2(ha), fb = __half22float2(hb);
+  h01 = *reinterpret_cast<uint32_t*>(&ha);
+  h23 = *reinterpret_cast<uint32_t*>(&hb);
+  auto lo = [](float x, float h) { return fminf(fmaxf((x - h) * 2048.f, -F16_MAX), F16_MAX); };
+  l01 = pack_h2(lo(c0, fa.x), lo(c1, fa.y));
+  l23 = pack_h2(lo(c2, fb.x), lo(c3, fb.y));
+}
+
+// k-th (0-based) set bit of m
+__device__ __forceinline__ int nth_bit(uint32_t m, int k) {
+  for (int i = 0; i < k; ++i) m &= m - 1;
+  return __ffs(m) - 1;
+}
+
 struct Ring {
   int slot;
   uint32_t phase;
@@ -176,16 +232,20 @@ __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" 
 // BN = 128 (one CTA per SM).  n_slots == G makes every group the sole owner of one slot, so a producer is never more
 // than one mbarrier phase ahead of the MMA issuer (the parity wait cannot tell phases two apart).
 // MT = 128-row sub-tiles per CTA tile.  MT = 2 (BN = 128, large M) halves the weight bytes streamed from L2 per
-// flop -- with 3xTF32 the B images (hi + lo) are the larger half of the L2 -> SM traffic and these layers are
+// flop -- with the hi/lo split the B images are the larger half of the L2 -> SM traffic and these layers are
 // L2-bandwidth bound -- at the price of single-buffered accumulators (TMEM: 2 sub-tiles x (main|cross) x 128 = 512).
-template <int MODE, int BN, int G, int MT>
-__global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p, int n_slots) {
+// F16: fp16 hi/lo operand split (K-step 64) instead of TF32 hi/lo (K-step 32).
+template <int MODE, int BN, int G, int MT, bool F16>
+__global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kernel(const TcP p) {
   constexpr int NPROD = 128 * G;
   constexpr int TM = TC_BM * MT;                                 // rows per CTA tile
+  constexpr int KS = F16 ? 64 : 32;                              // K values per pipeline stage (one 128-byte smem row)
+  constexpr int UPS = F16 ? 2 * MT : MT;                         // gather units (8 x 16 bytes per thread) per stage
   constexpr bool DEFER = MT == 1;                                // double-buffered accumulators -> deferred epilogue
-  // one CTA per SM has registers to spare: keep the NEXT stage's gather in flight while this one is split and
+  // one CTA per SM has registers to spare: keep the NEXT unit's gather in flight while this one is split and
   // stored, so a producer group always has 16 KB outstanding (the gather is latency-, not bandwidth-bound)
   constexpr bool PREFETCH = (BN == 128);
+  constexpr int n_slots = G;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [slots][A_hi 16K | A_lo 16K | B_hi BN*128 | B_lo BN*128], barriers, TMEM pointer, per-tile aux
   constexpr uint32_t A_BYTES = TC_BM * 128;
@@ -200,7 +260,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   const uint32_t tfull_bar = empty_bar + 8u * n_slots;           // [2]
   const uint32_t tempty_bar = tfull_bar + 16u;                   // [2]
   const uint32_t tmem_ptr = tempty_bar + 16u;
-  // SPARSE: nbr element offsets [taps][TM]; CONV2D: int4 row info [128] (16-byte aligned)
+  // SPARSE: source ROW of (unit position | tap, tile row) [<= 27][TM]; CONV2D: int4 row info [TM] (16-byte aligned)
   const uint32_t aux_s = (tmem_ptr + 4u + 15u) & ~15u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,6 +269,27 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   const int n_tiles_n = p.cout / BN;
   const int total_tiles = ((Mv + TM - 1) / TM) * n_tiles_n;
   if ((int)blockIdx.x >= total_tiles) return;   // uniform for the whole CTA, before any barrier / TMEM use
+
+  // unit mask of a CTA tile (identical in all three warp roles): bit u = unit u (tap, or multi-tap stage when
+  // cin < KS) is used by at least one row of the tile.  No mask / other modes: every unit.
+  const bool masked = MODE == FF3D_GEMM_SPARSE && p.tile_mask != nullptr;
+  auto unit_mask = [&](int tile) -> uint32_t {
+    if (!masked) return 0u;                                      // callers use p.n_stages instead
+    const int mtile = (tile / n_tiles_n) * MT;
+    uint32_t tm = 0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      if ((mtile + mt) * TC_BM < Mv) tm |= __ldg(p.tile_mask + mtile + mt);
+    uint32_t um = tm;
+    if (p.tps > 1) {
+      um = 0;
+      const uint32_t grp_bits = (1u << p.tps) - 1u;
+      for (int u = 0; u < p.n_units; ++u)
+        if ((tm >> (u * p.tps)) & grp_bits) um |= 1u << u;
+    }
+    return um ? um : 1u;                                         // never an empty tile: unit 0 then gathers zeros
+  };
+  auto stage_count = [&](uint32_t um) -> int { return masked ? __popc(um) * p.cpt : p.n_stages; };
 
   if (tid == 0) {
     for (int s = 0; s < n_slots; ++s) { mbar_init(full_bar + 8u * s, TC_BM + 1); mbar_init(empty_bar + 8u * s, 1); }
@@ -224,23 +305,28 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = (uint32_t)lds32(tmem_ptr);
-  const int n_stages = p.n_stages;
 
   if (warp < 4 * G) {
     // =========================== A producers (+ deferred epilogue) ===========================
-    // 8 consecutive lanes read the 8 16-byte chunks of ONE row (a full 128-byte line per quarter-warp request),
-    // 4 rows per warp instruction, 8 instructions per stage.
+    // 8 consecutive lanes read the 8 16-byte chunks of ONE 128-byte line (a full line per quarter-warp request)
     const int grp = warp >> 2;
     const int pw = warp & 3;
     const int j = lane & 7;
     const int q = lane >> 3;
     const int ptid = tid;                                     // producers are threads [0, NPROD)
+    // TF32 small-cin lane geometry: cin = 16 -> 2 taps per 32-wide stage, cin = 8 -> 4 taps
     const int qshift = p.cin == 16 ? 2 : 1;
     const int lane_tap = p.cin >= 32 ? 0 : (j >> qshift);
     const int lane_coff = p.cin >= 32 ? j * 4 : (j & ((1 << qshift) - 1)) * 4;
+    // F16: rows of one warp instruction are base + {0, 4, 1, 5}[q]: the two rows of a half-warp differ in bit 2 of
+    // (row & 7), so their 8-byte stores land in different swizzle halves of the 128-byte line (no bank conflict)
+    const int rq = (q & 1) * 4 + (q >> 1);
+    bool ovf = false;
     const int r = tid & 127;                                  // epilogue: thread <-> tile row (TMEM lane)
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    Ring ring{grp % n_slots, (uint32_t)((grp / n_slots) & 1)};
+    const int slot = grp;                                     // n_slots == G: group g owns slot g
+    uint32_t phase = 0u;
+    int gbase = 0;                                            // (stages issued by this CTA so far) mod G
 
     auto epilogue = [&](int tile, int it) {
       const int m0 = (tile / n_tiles_n) * TM;
@@ -300,7 +386,8 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         if (rvalid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a = v[i] + v2[i];
+            // F16: the cross terms carry the 2^11 scale of the lo parts
+            float a = F16 ? fmaf(v2[i], 1.f / 2048.f, v[i]) : v[i] + v2[i];
             if (p.bias) a += bs[i];
             if (p.res_after_act) a = apply_act(a, p.act);
             if (p.res) a += rs[i];
@@ -324,13 +411,25 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
     int it = 0, prev_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_tiles_n) * TM;
+      const uint32_t um = unit_mask(tile);
+      const int nst = stage_count(um);
       // ---- per-tile gather metadata (both groups are past the previous tile's stages after the first barrier)
       producer_bar<NPROD>();
       if (MODE == FF3D_GEMM_SPARSE) {
-        for (int i = ptid; i < p.taps * TM; i += NPROD) {
-          int t = i / TM, rr = i - t * TM;
-          int v = (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1;
-          sts32(aux_s + 4u * i, v < 0 ? -1 : v * p.ldx);    // element offset of the source row
+        if (masked && p.tps == 1) {
+          // one staged row list per PRESENT tap, indexed by its position in the tile's unit list
+          int li = 0;
+          for (uint32_t mm = um; mm; mm &= mm - 1u, ++li) {
+            const int t = __ffs(mm) - 1;
+            for (int rr = ptid; rr < TM; rr += NPROD)
+              sts32(aux_s + 4u * (uint32_t)(li * TM + rr),
+                    (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1);
+          }
+        } else {
+          for (int i = ptid; i < p.taps * TM; i += NPROD) {
+            int t = i / TM, rr = i - t * TM;
+            sts32(aux_s + 4u * i, (m0 + rr < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m0 + rr) : -1);
+          }
         }
       } else if (MODE == FF3D_GEMM_CONV2D) {
         for (int rr0 = ptid; rr0 < TM; rr0 += NPROD) {
@@ -347,96 +446,146 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
         }
       }
       producer_bar<NPROD>();
-      // my stages of this tile: global stage index (it * n_stages + s) has my parity
-      int s = (grp - it * n_stages) % G;                      // first stage of this tile with (it*n_stages + s) % G == grp
+      // my stages of this tile: local stage s has global index gbase + s (mod G), mine are those == grp
+      int s = (grp - gbase) % G;
       if (s < 0) s += G;
-      int t, cidx;                                           // tap and 32-channel chunk of stage s (cin >= 32)
+      gbase = (gbase + nst) % G;
+      int t, cidx;                                           // unit position and KS-channel chunk of stage s (cin >= KS)
       t = s / p.cpt; cidx = s - t * p.cpt;
-      int umt = 0;                                           // 128-row sub-tile of the gather cursor (s, t, cidx, umt)
-      // one gather unit = 8 x 16 bytes per thread = the 32 K-values of 128 rows (one sub-tile of one stage)
-      auto gather = [&](float4* v) {
-        int tap, coff, ky = 0, kx = 0;
-        if (p.cin >= 32) { tap = t; coff = cidx * 32 + lane_coff; }
-        else { tap = s * p.tps + lane_tap; coff = lane_coff; }
-        if (MODE == FF3D_GEMM_CONV2D) { ky = tap / p.kw; kx = tap - ky * p.kw; }
-        const bool tap_ok = tap < p.taps;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = umt * TC_BM + pw * 32 + i * 4 + q;
-          long long so = -1;                                 // element offset of the source row feeding (row, tap)
-          if (MODE == FF3D_GEMM_ROWS) {
-            if (tap_ok && m0 + row < Mv) so = (long long)(m0 + row) * p.ldx;
-          } else if (MODE == FF3D_GEMM_CONV2D) {
-            // staged per-tile row info (batch pixel base, top-left input y, x); rows past M hold y = x = -32768
-            const int4 info = lds128i(aux_s + 16u * (uint32_t)row);
-            const int iy = info.y + ky, ix = info.z + kx;
-            if (tap_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
-              so = ((long long)info.x + (long long)(iy * p.W + ix)) * p.ldx;
-          } else {
-            if (tap_ok) so = (long long)lds32(aux_s + 4u * (uint32_t)(tap * TM + row));
+      int uu = 0;                                            // gather unit inside stage s
+      // source ROW feeding (tile row, tap) -- or -1
+      auto src_row = [&](int row, int tap_or_pos, int tap, bool tap_ok) -> long long {
+        if (MODE == FF3D_GEMM_ROWS) return (tap_ok && m0 + row < Mv) ? (long long)(m0 + row) : -1;
+        if (MODE == FF3D_GEMM_CONV2D) {
+          // staged per-tile row info (batch pixel base, top-left input y, x); rows past M hold y = x = -32768
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          const int4 info = lds128i(aux_s + 16u * (uint32_t)row);
+          const int iy = info.y + ky, ix = info.z + kx;
+          if (tap_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
+            return (long long)info.x + (long long)(iy * p.W + ix);
+          return -1;
+        }
+        return tap_ok ? (long long)lds32(aux_s + 4u * (uint32_t)(tap_or_pos * TM + row)) : -1;
+      };
+      auto load4 = [&](long long so, int coff) -> float4 {
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (so >= 0) {
+          const long long e = so * p.ldx + coff;
+          val = __ldg(reinterpret_cast<const float4*>(p.x + e));
+          if (MODE == FF3D_GEMM_ROWS && p.x2) {
+            float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + e));
+            val.x += u.x; val.y += u.y; val.z += u.z; val.w += u.w;
           }
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (so >= 0) {
-            v[i] = __ldg(reinterpret_cast<const float4*>(p.x + so + coff));
-            if (MODE == FF3D_GEMM_ROWS && p.x2) {
-              float4 u = __ldg(reinterpret_cast<const float4*>(p.x2 + so + coff));
-              v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
-            }
+        }
+        return val;
+      };
+      // one gather unit = 8 x 16 bytes per thread.  TF32: the 32 K-values of 128 rows (8 rows per thread);
+      // F16: half of the 64 K-values x 128 rows (4 rows x the two 128-byte lines of the row's K-step)
+      auto gather = [&](float4* v) {
+        if constexpr (!F16) {
+          int tap, pos, coff;
+          if (p.cin >= KS) { pos = t; tap = t; coff = cidx * KS + lane_coff; }
+          else {
+            const int uid = masked ? nth_bit(um, s) : s;
+            tap = uid * p.tps + lane_tap; pos = tap; coff = lane_coff;
+          }
+          const bool tap_ok = tap < p.taps;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = uu * TC_BM + pw * 32 + i * 4 + q;
+            v[i] = load4(src_row(row, pos, tap, tap_ok), coff);
+          }
+        } else {
+          const int mt = uu >> 1, hf = uu & 1;
+          int tapL[2], posL[2], coffL[2];
+          const int uid = (p.cin >= KS) ? 0 : (masked ? nth_bit(um, s) : s);
+#pragma unroll
+          for (int L = 0; L < 2; ++L) {
+            const int k0 = L * 32 + 4 * j;                     // K index of my 4 values inside the 64-wide stage
+            if (p.cin >= KS) { tapL[L] = t; posL[L] = t; coffL[L] = cidx * KS + k0; }
+            else { tapL[L] = uid * p.tps + k0 / p.cin; posL[L] = tapL[L]; coffL[L] = k0 % p.cin; }
+          }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int i = hf * 4 + ii;
+            const int row = mt * TC_BM + pw * 32 + (i >> 1) * 8 + (i & 1) * 2 + rq;
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+              v[ii * 2 + L] = load4(src_row(row, posL[L], tapL[L], tapL[L] < p.taps), coffL[L]);
           }
         }
       };
       auto advance_cursor = [&]() {
-        if (++umt < MT) return;
-        umt = 0;
+        if (++uu < UPS) return;
+        uu = 0;
         s += G;
-        if (p.cin >= 32) { cidx += G; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
+        if (p.cin >= KS) { cidx += G; while (cidx >= p.cpt) { cidx -= p.cpt; ++t; } }
       };
-      // split one gathered unit into the hi / lo TF32 images of this group's smem slot; the last sub-tile of a stage
-      // hands the slot to the MMA issuer
-      auto commit_unit = [&](const float4* v, int mt) {
-        if (mt == 0) mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
-        const uint32_t a_hi = smem + (uint32_t)ring.slot * SLOT_BYTES + (uint32_t)mt * (2 * A_BYTES);
+      // split one gathered unit into the hi / lo images of this group's smem slot; the last unit of a stage hands the
+      // slot to the MMA issuer
+      auto commit_unit = [&](const float4* v, int u) {
+        if (u == 0) mbar_wait(empty_bar + 8u * slot, phase ^ 1u);
+        const int mt = F16 ? (u >> 1) : u;
+        const uint32_t a_hi = smem + (uint32_t)slot * SLOT_BYTES + (uint32_t)mt * (2 * A_BYTES);
         const uint32_t a_lo = a_hi + A_BYTES;
+        if constexpr (!F16) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 h, l;
-          split_tf32(v[i].x, h.x, l.x);
-          split_tf32(v[i].y, h.y, l.y);
-          split_tf32(v[i].z, h.z, l.z);
-          split_tf32(v[i].w, h.w, l.w);
-          const uint32_t o = swz(pw * 32 + i * 4 + q, j);
-          sts128(a_hi + o, h);
-          sts128(a_lo + o, l);
+          for (int i = 0; i < 8; ++i) {
+            float4 h, l;
+            split_tf32(v[i].x, h.x, l.x);
+            split_tf32(v[i].y, h.y, l.y);
+            split_tf32(v[i].z, h.z, l.z);
+            split_tf32(v[i].w, h.w, l.w);
+            const uint32_t o = swz(pw * 32 + i * 4 + q, j);
+            sts128(a_hi + o, h);
+            sts128(a_lo + o, l);
+          }
+        } else {
+          const int hf = u & 1;
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int i = hf * 4 + ii;
+            const int row = pw * 32 + (i >> 1) * 8 + (i & 1) * 2 + rq;
+#pragma unroll
+            for (int L = 0; L < 2; ++L) {
+              uint32_t h01, h23, l01, l23;
+              split_f16x4(v[ii * 2 + L], h01, h23, l01, l23, ovf);
+              // K 32L + 4j .. +3 -> halves [32L + 4j, +4) of the row = 16-byte chunk 4L + j/2, 8-byte half (j & 1)
+              const uint32_t o = (uint32_t)(row * 128 + ((((L * 4 + (j >> 1)) ^ (row & 7)) << 4) | ((j & 1) << 3)));
+              sts64(a_hi + o, h01, h23);
+              sts64(a_lo + o, l01, l23);
+            }
+          }
         }
-        if (mt == MT - 1) {
+        if (u == UPS - 1) {
           fence_proxy_async();
-          mbar_arrive(full_bar + 8u * ring.slot);
-          ring.advance(G, n_slots);
+          mbar_arrive(full_bar + 8u * slot);
+          phase ^= 1u;
         }
       };
       if (PREFETCH) {
         // two register sets in ping-pong: the loads of the next unit are in flight while this one is split and stored
         // (no register moves between the sets -- a move would wait for the very loads it is supposed to overlap)
         float4 va[8], vb[8];
-        int mta = 0, mtb = 0;
-        bool have = s < n_stages;
-        if (have) { gather(va); mta = umt; advance_cursor(); }
+        int ua = 0, ub = 0;
+        bool have = s < nst;
+        if (have) { gather(va); ua = uu; advance_cursor(); }
         while (have) {
-          bool more = s < n_stages;
-          if (more) { gather(vb); mtb = umt; advance_cursor(); }
-          commit_unit(va, mta);
+          bool more = s < nst;
+          if (more) { gather(vb); ub = uu; advance_cursor(); }
+          commit_unit(va, ua);
           if (!more) break;
-          have = s < n_stages;
-          if (have) { gather(va); mta = umt; advance_cursor(); }
-          commit_unit(vb, mtb);
+          have = s < nst;
+          if (have) { gather(va); ua = uu; advance_cursor(); }
+          commit_unit(vb, ub);
         }
       } else {
         float4 v[8];
-        while (s < n_stages) {
+        while (s < nst) {
           gather(v);
-          const int mt = umt;
+          const int u = uu;
           advance_cursor();
-          commit_unit(v, mt);
+          commit_unit(v, u);
         }
       }
       // epilogue of the PREVIOUS tile: its MMAs have had a whole tile's worth of gathers to finish, and the
@@ -449,19 +598,30 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       }
     }
     if (DEFER && prev_tile >= 0) epilogue(prev_tile, it - 1);
+    if (F16 && ovf && p.overflow) atomicOr(p.overflow, 1);
   } else if (warp == 4 * G) {
     // =========================== B producer ===========================
     if (lane == 0) {
       Ring ring{0, 0u};
+      const uint8_t* wbase = static_cast<const uint8_t*>(p.wimg);
+      const size_t stage_bytes = 2 * (size_t)B_BYTES;
+      auto copy_stage = [&](const uint8_t* wsrc, int img) {
+        mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
+        const uint32_t b_hi = smem + (uint32_t)ring.slot * SLOT_BYTES + MT * 2 * A_BYTES;
+        mbar_arrive_expect_tx(full_bar + 8u * ring.slot, 2 * B_BYTES);
+        bulk_g2s(b_hi, wsrc + (size_t)img * stage_bytes, 2 * B_BYTES, full_bar + 8u * ring.slot);
+        ring.advance(1, n_slots);
+      };
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ntile = tile - (tile / n_tiles_n) * n_tiles_n;
-        const float* wsrc = p.wimg + (size_t)ntile * n_stages * (2 * BN * 32);
-        for (int s = 0; s < n_stages; ++s) {
-          mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
-          const uint32_t b_hi = smem + (uint32_t)ring.slot * SLOT_BYTES + MT * 2 * A_BYTES;
-          mbar_arrive_expect_tx(full_bar + 8u * ring.slot, 2 * B_BYTES);
-          bulk_g2s(b_hi, wsrc + (size_t)s * (2 * BN * 32), 2 * B_BYTES, full_bar + 8u * ring.slot);
-          ring.advance(1, n_slots);
+        const uint8_t* wsrc = wbase + (size_t)ntile * p.n_stages * stage_bytes;
+        if (masked) {
+          for (uint32_t mm = unit_mask(tile); mm; mm &= mm - 1u) {
+            const int uid = __ffs(mm) - 1;
+            for (int c = 0; c < p.cpt; ++c) copy_stage(wsrc, uid * p.cpt + c);
+          }
+        } else {
+          for (int s = 0; s < p.n_stages; ++s) copy_stage(wsrc, s);
         }
       }
     }
@@ -471,23 +631,24 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       // [main | cross] accumulators are adjacent TMEM columns and [B_hi | B_lo] adjacent smem tiles, so
       // A_hi x [B_hi | B_lo] is ONE N = 2*BN MMA; A_lo x B_hi (N = BN) completes the cross term: 2 MMAs and
       // 2 reads of the A tiles per K step instead of 3 (the kernel is shared-memory-bandwidth bound)
-      const uint32_t idesc_wide = make_idesc(2 * BN), idesc_cross = make_idesc(BN);
+      const uint32_t idesc_wide = make_idesc<F16>(2 * BN), idesc_cross = make_idesc<F16>(BN);
       Ring ring{0, 0u};
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int ab = DEFER ? (it & 1) : 0;
+        const int nst = stage_count(unit_mask(tile));
         // the epilogue that last read this accumulator buffer (tile it-2, or it-1 when single-buffered) has drained it
         mbar_wait(tempty_bar + 8u * ab, (uint32_t)((DEFER ? ((it >> 1) & 1) : (it & 1)) ^ 1));
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(ab * ACC_COLS);
-        for (int s = 0; s < n_stages; ++s) {
+        for (int s = 0; s < nst; ++s) {
           mbar_wait(full_bar + 8u * ring.slot, ring.phase);
           tc_fence_after();
           const uint32_t slot_a = smem + (uint32_t)ring.slot * SLOT_BYTES;
           const uint32_t b_hi = slot_a + MT * 2 * A_BYTES;
           static_assert(B_BYTES % 1024 == 0, "B_lo must continue B_hi's 8-row swizzle atoms");
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzled row
+          for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 | 16 halves = 32 bytes) per 128-byte swizzled row
             const uint64_t dbh = make_desc(b_hi + k * 32);   // as an N = 2*BN operand it runs on into B_lo
             const uint32_t acc = (s | k) ? 1u : 0u;
 #pragma unroll
@@ -495,8 +656,8 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
               const uint32_t a_hi = slot_a + mt * 2 * A_BYTES, a_lo = a_hi + A_BYTES;
               const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
               const uint32_t d_main = d_base + (uint32_t)(mt * 2 * BN), d_cross = d_main + BN;
-              umma_tf32(d_main, dah, dbh, idesc_wide, acc);    // main += A_hi*B_hi ; cross += A_hi*B_lo
-              umma_tf32(d_cross, dal, dbh, idesc_cross, 1u);   // cross += A_lo*B_hi
+              umma<F16>(d_main, dah, dbh, idesc_wide, acc);    // main += A_hi*B_hi ; cross += A_hi*B_lo
+              umma<F16>(d_cross, dal, dbh, idesc_cross, 1u);   // cross += A_lo*B_hi
             }
           }
           umma_commit(empty_bar + 8u * ring.slot);   // frees the smem slot once these MMAs have read it
@@ -514,81 +675,74 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
   }
 }
 
-template <int MODE, int BN, int G, int MT>
+template <int MODE, int BN, int G, int MT, bool F16>
 static int launch_tc_cfg(const TcP& p, int n_tiles_n, cudaStream_t st) {
   constexpr size_t SLOT_BYTES = (size_t)MT * 2 * TC_BM * 128 + 2 * (size_t)BN * 128;
   constexpr int TM = TC_BM * MT;
-  const int n_slots = G;                                // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
+  constexpr int n_slots = G;                            // BN <= 64: <= 112 KB per CTA so two CTAs share an SM
   size_t smem = (size_t)n_slots * SLOT_BYTES + (2 * n_slots + 4) * sizeof(uint64_t) + 32 +
                 (MODE == FF3D_GEMM_SPARSE ? (size_t)TC_MAX_TAPS * TM * sizeof(int)
                                           : (MODE == FF3D_GEMM_CONV2D ? (size_t)TM * 16 : 0)) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(tcgemm_kernel<MODE, BN, G, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
+  // one-time opt-in to > 48 KB of dynamic shared memory: a function-local static initialiser is thread-safe (C++11)
+  static const cudaError_t attr = cudaFuncSetAttribute(tcgemm_kernel<MODE, BN, G, MT, F16>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (attr != cudaSuccess) {
+    set_error("ff3d_tcgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr));
+    return FF3D_ECUDA;
   }
   // persistent CTAs: one (BN = 128) or two (BN <= 64) per SM, each looping over output tiles
   long long tiles = (long long)cdiv(p.M, TM) * n_tiles_n;
   long long resident = (long long)num_sms() * (BN <= 64 ? 2 : 1);
   dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-  tcgemm_kernel<MODE, BN, G, MT><<<grid, 128 * G + 64, smem, st>>>(p, n_slots);
+  tcgemm_kernel<MODE, BN, G, MT, F16><<<grid, 128 * G + 64, smem, st>>>(p);
   return check_launch("ff3d_tcgemm");
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool F16>
 static int launch_tc(const TcP& p, int n_tiles_n, cudaStream_t st) {
   if constexpr (BN == 128) {
     // enough 256-row tiles to fill the machine -> share each weight stage between two row sub-tiles
     // (only the sparse gather profits: dense layers lose more from the single-buffered accumulators, measured)
     if constexpr (MODE == FF3D_GEMM_SPARSE) {
-      if ((long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms()) return launch_tc_cfg<MODE, BN, 2, 2>(p, n_tiles_n, st);
+      if ((long long)cdiv(p.M, 2 * TC_BM) * n_tiles_n >= num_sms()) return launch_tc_cfg<MODE, BN, 2, 2, F16>(p, n_tiles_n, st);
     }
-    return launch_tc_cfg<MODE, BN, 3, 1>(p, n_tiles_n, st);
+    return launch_tc_cfg<MODE, BN, 3, 1, F16>(p, n_tiles_n, st);
   } else {
-    return launch_tc_cfg<MODE, BN, 2, 1>(p, n_tiles_n, st);
+    return launch_tc_cfg<MODE, BN, 2, 1, F16>(p, n_tiles_n, st);
   }
 }
 
-template <int MODE>
+template <int MODE, bool F16>
 static int launch_tc_mode(const TcP& p, int bn, int n_tiles_n, cudaStream_t st) {
   switch (bn) {
-    case 16: return launch_tc<MODE, 16>(p, n_tiles_n, st);
-    case 32: return launch_tc<MODE, 32>(p, n_tiles_n, st);
-    case 64: return launch_tc<MODE, 64>(p, n_tiles_n, st);
-    case 128: return launch_tc<MODE, 128>(p, n_tiles_n, st);
+    case 16: return launch_tc<MODE, 16, F16>(p, n_tiles_n, st);
+    case 32: return launch_tc<MODE, 32, F16>(p, n_tiles_n, st);
+    case 64: return launch_tc<MODE, 64, F16>(p, n_tiles_n, st);
+    case 128: return launch_tc<MODE, 128, F16>(p, n_tiles_n, st);
   }
   set_error("ff3d_tcgemm: unsupported N tile %d", bn);
   return FF3D_EINVAL;
 }
 
-}  // namespace ff3d
-
-// N tile used for a given cout (0 = shape not supported by the tensor-core path)
-extern "C" int ff3d_tcgemm_ntile(int cin, int cout) {
-  if (!(cin == 8 || cin == 16 || (cin >= 32 && cin % 32 == 0))) return 0;
+static int ntile_for(int cin, int cout, int ks) {
+  const bool cin_ok = (cin >= ks) ? (cin % ks == 0) : (cin >= 8 && (ks % cin) == 0 && (cin & (cin - 1)) == 0);
+  if (!cin_ok) return 0;
   if (cout % 128 == 0) return 128;
   if (cout == 64 || cout == 32 || cout == 16) return cout;
   return 0;
 }
-extern "C" int ff3d_tcgemm_stages(int cin, int taps) {
-  if (cin >= 32) return taps * (cin / 32);
-  int tps = 32 / cin;
+static int stages_for(int cin, int taps, int ks) {
+  if (cin >= ks) return taps * (cin / ks);
+  int tps = ks / cin;
   return (taps + tps - 1) / tps;
 }
 
-extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn, ff3d_stream_t stream);
-
-extern "C" int ff3d_tcgemm(const ff3d_gemm_desc* d, const float* wimg, ff3d_stream_t stream) {
-  return ff3d_tcgemm_bn(d, wimg, 0, stream);
-}
-
-// bn = N tile the weight images were packed for (0 = ff3d_tcgemm_ntile's default).  A smaller tile than the default
-// (e.g. 64 for cout = 512) gives small-M / huge-K layers enough CTAs to fill the machine.
-extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn, ff3d_stream_t stream) {
-  using namespace ff3d;
+template <bool F16>
+static int tcgemm_run(const ff3d_gemm_desc* d, const void* wimg, int bn, int* overflow_dev, ff3d_stream_t stream) {
+  constexpr int KS = F16 ? 64 : 32;
   FF3D_REQUIRE(d != nullptr && wimg != nullptr, "ff3d_tcgemm: null argument");
-  if (bn == 0) bn = ff3d_tcgemm_ntile(d->cin, d->cout);
-  FF3D_REQUIRE(bn > 0 && ff3d_tcgemm_ntile(d->cin, d->cout) > 0 && d->cout % bn == 0 &&
+  if (bn == 0) bn = ntile_for(d->cin, d->cout, KS);
+  FF3D_REQUIRE(bn > 0 && ntile_for(d->cin, d->cout, KS) > 0 && d->cout % bn == 0 &&
                    (bn == 16 || bn == 32 || bn == 64 || bn == 128),
                "ff3d_tcgemm: shape cin=%d cout=%d (N tile %d) is not tensor-core tileable", d->cin, d->cout, bn);
   FF3D_REQUIRE(d->ldx % 4 == 0 && d->x && d->y && d->taps > 0, "ff3d_tcgemm: bad operands");
@@ -606,13 +760,17 @@ extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn
   p.ux = d->ux > 0 ? d->ux : 1; p.uy = d->uy > 0 ? d->uy : 1; p.dx = d->dx; p.dy = d->dy;
   p.x_bstride = d->x_bstride; p.y_bstride = d->y_bstride; p.y_row0 = d->y_row0;
   p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.y_off = d->y_off;
-  p.n_stages = ff3d_tcgemm_stages(d->cin, d->taps);
-  p.tps = d->cin >= 32 ? 1 : 32 / d->cin;
-  p.cpt = d->cin >= 32 ? d->cin / 32 : 1;
+  p.tile_mask = d->mode == FF3D_GEMM_SPARSE ? d->tile_mask : nullptr;
+  p.overflow = overflow_dev;
+  p.n_stages = stages_for(d->cin, d->taps, KS);
+  p.tps = d->cin >= KS ? 1 : KS / d->cin;
+  p.cpt = d->cin >= KS ? d->cin / KS : 1;
+  p.n_units = d->cin >= KS ? d->taps : p.n_stages;
   if (d->mode == FF3D_GEMM_CONV2D) {
     FF3D_REQUIRE(d->taps == d->kh * d->kw && (long long)d->B * d->Ho * d->Wo == d->M, "ff3d_tcgemm: bad conv geometry");
     if (p.x_bstride == 0) p.x_bstride = (long long)d->H * d->W;
     if (p.y_bstride == 0) p.y_bstride = (long long)d->Ho * p.uy * d->Wo * p.ux;
+    FF3D_REQUIRE((long long)d->B * p.x_bstride < 0x7FFFFFFFLL, "ff3d_tcgemm: conv input has more than 2^31 pixels");
   } else if (d->mode == FF3D_GEMM_SPARSE) {
     FF3D_REQUIRE(d->nbr != nullptr && d->nbr_stride >= d->M && d->taps <= TC_MAX_TAPS,
                  "ff3d_tcgemm: sparse mode needs nbr [taps <= 27, >=M]");
@@ -621,7 +779,31 @@ extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn
   }
   int n_tiles_n = d->cout / bn;
   cudaStream_t st = as_stream(stream);
-  if (d->mode == FF3D_GEMM_ROWS) return launch_tc_mode<FF3D_GEMM_ROWS>(p, bn, n_tiles_n, st);
-  if (d->mode == FF3D_GEMM_CONV2D) return launch_tc_mode<FF3D_GEMM_CONV2D>(p, bn, n_tiles_n, st);
-  return launch_tc_mode<FF3D_GEMM_SPARSE>(p, bn, n_tiles_n, st);
+  if (d->mode == FF3D_GEMM_ROWS) return launch_tc_mode<FF3D_GEMM_ROWS, F16>(p, bn, n_tiles_n, st);
+  if (d->mode == FF3D_GEMM_CONV2D) return launch_tc_mode<FF3D_GEMM_CONV2D, F16>(p, bn, n_tiles_n, st);
+  return launch_tc_mode<FF3D_GEMM_SPARSE, F16>(p, bn, n_tiles_n, st);
+}
+
+}  // namespace ff3d
+
+// N tile used for a given cout (0 = shape not supported by the tensor-core path)
+extern "C" int ff3d_tcgemm_ntile(int cin, int cout) { return ff3d::ntile_for(cin, cout, 32); }
+extern "C" int ff3d_tcgemm_stages(int cin, int taps) { return ff3d::stages_for(cin, taps, 32); }
+extern "C" int ff3d_tcgemm_f16_ntile(int cin, int cout) { return ff3d::ntile_for(cin, cout, 64); }
+extern "C" int ff3d_tcgemm_f16_stages(int cin, int taps) { return ff3d::stages_for(cin, taps, 64); }
+
+extern "C" int ff3d_tcgemm(const ff3d_gemm_desc* d, const float* wimg, ff3d_stream_t stream) {
+  return ff3d::tcgemm_run<false>(d, wimg, 0, nullptr, stream);
+}
+
+// bn = N tile the weight images were packed for (0 = ff3d_tcgemm_ntile's default).  A smaller tile than the default
+// (e.g. 64 for cout = 512) gives small-M / huge-K layers enough CTAs to fill the machine.
+extern "C" int ff3d_tcgemm_bn(const ff3d_gemm_desc* d, const float* wimg, int bn, ff3d_stream_t stream) {
+  return ff3d::tcgemm_run<false>(d, wimg, bn, nullptr, stream);
+}
+
+// fp16 hi/lo split variant (kind::f16): wimg16 = [cout/ntile][ff3d_tcgemm_f16_stages][2][ntile*64] halves (hi | lo*2^11);
+// overflow_dev (may be NULL) is OR-ed with 1 when an activation left the fp16 range (the result is then invalid)
+extern "C" int ff3d_tcgemm_f16(const ff3d_gemm_desc* d, const void* wimg16, int bn, int* overflow_dev, ff3d_stream_t stream) {
+  return ff3d::tcgemm_run<true>(d, wimg16, bn, overflow_dev, stream);
 }

@@ -59,6 +59,9 @@ SIGNATURES = {
     "ff3d_igemm": (_I, [C.POINTER(GemmDesc), _P]),
     "ff3d_tcgemm": (_I, [C.POINTER(GemmDesc), _P, _P]),
     "ff3d_tcgemm_bn": (_I, [C.POINTER(GemmDesc), _P, _I, _P]),
+    "ff3d_tcgemm_f16": (_I, [C.POINTER(GemmDesc), _P, _I, _P, _P]),
+    "ff3d_tcgemm_f16_ntile": (_I, [_I, _I]),
+    "ff3d_tcgemm_f16_stages": (_I, [_I, _I]),
     "ff3d_tcgemm_ntile": (_I, [_I, _I]),
     "ff3d_tcgemm_stages": (_I, [_I, _I]),
     "ff3d_dwconv3x3": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

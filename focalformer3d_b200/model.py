@@ -1070,6 +1070,7 @@ class FocalFormer3D(nn.Module):
         img_metas: list[B] of dict(lidar2img=[N, 4, 4]).  focalformer3d.py:133-153,186 + focal_encoder.py:171-197."""
         dev = self._prepared_on
         B, N, Cc, H, W = img.shape
+        ops.gemm_flag(dev).zero_()
         ops.mark("start")
         x = ops.nchw_to_nhwc(img.to(dev, torch.float32).reshape(B * N, Cc, H, W).contiguous(), 8)
         feats = self.img_backbone(x)
@@ -1119,6 +1120,7 @@ class FocalFormer3D(nn.Module):
         # focalformer3d.py:80,159-163: a 'Dynamic*' voxel encoder switches to dynamic voxelisation (no caps)
         dynamic = isinstance(self.pts_voxel_encoder, DynamicSimpleVFE)
         mv = n_max if (dynamic or mv <= 0) else min(mv, n_max)
+        ops.gemm_flag(dev).zero_()
         ops.mark("start")
         hard_vfe = isinstance(self.pts_voxel_encoder, HardVFE)
         vox = ops.voxelize(allp, offs, vc["voxel_size"], vc["point_cloud_range"], -1 if dynamic else vc["max_num_points"], mv,
@@ -1166,11 +1168,20 @@ class FocalFormer3D(nn.Module):
                           extra=extra, ms_value=ms_value, overflow=overflow, level_sizes=me.level_sizes, cam=cam)
         return res, det, stages
 
+    def check_flags(self):
+        """Device-side failure flags of the last forward_raw (one small D2H copy): sparse-level capacity overflow and
+        fp16-range saturation of a GEMM operand.  Either one invalidates the result: fail loudly."""
+        flags = torch.cat([self._overflow.view(-1)[:1], ops.gemm_flag(self._prepared_on).view(-1)]).cpu().tolist()
+        if flags[0]:
+            raise RuntimeError("sparse encoder level capacity exceeded; raise SparseEncoder.cap_growth")
+        if flags[1]:
+            raise RuntimeError("an activation left the fp16 range (|a| > 65504) in the fp16 hi/lo GEMM: the result is "
+                               "invalid; rerun with FF3D_GEMM=tf32 (TF32 hi/lo operand split, no range limit)")
+
     def simple_test(self, points, img_metas=None, img=None, rescale=False):
         """Reference signature (focalformer3d.py:321): list of dict(pts_bbox=dict(boxes_3d, scores_3d, labels_3d)) on CPU."""
         _, (boxes, scores, labels, keep), _ = self.forward_raw(points, img=img, img_metas=img_metas)
-        if int(self._overflow.item()):
-            raise RuntimeError("sparse encoder level capacity exceeded; raise SparseEncoder.cap_growth")
+        self.check_flags()
         out = []
         for b in range(boxes.shape[0]):
             m = keep[b].bool()

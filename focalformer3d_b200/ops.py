@@ -118,12 +118,97 @@ def tc_weight_images(w, bn=None):
     return imgs.contiguous(), bn
 
 
-class PackedW:
-    """Device weights of one GEMM-like layer: ``w`` [taps, cin, ldw] (SIMT kernel) and ``img`` (tcgen05 kernel)."""
+LO_SCALE = 2048.0          # fp16 split: w = hi + lo / 2048
 
-    def __init__(self, w_cpu, dev, bn=None):
+
+def split_f16(t):
+    """fp32 tensor -> (hi, lo) fp16 tensors with t ~= hi + lo / 2048 (saturating at the fp16 range)."""
+    hi = t.clamp(-65504.0, 65504.0).half()
+    lo = ((t - hi.float()) * LO_SCALE).clamp(-65504.0, 65504.0).half()
+    return hi, lo
+
+
+def tc_weight_images_f16(w, bn=None):
+    """[taps, cin, cout] fp32 (cin in {8,16,32} or a multiple of 64) -> ([n_tiles, n_stages, 2, bn, 64] fp16, bn): per
+    (N tile, pipeline K-step of 64) the hi and lo * 2^11 fp16 parts of the weights as 128B-swizzled K-major smem images
+    (row n = output channel, 16-byte chunk j = 8 halves stored at chunk j ^ (n % 8)): one cp.async.bulk per stage."""
+    taps, cin, cout = w.shape
+    default_bn = lib.ff3d_tcgemm_f16_ntile(cin, cout)
+    if default_bn <= 0:
+        return None, 0
+    bn = bn or default_bn
+    assert cout % bn == 0 and bn in (16, 32, 64, 128)
+    n_stages = lib.ff3d_tcgemm_f16_stages(cin, taps)
+    if cin >= 64:
+        kmat = w.reshape(taps * cin, cout)                          # stage s = rows [64 s, 64 s + 64)
+    else:
+        tps = 64 // cin
+        kmat = torch.zeros((n_stages * tps, cin, cout), dtype=torch.float32)
+        kmat[:taps] = w
+        kmat = kmat.reshape(n_stages * 64, cout)
+    hi, lo = split_f16(kmat.float())
+    n_tiles = cout // bn
+    n_idx, j_idx = torch.arange(bn), torch.arange(8)
+    dst_chunk = j_idx[None, :] ^ (n_idx[:, None] & 7)              # [bn, 8]
+    imgs = torch.empty((n_tiles, n_stages, 2, bn, 64), dtype=torch.float16)
+    for part, src in enumerate((hi, lo)):
+        blk = src.view(n_stages, 8, 8, n_tiles, bn).permute(3, 0, 4, 1, 2)      # [tile, stage, n, chunk j, 8 halves]
+        out = torch.empty((n_tiles, n_stages, bn, 8, 8), dtype=torch.float16)
+        out.scatter_(3, dst_chunk[None, None, :, :, None].expand(n_tiles, n_stages, bn, 8, 8), blk)
+        imgs[:, :, part] = out.view(n_tiles, n_stages, bn, 64)
+    return imgs.contiguous(), bn
+
+
+def unpack_images_f16(imgs, taps, cin, cout):
+    """Inverse of tc_weight_images_f16 (test helper): -> (hi, lo) as [taps, cin, cout] fp32."""
+    n_tiles, n_stages, _, bn, _ = imgs.shape
+    n_idx, j_idx = torch.arange(bn), torch.arange(8)
+    src_chunk = j_idx[None, :] ^ (n_idx[:, None] & 7)
+    parts = []
+    for part in range(2):
+        sw = imgs[:, :, part].reshape(n_tiles, n_stages, bn, 8, 8)
+        un = sw.gather(3, src_chunk[None, None, :, :, None].expand(n_tiles, n_stages, bn, 8, 8))
+        kmat = un.permute(1, 3, 4, 0, 2).reshape(n_stages * 64, n_tiles * bn).float()       # [K, cout]
+        parts.append(kmat.reshape(taps, cin, cout) if cin >= 64 else kmat.reshape(-1, cin, cout)[:taps])
+    return parts[0], parts[1]
+
+
+# Operand format of the tensor-core GEMM: "f16" = fp16 hi/lo split on kind::f16 (default: twice the MMA rate, half the
+# shared-memory bytes per product, and -- measured at full size against an fp64 run of the oracle -- HALF the error of
+# the TF32 split, because the accumulator is truncated once per 16 instead of once per 8 products); "tf32" = TF32 hi/lo
+# split (no range limit).  Activations beyond +-65504 raise a device flag in f16 mode (gemm_flag) and fail the call.
+GEMM_KIND = _os.environ.get("FF3D_GEMM", "f16")
+if GEMM_KIND not in ("f16", "tf32"):
+    raise L.Ff3dError(f"FF3D_GEMM={GEMM_KIND!r}: expected 'f16' or 'tf32'")
+
+_flags = {}
+
+
+def gemm_flag(dev=None):
+    """Device int32[1] raised by the f16 kernels when an activation saturated the fp16 range."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else torch.device(dev)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _flags:
+        _flags[key] = torch.zeros((1,), dtype=torch.int32, device=dev)
+    return _flags[key]
+
+
+class PackedW:
+    """Device weights of one GEMM-like layer: ``w`` [taps, cin, ldw] (SIMT kernel) and the tcgen05 kernel's pre-swizzled
+    hi/lo images in the selected operand format (``kind`` 'f16' / 'tf32'; None = not tensor-core tileable)."""
+
+    def __init__(self, w_cpu, dev, bn=None, kind=None):
         self.w = w_cpu.to(dev)
-        img, self.bn = tc_weight_images(w_cpu, bn)
+        kind = kind or GEMM_KIND
+        img, self.bn, self.kind = None, 0, None
+        if kind == "f16":
+            img, self.bn = tc_weight_images_f16(w_cpu, bn)
+            if img is not None:
+                self.kind = "f16"
+        if self.kind is None:                                   # 'tf32' requested, or a cin only the 32-wide K step tiles
+            img, self.bn = tc_weight_images(w_cpu, bn)
+            if img is not None:
+                self.kind = "tf32"
         self.img = img.to(dev) if img is not None else None
 
     @property
@@ -137,10 +222,14 @@ TC_MIN_ROWS = int(_os.environ.get("FF3D_TC_MIN_ROWS", "0"))
 
 
 def _gemm(d, w, what):
-    """Dispatch one implicit-GEMM launch: tcgen05 3xTF32 kernel when the layer is tensor-core tileable."""
+    """Dispatch one implicit-GEMM launch: tcgen05 split-precision kernel when the layer is tensor-core tileable."""
     small = d.mode == GEMM_ROWS and d.M < TC_MIN_ROWS and d.cin <= 1024
     if USE_TC and w.img is not None and not small:
-        check(lib.ff3d_tcgemm_bn(C.byref(d), _ptr(w.img), w.bn, _stream()), f"ff3d_tcgemm({what})")
+        if w.kind == "f16":
+            check(lib.ff3d_tcgemm_f16(C.byref(d), _ptr(w.img), w.bn, _ptr(gemm_flag(w.img.device)), _stream()),
+                  f"ff3d_tcgemm_f16({what})")
+        else:
+            check(lib.ff3d_tcgemm_bn(C.byref(d), _ptr(w.img), w.bn, _stream()), f"ff3d_tcgemm({what})")
     else:
         check(lib.ff3d_igemm(C.byref(d), _stream()), f"ff3d_igemm({what})")
 

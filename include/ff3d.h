@@ -180,6 +180,16 @@ int ff3d_tcgemm(const ff3d_gemm_desc* desc, const float* wimg, ff3d_stream_t str
 int ff3d_tcgemm_bn(const ff3d_gemm_desc* desc, const float* wimg, int ntile, ff3d_stream_t stream);
 int ff3d_tcgemm_ntile(int cin, int cout);
 int ff3d_tcgemm_stages(int cin, int taps);
+/* Same contract with an fp16 hi/lo operand split on kind::f16 (twice the MMA rate of kind::tf32, 64 K-values per 128-byte
+ * shared-memory row): a = hi + 2^-11 lo, hi = rn_f16(a), lo = rn_f16((a - hi) 2^11); D_main += A_hi*B_hi,
+ * D_cross += A_hi*B_lo + A_lo*B_hi, y = D_main + 2^-11 D_cross -- the same 22-bit products as the TF32 split.
+ * Supported when ff3d_tcgemm_f16_ntile(cin, cout) > 0 (cin in {8,16,32} or a multiple of 64).  `wimg16` =
+ * [cout/ntile][ff3d_tcgemm_f16_stages(cin,taps)][2][ntile*64] halves (focalformer3d_b200/ops.py tc_weight_images_f16).
+ * Values beyond +-65504 saturate: *overflow_dev (int32, may be NULL) is OR-ed with 1 and the result is invalid -- the
+ * caller must check the flag and fail (or rerun the layer through ff3d_tcgemm). */
+int ff3d_tcgemm_f16(const ff3d_gemm_desc* desc, const void* wimg16, int ntile, int* overflow_dev, ff3d_stream_t stream);
+int ff3d_tcgemm_f16_ntile(int cin, int cout);
+int ff3d_tcgemm_f16_stages(int cin, int taps);
 
 /* Depthwise 3x3 stride 1 pad 1, NHWC, folded BN + activation (torchvision InvertedResidual dw conv,
  * focal_encoder.py:36-38). x [B,H,W,C] (ldx), w [9, C], bias [C]. */

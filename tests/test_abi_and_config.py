@@ -165,7 +165,15 @@ def test_weight_packing_runs_without_a_gpu(tiny_cfg, tiny_sd):
     model.load_state_dict(tiny_sd, strict=True)
     model.prepare("cpu")
     w = model.pts_bbox_head.pk["heat"][0][2]                 # 128 -> 10 heatmap conv, padded to 16 for the tensor cores
-    assert tuple(w.shape) == (9, 128, 16) and w.img is not None and tuple(w.img.shape) == (1, 36, 2, 16, 32)
-    hi, lo = w.img[0, :, 0], w.img[0, :, 1]
+    # default operand format: fp16 hi/lo images, 64-wide K steps (9 taps x 128 channels = 18 stages)
+    assert w.kind == "f16" and tuple(w.shape) == (9, 128, 16) and tuple(w.img.shape) == (1, 18, 2, 16, 64)
+    assert w.img.dtype == torch.float16
+    hi, lo = w.img[0, :, 0].float(), w.img[0, :, 1].float()
+    assert (lo.abs() / 2048.0 <= hi.abs() * 2 ** -10 + 2 ** -24).all()            # lo carries only the bits below hi
+    # TF32 hi/lo images (FF3D_GEMM=tf32): 32-wide K steps
+    from focalformer3d_b200.ops import PackedW
+    w32 = PackedW(w.w.cpu(), "cpu", kind="tf32")
+    assert w32.kind == "tf32" and tuple(w32.img.shape) == (1, 36, 2, 16, 32)
+    hi, lo = w32.img[0, :, 0], w32.img[0, :, 1]
     assert (hi.view(torch.int32) & 0x1FFF).abs().sum() == 0                      # hi parts are exact TF32 values
     assert (lo.abs() <= hi.abs() * 2 ** -10 + 1e-30).all()

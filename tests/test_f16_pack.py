@@ -1,12 +1,14 @@
-"""Host side of the EXPERIMENTAL fp16 hi/lo GEMM operand format (round-2 work item; not on the product path): the weight
-images round-trip, keep fp32-grade precision and follow the same swizzle rule as the TF32 images the shipped kernel uses."""
+"""Host side of the fp16 hi/lo GEMM operand format (ff3d_tcgemm_f16): the weight images round-trip, keep fp32-grade
+precision and follow the same swizzle rule as the TF32 images."""
 import pytest
 import torch
 
 
 @pytest.mark.parametrize("taps,cin,cout", [(27, 128, 128), (9, 64, 256), (27, 16, 32), (49, 8, 64), (1, 32, 16), (3, 832, 64)])
 def test_f16_weight_images_round_trip(taps, cin, cout):
-    from focalformer3d_b200.experimental_f16 import tc_weight_images_f16, unpack_images_f16, f16_stages
+    from focalformer3d_b200.ops import tc_weight_images_f16, unpack_images_f16
+    from focalformer3d_b200.lib import lib
+    f16_stages = lib.ff3d_tcgemm_f16_stages
     g = torch.Generator().manual_seed(taps * 1000 + cin)
     w = torch.randn(taps, cin, cout, generator=g) / (taps * cin) ** 0.5
     imgs, bn = tc_weight_images_f16(w)
@@ -20,7 +22,7 @@ def test_f16_weight_images_round_trip(taps, cin, cout):
 
 def test_f16_and_tf32_images_share_the_swizzle_rule():
     """chunk j of row n sits at chunk j ^ (n % 8) in both formats (8 halves vs 4 floats per 16-byte chunk)."""
-    from focalformer3d_b200.experimental_f16 import tc_weight_images_f16
+    from focalformer3d_b200.ops import tc_weight_images_f16
     w = torch.zeros(1, 64, 16)
     w[0, 8 * 3 + 2, 5] = 1.0                                  # K = 26 -> chunk 3, half 2 of output row 5
     imgs, bn = tc_weight_images_f16(w)
@@ -31,7 +33,7 @@ def test_f16_and_tf32_images_share_the_swizzle_rule():
 
 
 def test_f16_split_matches_the_numerics_study():
-    from focalformer3d_b200.experimental_f16 import split_f16
+    from focalformer3d_b200.ops import split_f16
     g = torch.Generator().manual_seed(0)
     a = torch.randn(64, 512, generator=g) * 3.0
     b = torch.randn(512, 32, generator=g) / 512 ** 0.5
