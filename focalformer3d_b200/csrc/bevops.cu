@@ -312,11 +312,10 @@ extern "C" int ff3d_local_attention(const float* q, int ldq, const float* k, int
     const int hw = LA_T + K - 1;
     const size_t smem = sizeof(float) * ((size_t)LA_T * LA_T * LA_C + (size_t)hw * (hw + 1) * LA_LD);
     if (smem <= 227 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(local_attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-      }
+      // one-time opt-in to > 48 KB dynamic shared memory: function-local static initialiser (thread-safe, C++11)
+      static const cudaError_t attr =
+          cudaFuncSetAttribute(local_attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      (void)attr;
       const int tiles = cdiv(H, LA_T) * cdiv(W, LA_T);
       local_attention_tiled_kernel<<<B * tiles, 512, smem, as_stream(stream)>>>(q, ldq, k, ldk, v, ldv, y, ldy, H, W, K, scale);
       return check_launch("ff3d_local_attention");

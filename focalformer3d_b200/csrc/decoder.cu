@@ -302,11 +302,15 @@ extern "C" int ff3d_mha_core(const float* q, int ldq, const float* k, int ldk, c
   if (ny > one_wave && one_wave >= 1) ny = one_wave;
   dim3 grid(B * heads, ny);
   cudaStream_t st = as_stream(stream);
+  // the shared-memory size depends on Nq: opt in to the device maximum once (thread-safe static initialisers)
+  FF3D_REQUIRE(smem <= 227 * 1024, "mha_core: Nq=%d needs %zu bytes of shared memory", Nq, smem);
   if (d == 16) {
-    cudaFuncSetAttribute(mha_core_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static const cudaError_t attr = cudaFuncSetAttribute(mha_core_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    (void)attr;
     mha_core_kernel<16><<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, heads);
   } else {
-    cudaFuncSetAttribute(mha_core_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static const cudaError_t attr = cudaFuncSetAttribute(mha_core_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    (void)attr;
     mha_core_kernel<32><<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, heads);
   }
   return check_launch("ff3d_mha_core");

@@ -309,11 +309,9 @@ extern "C" int ff3d_hip_stage(const float* logits, int ldl, const float* logits2
   if (nb > cap) nb = cap;
   hip_heat_kernel<<<nb, 256, 0, st>>>(logits, ldl, logits2, ldl2, acc_mask, heat, p);
   hip_nms_kernel<<<nb, 256, 0, st>>>(heat, nms_heat, cand, cnt, p);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(hip_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_CAP * 8);
-    attr_set = true;
-  }
+  // one-time opt-in to > 48 KB dynamic shared memory: function-local static initialiser (thread-safe, C++11)
+  static const cudaError_t attr = cudaFuncSetAttribute(hip_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_CAP * 8);
+  (void)attr;
   hip_select_kernel<<<B, SEL_THREADS, SEL_CAP * sizeof(unsigned long long), st>>>(cand, cnt, nms_heat, acc_mask, feat, ldf, Cf, cls_w, cls_b, p, q0,
                                                nq_total, top_idx, query_feat, query_pos, query_score, query_label);
   return check_launch("ff3d_hip_stage");

@@ -35,8 +35,7 @@
 //    all three warp roles walk only the taps (cin >= K-step) / multi-tap stages (cin < K-step) whose bit is set, so the
 //    (row, tap) pairs that exist in no row of the tile are neither gathered, split, copied nor multiplied.
 //  * Row offsets are 64-bit (row index * ld), the one-time kernel attribute setup is a thread-safe static initialiser.
-#include "common.cuh"
-#include <cuda_fp16.h>
+#include "tc_common.cuh"
 
 namespace ff3d {
 
@@ -60,169 +59,6 @@ struct TcP {
   int* overflow;            // F16: device flag raised when an activation saturates the fp16 range
   int n_stages, tps, cpt;   // pipeline K-steps; taps per stage (cin < KS); KS-channel chunks per tap (cin >= KS)
   int n_units;              // skippable units of a tile: taps (cin >= KS) or multi-tap stages (cin < KS)
-};
-
-constexpr int TC_BM = 128;
-constexpr int TC_MAX_TAPS = 27;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// All shared-memory traffic of this kernel goes through 32-bit shared-space addresses: the 1024-byte alignment of the
-// dynamic window is established on the ADDRESS, not by rounding a generic pointer (which loses the address space and
-// makes every access a generic LD/ST on the long scoreboard).
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts128i(uint32_t addr, int4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t addr, int v) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ int lds32(uint32_t addr) {
-  int v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));   // volatile: ordered against the barrier asms
-  return v;
-}
-__device__ __forceinline__ int4 lds128i(uint32_t addr) {
-  int4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
-// SBO(1024B>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major A and B,
-// N>>3 at [17,23), M>>4 at [24,29)
-// (A = B = F16: format code 0 instead of 2)
-template <bool F16>
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  const uint32_t fmt = F16 ? 0u : 2u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-template <bool F16>
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  if constexpr (F16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(da), "l"(db), "r"(idesc), "r"(acc)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(da), "l"(db), "r"(idesc), "r"(acc)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// round-to-nearest fp32 -> tf32 (result in fp32 layout, low 13 mantissa bits zero)
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
-// byte offset of (row r, 16-byte chunk j) inside a 128B-swizzled K-major tile whose base is 1024B aligned
-__device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
-
-// cheap round-to-nearest split: hi = rn_tf32(v) by integer add + mask (2 ALU ops), lo = v - hi (exact; the tensor core
-// drops lo's bits below its own 2^-11, i.e. ~2^-23 of v)
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
-  lo = v - hi;
-}
-
-// fp16 hi/lo split of four fp32 values -> two packed half2 words each.  Saturating: beyond +-65504 the hi part clamps
-// (and the caller's overflow flag is raised); lo = (v - hi) * 2^11 cannot overflow unless hi already did.
-constexpr float F16_MAX = 65504.f;
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void split_f16x4(const float4& v, uint32_t& h01, uint32_t& h23, uint32_t& l01, uint32_t& l23,
-                                            bool& ovf) {
-  float c0 = fminf(fmaxf(v.x, -F16_MAX), F16_MAX), c1 = fminf(fmaxf(v.y, -F16_MAX), F16_MAX);
-  float c2 = fminf(fmaxf(v.z, -F16_MAX), F16_MAX), c3 = fminf(fmaxf(v.w, -F16_MAX), F16_MAX);
-  ovf = ovf || c0 != v.x || c1 != v.y || c2 != v.z || c3 != v.w;      // also true for NaN
-  __half2 ha = __floats2half2_rn(c0, c1), hb = __floats2half2_rn(c2, c3);
-  float2 fa = __half22float2(ha), fb = __half22float2(hb);
-  h01 = *reinterpret_cast<uint32_t*>(&ha);
-  h23 = *reinterpret_cast<uint32_t*>(&hb);
-  auto lo = [](float x, float h) { return fminf(fmaxf((x - h) * 2048.f, -F16_MAX), F16_MAX); };
-  l01 = pack_h2(lo(c0, fa.x), lo(c1, fa.y));
-  l23 = pack_h2(lo(c2, fb.x), lo(c3, fb.y));
-}
-
-// k-th (0-based) set bit of m
-__device__ __forceinline__ int nth_bit(uint32_t m, int k) {
-  for (int i = 0; i < k; ++i) m &= m - 1;
-  return __ffs(m) - 1;
-}
-
-struct Ring {
-  int slot;
-  uint32_t phase;
-  __device__ __forceinline__ void advance(int k, int n) {
-    slot += k;
-    while (slot >= n) { slot -= n; phase ^= 1u; }
-  }
 };
 
 template <int N>

@@ -1108,15 +1108,22 @@ class FocalFormer3D(nn.Module):
             if not self.input_pts:
                 return self.forward_camera(img, img_metas, keep_stages)
         dev = self._prepared_on
-        B = len(points)
-        offs = [0]
-        for p in points:
-            offs.append(offs[-1] + int(p.shape[0]))
-        allp = torch.cat([p.to(dev, torch.float32) for p in points], 0).contiguous() if B > 1 else points[0].to(dev, torch.float32).contiguous()
+        if isinstance(points, tuple):
+            # (concatenated [sum N_i, F] device tensor, host row offsets [B+1]): the CUDA-graph runner's static input buffer
+            allp, offs = points
+            B = len(offs) - 1
+            sizes = [offs[b + 1] - offs[b] for b in range(B)]
+        else:
+            B = len(points)
+            offs = [0]
+            for p in points:
+                offs.append(offs[-1] + int(p.shape[0]))
+            sizes = [int(p.shape[0]) for p in points]
+            allp = torch.cat([p.to(dev, torch.float32) for p in points], 0).contiguous() if B > 1 else points[0].to(dev, torch.float32).contiguous()
         vc = self.voxel_cfg
         mv = vc["max_voxels"]
         mv = mv[1] if isinstance(mv, (tuple, list)) else mv
-        n_max = max(max(int(p.shape[0]) for p in points), 1)
+        n_max = max(max(sizes), 1)
         # focalformer3d.py:80,159-163: a 'Dynamic*' voxel encoder switches to dynamic voxelisation (no caps)
         dynamic = isinstance(self.pts_voxel_encoder, DynamicSimpleVFE)
         mv = n_max if (dynamic or mv <= 0) else min(mv, n_max)
