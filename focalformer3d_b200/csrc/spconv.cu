@@ -188,7 +188,7 @@ __global__ void sp_level_permute_kernel(const int* __restrict__ coors_in, const 
 }
 
 // neighbour map in (sorted) tile order + the OR of the tap masks of every 128-row tile + the output row map.
-// One 128-thread block per 128-row tile.  y_mode 0: no row map; 1: y_off[j] = source row * ldy; 2: NHWC BEV element
+// One 128-thread block per 128-row tile.  y_mode 0: no row map; 1: y_off[j] = source ROW (a row map); 2: NHWC BEV element
 // offset ((b*Hb + y)*Wb + x)*ld + z*C of the source row's coordinates.
 __global__ void __launch_bounds__(128) sp_nbr_build_kernel(const int* __restrict__ coors_out, const int* __restrict__ perm,
                                                            const int* __restrict__ n_out_dev, int cap_out, Down g,
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) sp_nbr_build_kernel(const int* __restrict
       int rows[27];
       m = probe_taps(c, g, hkeys_in, hvals_in, hmask_in, kvol, rows);
       for (int t = 0; t < kvol; ++t) nbr[(size_t)t * cap_out + j] = rows[t];
-      if (y_mode == 1) y_off[j] = o * ldy;
+      if (y_mode == 1) y_off[j] = o;                 // output ROW of tile position j
       else if (y_mode == 2) y_off[j] = ((c.x * g.Ho + c.z) * g.Wo + c.w) * ldy + c.y * Cc;
     }
     m = __reduce_or_sync(0xffffffffu, m);
@@ -350,7 +350,6 @@ extern "C" int ff3d_sp_nbr_build(const int* coors_out, const int* perm, const in
   using namespace ff3d;
   FF3D_REQUIRE(is_pow2(hsize_in) && nbr && tile_mask, "sp_nbr_build: bad arguments");
   FF3D_REQUIRE(y_mode == 0 || y_off != nullptr, "sp_nbr_build: y_off missing");
-  FF3D_REQUIRE(y_mode != 1 || (long long)cap_out * ldy < 0x7FFFFFFFLL, "sp_nbr_build: row offsets exceed int32");
   Down g;
   const int kvol = fill_down(g, k3, s3, p3, D, H, W, 0, bev_h, bev_w);
   FF3D_REQUIRE(kvol >= 1 && kvol <= 27, "sp_nbr_build: kernel volume %d not in 1..27", kvol);

@@ -56,6 +56,8 @@ struct TcP {
   const int* nbr; int nbr_stride;
   const int* y_off;
   const uint32_t* tile_mask;   // SPARSE, optional: per 128-row tile the OR of its rows' tap masks
+  const int* y_row;            // SPARSE, optional: output row of tile position m
+  __half* ys; int ldys, ys_lo; // optional split (fp16 hi | lo) copy of the output rows for a TMA-fed consumer (tmagemm.cu)
   int* overflow;            // F16: device flag raised when an activation saturates the fp16 range
   int n_stages, tps, cpt;   // pipeline K-steps; taps per stage (cin < KS); KS-channel chunks per tap (cin >= KS)
   int n_units;              // skippable units of a tile: taps (cin >= KS) or multi-tap stages (cin < KS)
@@ -175,19 +177,21 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       const int m = m0 + mt * TC_BM + r;
       const bool rvalid = m < Mv;
       float* yp = nullptr;
+      __half* ysp = nullptr;
       if (rvalid) {
+        long long orow = m;
         if (MODE == FF3D_GEMM_CONV2D) {
           int hw = p.Ho * p.Wo;
           int cb = m / hw;
           int rr = m - cb * hw;
           int coy = rr / p.Wo, cox = rr - (rr / p.Wo) * p.Wo;
-          long long row = cb * p.y_bstride + p.y_row0 + (long long)(coy * p.uy + p.dy) * (p.Wo * p.ux) + cox * p.ux + p.dx;
-          yp = p.y + row * p.ldy;
-        } else if (MODE == FF3D_GEMM_SPARSE && p.y_off) {
-          yp = p.y + __ldg(p.y_off + m);
-        } else {
-          yp = p.y + (long long)m * p.ldy;
+          orow = cb * p.y_bstride + p.y_row0 + (long long)(coy * p.uy + p.dy) * (p.Wo * p.ux) + cox * p.ux + p.dx;
+        } else if (MODE == FF3D_GEMM_SPARSE && p.y_row) {
+          orow = __ldg(p.y_row + m);
         }
+        if (MODE == FF3D_GEMM_SPARSE && p.y_off) yp = p.y + __ldg(p.y_off + m);
+        else if (p.y) yp = p.y + orow * p.ldy;
+        if (p.ys) ysp = p.ys + orow * p.ldys;
       }
       const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS + mt * 2 * BN);
 #pragma unroll 1
@@ -230,12 +234,25 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
             if (!p.res_after_act) a = apply_act(a, p.act);
             v[i] = a;
           }
-          if ((reinterpret_cast<uintptr_t>(yp + n) & 15) == 0) {
+          if (yp) {
+            if ((reinterpret_cast<uintptr_t>(yp + n) & 15) == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yp + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yp + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) yp[n + i] = v[i];
+              for (int i = 0; i < 16; ++i) yp[n + i] = v[i];
+            }
+          }
+          if (ysp) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              split_f16x4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hw[2 * i], hw[2 * i + 1], lw[2 * i],
+                          lw[2 * i + 1], ovf);
+            uint4* dh = reinterpret_cast<uint4*>(ysp + n);
+            uint4* dl = reinterpret_cast<uint4*>(ysp + p.ys_lo + n);
+            dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); dh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+            dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
           }
         }
       }
@@ -434,7 +451,7 @@ __global__ void __launch_bounds__(128 * G + 64, (BN <= 64 ? 2 : 1)) tcgemm_kerne
       }
     }
     if (DEFER && prev_tile >= 0) epilogue(prev_tile, it - 1);
-    if (F16 && ovf && p.overflow) atomicOr(p.overflow, 1);
+    if (ovf && p.overflow) atomicOr(p.overflow, 1);
   } else if (warp == 4 * G) {
     // =========================== B producer ===========================
     if (lane == 0) {
@@ -581,7 +598,10 @@ static int tcgemm_run(const ff3d_gemm_desc* d, const void* wimg, int bn, int* ov
   FF3D_REQUIRE(bn > 0 && ntile_for(d->cin, d->cout, KS) > 0 && d->cout % bn == 0 &&
                    (bn == 16 || bn == 32 || bn == 64 || bn == 128),
                "ff3d_tcgemm: shape cin=%d cout=%d (N tile %d) is not tensor-core tileable", d->cin, d->cout, bn);
-  FF3D_REQUIRE(d->ldx % 4 == 0 && d->x && d->y && d->taps > 0, "ff3d_tcgemm: bad operands");
+  FF3D_REQUIRE(d->ldx % 4 == 0 && d->x && (d->y || d->ys) && d->taps > 0, "ff3d_tcgemm: bad operands");
+  FF3D_REQUIRE(!d->ys || ((reinterpret_cast<uintptr_t>(d->ys) & 15) == 0 && d->ldys % 8 == 0 && d->ys_lo % 8 == 0),
+               "ff3d_tcgemm: split output rows must be 16-byte aligned");
+  FF3D_REQUIRE(!d->y_off || d->y, "ff3d_tcgemm: y_off addresses the fp32 output");
   FF3D_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wimg) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0,
                "ff3d_tcgemm: x, wimg and bias must be 16-byte aligned");
@@ -597,6 +617,8 @@ static int tcgemm_run(const ff3d_gemm_desc* d, const void* wimg, int bn, int* ov
   p.x_bstride = d->x_bstride; p.y_bstride = d->y_bstride; p.y_row0 = d->y_row0;
   p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.y_off = d->y_off;
   p.tile_mask = d->mode == FF3D_GEMM_SPARSE ? d->tile_mask : nullptr;
+  p.y_row = d->mode == FF3D_GEMM_SPARSE ? d->y_row : nullptr;
+  p.ys = static_cast<__half*>(d->ys); p.ldys = d->ldys; p.ys_lo = d->ys_lo;
   p.overflow = overflow_dev;
   p.n_stages = stages_for(d->cin, d->taps, KS);
   p.tps = d->cin >= KS ? 1 : KS / d->cin;

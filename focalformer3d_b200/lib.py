@@ -31,6 +31,10 @@ class GemmDesc(C.Structure):
         ("ux", C.c_int), ("uy", C.c_int), ("dx", C.c_int), ("dy", C.c_int),
         ("nbr", C.c_void_p), ("nbr_stride", C.c_int), ("y_off", C.c_void_p), ("res_after_act", C.c_int),
         ("tile_mask", C.c_void_p),
+        ("xs", C.c_void_p), ("ldxs", C.c_int), ("xs_lo", C.c_int), ("xs_rows", C.c_int),
+        ("res_s", C.c_void_p), ("ldres_s", C.c_int), ("res_s_lo", C.c_int),
+        ("ys", C.c_void_p), ("ldys", C.c_int), ("ys_lo", C.c_int),
+        ("y_row", C.c_void_p), ("zero_row", C.c_int),
     ]
 
 
@@ -62,6 +66,11 @@ SIGNATURES = {
     "ff3d_tcgemm_f16": (_I, [C.POINTER(GemmDesc), _P, _I, _P, _P]),
     "ff3d_tcgemm_f16_ntile": (_I, [_I, _I]),
     "ff3d_tcgemm_f16_stages": (_I, [_I, _I]),
+    "ff3d_tmagemm": (_I, [C.POINTER(GemmDesc), _P, _I, _P, _P]),
+    "ff3d_tmagemm_supported": (_I, [C.POINTER(GemmDesc)]),
+    "ff3d_tmagemm_conv_patch": (None, [_I, _I, _IP, _IP]),
+    "ff3d_split_rows": (_I, [_P, _I, _P, _LL, _I, _P, _I, _I, _P, _P]),
+    "ff3d_unsplit_rows": (_I, [_P, _I, _I, _P, _LL, _I, _P, _I, _P]),
     "ff3d_tcgemm_ntile": (_I, [_I, _I]),
     "ff3d_tcgemm_stages": (_I, [_I, _I]),
     "ff3d_dwconv3x3": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -185,9 +185,21 @@ class SparseEncoder(ParamTree):
         lvl.build_hash()
         perm = lvl.sort_by_mask()
         feats = ops.gather_rows(vox["mean"], perm, lvl.n_dev, vox["mean"].shape[1])
-        w, b = self.pk["conv_input"]
-        x = torch.empty((cap1, w.shape[-1]), dtype=torch.float32, device=dev)
-        ops.sparse_conv(feats, lvl.subm_map(), lvl.n_dev, w, b, x, act=ACT_RELU)
+
+        def conv(x, rb, n_dev, wb, cap_out, act, res=None):
+            """One sparse conv.  Activations of a level whose channel count the TMA-fed kernel tiles (C % 64 == 0) live in
+            split form (ops.Split, written by the producing conv's epilogue); narrower levels stay fp32 rows."""
+            w, b = wb
+            cout = w.shape[-1]
+            if ops.tma_enabled() and cout % 64 == 0:            # the consumers of a C % 64 == 0 level take split rows
+                ys = ops.Split.empty((cap_out,), cout, dev, zero_row=True)
+                ops.sparse_conv(x, rb, n_dev, w, b, None, act=act, res=res, out_s=ys)
+                return ys
+            y = torch.empty((cap_out, cout), dtype=torch.float32, device=dev)
+            ops.sparse_conv(x, rb, n_dev, w, b, y, act=act, res=res)
+            return y
+
+        x = conv(feats, lvl.subm_map(), lvl.n_dev, self.pk["conv_input"], cap1, ACT_RELU)
         self.level_sizes = [lvl.n_dev]
         for i, blocks in enumerate(self.encoder_channels):
             for j, cout in enumerate(blocks):
@@ -197,20 +209,13 @@ class SparseEncoder(ParamTree):
                     p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
                     cap_out = int(lvl.cap * self.cap_growth[i])
                     nl, rb = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow, ldy=cout)
-                    w, b = self.pk[q]
-                    y = torch.empty((nl.cap, cout), dtype=torch.float32, device=dev)
-                    ops.sparse_conv(x, rb, nl.n_dev, w, b, y, act=ACT_RELU)
-                    lvl, x = nl, y
+                    x = conv(x, rb, nl.n_dev, self.pk[q], nl.cap, ACT_RELU)
+                    lvl = nl
                     self.level_sizes.append(lvl.n_dev)
                 else:
                     rb = lvl.subm_map()
-                    w1, b1 = self.pk[q + ".1"]
-                    w2, b2 = self.pk[q + ".2"]
-                    t = torch.empty_like(x)
-                    ops.sparse_conv(x, rb, lvl.n_dev, w1, b1, t, act=ACT_RELU)
-                    y = torch.empty_like(x)
-                    ops.sparse_conv(t, rb, lvl.n_dev, w2, b2, y, act=ACT_RELU, res=x)
-                    x = y
+                    t = conv(x, rb, lvl.n_dev, self.pk[q + ".1"], lvl.cap, ACT_RELU)
+                    x = conv(t, rb, lvl.n_dev, self.pk[q + ".2"], lvl.cap, ACT_RELU, res=x)
         # conv_out: SparseConv3d k(3,1,1) s(2,1,1) p0 + BN + ReLU, scattered straight into the NHWC BEV grid
         Cc = self.output_channels
         assert bev_out.is_contiguous()
@@ -253,17 +258,31 @@ class SECOND(ParamTree):
             self.pk.append(layers)
 
     def forward(self, x):
+        """x [B,H,W,C] fp32 NHWC.  Returns the stage outputs as (fp32 NHWC, ops.Split or None) pairs.  Inside a stage the
+        activations live in split form only (TMA-fed convs); the stage outputs are stored in both forms (fp32 for the
+        stride-2 / transposed-conv consumers and the tests, split for the TMA consumers)."""
         outs = []
         B, H, W, _ = x.shape
+        dev = x.device
+        xs = None                                                   # split form of x (when the next conv can take it)
         for i, layers in enumerate(self.pk):
             st = self.layer_strides[i]
             for l, (w, b) in enumerate(layers):
                 s = st if l == 0 else 1
                 Ho, Wo = ((H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1)
-                y = torch.empty((B, Ho, Wo, self.out_channels[i]), dtype=torch.float32, device=x.device)
-                ops.conv2d(x, w, b, y, 3, stride=s, act=ACT_RELU)
-                x, H, W = y, Ho, Wo
-            outs.append(x)
+                cin, cout = w.shape[1], self.out_channels[i]
+                last = l == len(layers) - 1
+                use_tma = s == 1 and ops.tma_ok(w, cin, cout)
+                if use_tma and xs is None:
+                    xs = ops.split_rows(x)                          # one elementwise pass (the BEV scatter output is fp32)
+                nxt = layers[l + 1][0] if not last else None
+                want_split = last or (nxt is not None and ops.tma_ok(nxt, cout, cout))
+                ys = ops.Split.empty((B, Ho, Wo), cout, dev) if (want_split and ops.tma_enabled() and cout % 64 == 0) else None
+                want_f32 = last or ys is None
+                y = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=dev) if want_f32 else None
+                ops.conv2d(xs if use_tma else x, w, b, y, 3, stride=s, act=ACT_RELU, out_s=ys)
+                x, xs, H, W = y, ys, Ho, Wo
+            outs.append((x, xs))
         return outs
 
 
@@ -294,18 +313,22 @@ class SECONDFPN(ParamTree):
             else:
                 self.pk.append(("conv", 1, pack_conv2d(w, s, dev), vec(b, dev)))
 
-    def forward(self, xs, out):
-        """xs: list of NHWC level tensors; out [B,H,W,sum(out_channels)]."""
+    def forward(self, xs, out, out_s=None):
+        """xs: list of (fp32 NHWC, ops.Split or None) level pairs; out [B,H,W,sum(out_channels)] fp32; out_s: optional
+        ops.Split of the same shape that also receives every level (for a TMA-fed consumer)."""
         c0 = 0
         for i, (kind, st, w, b) in enumerate(self.pk):
             oc = self.out_channels[i]
             view = out[..., c0:c0 + oc]
+            view_s = out_s.slice(c0, c0 + oc) if out_s is not None else None
+            x, x_s = xs[i]
             if kind == "conv":
-                ops.conv2d(xs[i], w, b, view, 1, act=ACT_RELU)
+                use_tma = x_s is not None and ops.tma_ok(w, w.shape[1], oc)
+                ops.conv2d(x_s if use_tma else x, w, b, view, 1, act=ACT_RELU, out_s=view_s)
             else:
                 for dy in range(st):
                     for dx in range(st):
-                        ops.conv2d(xs[i], w[dy * st + dx], b, view, 1, act=ACT_RELU, up=(st, dy, dx))
+                        ops.conv2d(x, w[dy * st + dx], b, view, 1, act=ACT_RELU, up=(st, dy, dx), out_s=view_s)
             c0 += oc
         return out
 
@@ -611,7 +634,7 @@ class FocalEncoder(ParamTree):
         rots, trans = self.camera_rots_trans(img_metas, img_feat.device)
         return self.pk["lss"](img_feat, rots, trans, len(img_metas), out)
 
-    def forward_fusion(self, pts_feats, img_feat, img_metas, extra_out):
+    def forward_fusion(self, pts_feats, img_feat, img_metas, extra_out, neck_s=None):
         """focal_encoder.py:171-219 with both towers.  pts_feats [B,H,W,512] (SECONDFPN), img_feat [B*N,fH,fW,256] (FPN
         level 0).  Concatenations are channel slices of two ping-pong buffers per layer: catA = [camera BEV | P2P],
         catB = [P_Aug | LiDAR BEV]; every producer writes straight into its slice.
@@ -624,7 +647,9 @@ class FocalEncoder(ParamTree):
         pk["lss"](img_feat, rots, trans, B, catA[..., :hc])                                        # :196 camera BEV
         img_bev0 = catA[..., :hc]
         conv_feat = new(hc)
-        ops.conv2d(pts_feats, *pk["shared"], conv_feat, 3, act=ACT_NONE)                           # :204
+        sw = pk["shared"][0]
+        shared_in = neck_s if (neck_s is not None and ops.tma_ok(sw, sw.shape[1], hc)) else pts_feats
+        ops.conv2d(shared_in, *pk["shared"], conv_feat, 3, act=ACT_NONE)                           # :204
         catB[..., hc:].copy_(conv_feat)                                                            # :207 (.clone())
         stages = []
         for i in range(self.num_layers):
@@ -657,13 +682,16 @@ class FocalEncoder(ParamTree):
             ops.conv2d(stages[-1], *pk["extra"], extra, 3, act=ACT_NONE)                           # :218-219
         return conv_feat, stages, extra, img_bev0
 
-    def forward(self, pts_feats, extra_out=None):
-        """pts_feats [B,H,W,512] NHWC.  Returns (conv_feat view, [stage feature views...], extra view)."""
+    def forward(self, pts_feats, extra_out=None, neck_s=None):
+        """pts_feats [B,H,W,512] NHWC (neck_s: the same in split form for the TMA-fed shared conv).
+        Returns (conv_feat view, [stage feature views...], extra view)."""
         B, H, W, _ = pts_feats.shape
         dev, hc = pts_feats.device, self.hidden
         cat1 = torch.empty((B, H, W, 2 * hc), dtype=torch.float32, device=dev)
         feat = cat1[..., :hc]
-        ops.conv2d(pts_feats, self.pk["shared"][0], self.pk["shared"][1], feat, 3, act=ACT_NONE)   # :204
+        sw = self.pk["shared"][0]
+        shared_in = neck_s if (neck_s is not None and ops.tma_ok(sw, sw.shape[1], hc)) else pts_feats
+        ops.conv2d(shared_in, sw, self.pk["shared"][1], feat, 3, act=ACT_NONE)                     # :204
         conv_feat = feat
         stages = []
         for i in range(self.num_layers):
@@ -1144,8 +1172,10 @@ class FocalFormer3D(nn.Module):
         ops.mark("sparse_encoder")
         xs = self.pts_backbone(bev)
         ops.mark("second")
-        neck = torch.empty((B, H, W, sum(self.pts_neck.out_channels)), dtype=torch.float32, device=dev)
-        self.pts_neck(xs, neck)
+        c_neck = sum(self.pts_neck.out_channels)
+        neck = torch.empty((B, H, W, c_neck), dtype=torch.float32, device=dev)
+        neck_s = ops.Split.empty((B, H, W), c_neck, dev) if (ops.tma_enabled() and c_neck % 64 == 0) else None
+        self.pts_neck(xs, neck, neck_s)
         ops.mark("secondfpn")
         head = self.pts_bbox_head
         geom = ops.LevelGeom([(H >> l, W >> l) for l in range(head.n_levels)])
@@ -1160,10 +1190,10 @@ class FocalFormer3D(nn.Module):
             ops.mark("img_backbone")
             f0 = self.img_neck(feats)
             ops.mark("img_neck")
-            conv_feat, stage_feats, extra, img_bev = self.imgpts_neck.forward_fusion(neck, f0, img_metas, extra_view)
+            conv_feat, stage_feats, extra, img_bev = self.imgpts_neck.forward_fusion(neck, f0, img_metas, extra_view, neck_s=neck_s)
             cam = dict(img_backbone=feats, img_feat=f0, img_bev=img_bev)
         else:
-            conv_feat, stage_feats, extra = self.imgpts_neck(neck, extra_out=extra_view)
+            conv_feat, stage_feats, extra = self.imgpts_neck(neck, extra_out=extra_view, neck_s=neck_s)
         ops.mark("focal_encoder")
         res = head(conv_feat, stage_feats, ms_value, geom)
         det = head.get_bboxes()
@@ -1171,7 +1201,7 @@ class FocalFormer3D(nn.Module):
         self._overflow = overflow
         stages = None
         if keep_stages:
-            stages = dict(vox=vox, bev=bev, backbone=xs, neck=neck, conv_feat=conv_feat, stage_feats=stage_feats,
+            stages = dict(vox=vox, bev=bev, backbone=[a for a, _ in xs], neck=neck, conv_feat=conv_feat, stage_feats=stage_feats,
                           extra=extra, ms_value=ms_value, overflow=overflow, level_sizes=me.level_sizes, cam=cam)
         return res, det, stages
 

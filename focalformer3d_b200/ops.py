@@ -234,26 +234,140 @@ def _gemm(d, w, what):
         check(lib.ff3d_igemm(C.byref(d), _stream()), f"ff3d_igemm({what})")
 
 
+class Split:
+    """Activation rows in split form for the TMA-fed GEMM (csrc/tmagemm.cu): ``t`` [..., 2*C] fp16, channels [0, C) = hi,
+    [C, 2C) = lo * 2^11 (value = hi + lo / 2048) -- 4C bytes per row, the footprint of fp32.  ``c0:c1`` selects a channel
+    slice (concat-free views); ``zero_row`` = index of an all-zero row kept after the last data row (sparse levels)."""
+
+    def __init__(self, t, C, c0=0, c1=None, zero_row=-1):
+        self.t, self.C, self.c0, self.c1, self.zero_row = t, C, c0, (C if c1 is None else c1), zero_row
+
+    @staticmethod
+    def empty(shape, C, dev, zero_row=False):
+        """shape = leading dims (rows,) or (B, H, W); with zero_row one extra all-zero row is appended to a 2-D buffer."""
+        shape = tuple(shape)
+        if zero_row:
+            assert len(shape) == 1
+            t = torch.empty((shape[0] + 1, 2 * C), dtype=torch.float16, device=dev)
+            t[shape[0]].zero_()
+            return Split(t, C, zero_row=shape[0])
+        return Split(torch.empty(shape + (2 * C,), dtype=torch.float16, device=dev), C)
+
+    def slice(self, c0, c1):
+        return Split(self.t, self.C, self.c0 + c0, self.c0 + c1, self.zero_row)
+
+    @property
+    def channels(self):
+        return self.c1 - self.c0
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 2 * self.c0
+
+    @property
+    def ld(self):
+        return 2 * self.C
+
+
+def split_rows(x, n_dev=None, zero_row=False, out=None):
+    """fp32 rows [..., C] (last dim contiguous, uniform row stride) -> Split of the same leading shape."""
+    _chk_f32(x, "split_rows.x")
+    Cc = x.shape[-1]
+    lead = tuple(x.shape[:-1])
+    rows = 1
+    for v in lead:
+        rows *= v
+    ldx = x.stride(-2) if x.dim() > 1 else Cc
+    if out is None:
+        out = Split.empty((rows,), Cc, x.device, zero_row=True) if zero_row else Split.empty(lead, Cc, x.device)
+    check(lib.ff3d_split_rows(_ptr(x), ldx, _ptr(n_dev), rows, Cc, C.c_void_p(out.ptr), out.ld, out.C, _ptr(gemm_flag(x.device)),
+                              _stream()), "ff3d_split_rows")
+    _count()
+    return out
+
+
+def unsplit_rows(xs, rows, n_dev=None):
+    """Split (2-D, or any leading shape flattened to ``rows`` rows) -> fp32 [rows, channels]."""
+    out = torch.empty((rows, xs.channels), dtype=torch.float32, device=xs.t.device)
+    check(lib.ff3d_unsplit_rows(C.c_void_p(xs.ptr), xs.ld, xs.C, _ptr(n_dev), rows, xs.channels, _ptr(out), out.stride(0),
+                                _stream()), "ff3d_unsplit_rows")
+    _count()
+    return out
+
+
+USE_TMA = _os.environ.get("FF3D_TMA", "1") != "0"     # FF3D_TMA=0: never take the TMA-fed kernel (debugging aid)
+
+
+def _attach_split(d, xs=None, res_s=None, out_s=None, xs_rows=0):
+    if xs is not None:
+        d.xs, d.ldxs, d.xs_lo, d.xs_rows, d.zero_row = xs.ptr, xs.ld, xs.C, xs_rows, xs.zero_row
+    if res_s is not None:
+        d.res_s, d.ldres_s, d.res_s_lo = res_s.ptr, res_s.ld, res_s.C
+    if out_s is not None:
+        d.ys, d.ldys, d.ys_lo = out_s.ptr, out_s.ld, out_s.C
+
+
+def _gemm_any(d, w, what, x_is_split):
+    """TMA-fed kernel when the A rows are in split form and the layer qualifies, else the register-path kernels."""
+    if x_is_split:
+        if not (USE_TC and USE_TMA and w.kind == "f16" and lib.ff3d_tmagemm_supported(C.byref(d))):
+            raise L.Ff3dError(f"{what}: split input given but the layer is not TMA-tileable (cin={d.cin} cout={d.cout})")
+        bn = w.bn if w.bn in (64, 128) else 0
+        check(lib.ff3d_tmagemm(C.byref(d), _ptr(w.img), bn, _ptr(gemm_flag(w.img.device)), _stream()), f"ff3d_tmagemm({what})")
+    else:
+        _gemm(d, w, what)
+
+
+def tma_enabled():
+    """Is the TMA-fed kernel (split activations) in use at all?  (fp16 operand format, not disabled by FF3D_TMA / FF3D_TC)"""
+    return bool(USE_TC and USE_TMA and GEMM_KIND == "f16")
+
+
+def tma_ok(w, cin, cout):
+    """Can a layer with these weights take split A rows (ff3d_tmagemm)?"""
+    return bool(USE_TC and USE_TMA and w.img is not None and w.kind == "f16" and cin % 64 == 0 and cin >= 64
+                and (cout % 128 == 0 or cout == 64) and w.bn in (64, 128))
+
+
 # --------------------------------------------------------------------------------------------------------------
-def linear(x, w, bias=None, out=None, act=ACT_NONE, res=None, x2=None, cout=None, res_after_act=False):
-    """y = act(x @ w + bias (+ res)).  x [M, cin] row view (ld from stride), w packed [1, cin, ldw]."""
-    _chk_f32(x, "linear.x")
-    M, cin = x.shape
+def linear(x, w, bias=None, out=None, act=ACT_NONE, res=None, x2=None, cout=None, res_after_act=False, out_s=None,
+           want_out=True):
+    """y = act(x @ w + bias (+ res)).  x [M, cin] fp32 row view (ld from stride) or a Split; w packed [1, cin, ldw].
+    ``out_s``: Split that also receives the output rows; ``want_out=False`` skips the fp32 output (TMA kernel only)."""
+    split_in = isinstance(x, Split)
+    if split_in:
+        M, cin = x.t.shape[0] - (1 if x.zero_row >= 0 else 0), x.channels
+        dev = x.t.device
+    else:
+        _chk_f32(x, "linear.x")
+        M, cin = x.shape
+        dev = x.device
     ldw = w.shape[-1]
     cout = cout or ldw
-    if out is None:
-        out = torch.empty((M, cout), device=x.device, dtype=torch.float32)
+    if out is None and want_out:
+        out = torch.empty((M, cout), device=dev, dtype=torch.float32)
     d = GemmDesc()
     d.mode, d.M, d.cin, d.cout, d.taps = GEMM_ROWS, M, cin, cout, 1
-    d.x, d.ldx, d.x2 = x.data_ptr(), x.stride(0), (x2.data_ptr() if x2 is not None else None)
-    if x2 is not None and x2.stride(0) != x.stride(0):
-        raise L.Ff3dError("linear: x2 must share x's row stride")
+    if split_in:
+        if x2 is not None:
+            raise L.Ff3dError("linear: x2 is not supported with a split input")
+        _attach_split(d, xs=x, xs_rows=M)
+    else:
+        d.x, d.ldx, d.x2 = x.data_ptr(), x.stride(0), (x2.data_ptr() if x2 is not None else None)
+        if x2 is not None and x2.stride(0) != x.stride(0):
+            raise L.Ff3dError("linear: x2 must share x's row stride")
     d.w, d.ldw, d.bias = w.w.data_ptr(), ldw, (bias.data_ptr() if bias is not None else None)
-    d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
-    d.y, d.ldy, d.act = out.data_ptr(), out.stride(0), act
+    if isinstance(res, Split):
+        _attach_split(d, res_s=res)
+    else:
+        d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
+    if out is not None:
+        d.y, d.ldy = out.data_ptr(), out.stride(0)
+    d.act = act
     d.res_after_act = 1 if res_after_act else 0
+    _attach_split(d, out_s=out_s)
     t0 = prof.begin()
-    _gemm(d, w, "rows")
+    _gemm_any(d, w, "rows", split_in)
     prof.end(t0, f"linear[{cin}x{cout}]", 2.0 * M * cin * cout, 4.0 * (M * cin + cin * cout + M * cout))
     _count()
     return out
@@ -268,32 +382,61 @@ def _nhwc_geom(t, name):
     return B, H, W, Cc, ld, t.stride(0) // ld
 
 
-def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=None):
-    """NHWC conv: x [B,H,W,cin] view, w packed [k*k, cin, ldw], out [B,Ho*u,Wo*u,cout] view.
+def _split_nhwc_geom(xs, name):
+    t = xs.t
+    if t.dim() != 4 or not t.is_contiguous():
+        raise L.Ff3dError(f"{name}: a split NHWC activation is a contiguous [B, H, W, 2C] fp16 buffer")
+    B, H, W, _ = t.shape
+    return B, H, W, xs.channels, H * W
+
+
+def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=None, out_s=None):
+    """NHWC conv: x [B,H,W,cin] fp32 view or a Split ([B,H,W,2C] fp16), w packed [k*k, cin, ldw], out [B,Ho*u,Wo*u,cout] view
+    (None with a Split input when only the split output ``out_s`` is wanted).
     ``up=(u, dy, dx)`` writes onto the (oy*u+dy, ox*u+dx) lattice (transposed conv with kernel == stride)."""
-    B, H, W, cin, ldx, xbs = _nhwc_geom(x, "conv2d.x")
-    Bo, Hy, Wy, cout, ldy, ybs = _nhwc_geom(out, "conv2d.out")
+    split_in = isinstance(x, Split)
+    if split_in:
+        B, H, W, cin, xbs = _split_nhwc_geom(x, "conv2d.x")
+        ldx = 0
+    else:
+        B, H, W, cin, ldx, xbs = _nhwc_geom(x, "conv2d.x")
     pad = (k // 2) if pad is None else pad
     Ho = (H + 2 * pad - k) // stride + 1
     Wo = (W + 2 * pad - k) // stride + 1
     u, dy, dx = up if up else (1, 0, 0)
-    if (Bo, Hy, Wy) != (B, Ho * u, Wo * u):
-        raise L.Ff3dError(f"conv2d: out shape {tuple(out.shape)} != expected {(B, Ho * u, Wo * u, cout)}")
     d = GemmDesc()
+    if out is not None:
+        Bo, Hy, Wy, cout, ldy, ybs = _nhwc_geom(out, "conv2d.out")
+        if (Bo, Hy, Wy) != (B, Ho * u, Wo * u):
+            raise L.Ff3dError(f"conv2d: out shape {tuple(out.shape)} != expected {(B, Ho * u, Wo * u, cout)}")
+        d.y, d.ldy = out.data_ptr(), ldy
+    else:
+        if out_s is None:
+            raise L.Ff3dError("conv2d: no output")
+        cout, ybs = out_s.channels, Ho * Wo
     d.mode, d.M, d.cin, d.cout, d.taps = GEMM_CONV2D, B * Ho * Wo, cin, cout, k * k
-    d.x, d.ldx = x.data_ptr(), ldx
+    if split_in:
+        _attach_split(d, xs=x, xs_rows=B * H * W)
+    else:
+        d.x, d.ldx = x.data_ptr(), ldx
     d.w, d.ldw, d.bias = w.w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
-    if res is not None:
+    if isinstance(res, Split):
+        _attach_split(d, res_s=res)
+    elif res is not None:
         rB, rH, rW, rC, ldr, rbs = _nhwc_geom(res, "conv2d.res")
         if rbs != rH * rW or (rB, rH, rW) != (B, Ho, Wo) or u != 1:
             raise L.Ff3dError("conv2d: residual must be a batch-dense NHWC view of the output shape")
         d.res, d.ldres = res.data_ptr(), ldr
-    d.y, d.ldy, d.act = out.data_ptr(), ldy, act
+    d.act = act
     d.B, d.H, d.W, d.Ho, d.Wo, d.kh, d.kw, d.stride, d.pad = B, H, W, Ho, Wo, k, k, stride, pad
     d.x_bstride, d.y_bstride, d.y_row0 = xbs, ybs, 0
     d.ux, d.uy, d.dx, d.dy = u, u, dx, dy
+    if out_s is not None:
+        if out_s.t.dim() != 4 or tuple(out_s.t.shape[:3]) != (B, Ho, Wo) or u != 1 or (out is not None and ybs != Ho * Wo):
+            raise L.Ff3dError("conv2d: the split output is a batch-dense [B, Ho, Wo, 2C] buffer")
+        _attach_split(d, out_s=out_s)
     t0 = prof.begin()
-    _gemm(d, w, "conv2d")
+    _gemm_any(d, w, "conv2d", split_in)
     Mo = B * Ho * Wo
     prof.end(t0, f"conv{k}x{k}s{stride}[{cin}->{cout}@{Ho}]", 2.0 * Mo * k * k * cin * cout,
              4.0 * (B * H * W * cin + k * k * cin * cout + Mo * cout))
@@ -301,27 +444,44 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     return out
 
 
-def sparse_conv(x, rb, n_dev, w, bias, out, act=ACT_RELU, res=None, cout=None):
-    """Rulebook gather-GEMM: x [cap_in, cin] rows, rb a Rulebook (nbr [taps, cap_out], per-tile tap masks, optional row
-    map), out [cap_out, cout] rows (or an arbitrary buffer when the rulebook carries element offsets)."""
-    _chk_f32(x, "sparse_conv.x")
-    nbr, y_off = rb.nbr, rb.y_off
+def sparse_conv(x, rb, n_dev, w, bias, out, act=ACT_RELU, res=None, cout=None, out_s=None):
+    """Rulebook gather-GEMM: x [cap_in, cin] fp32 rows or a Split (with its all-zero row), rb a Rulebook (nbr [taps, cap_out],
+    per-tile tap masks, optional row map), out [cap_out, cout] fp32 rows (None: split output only) or an arbitrary buffer
+    when the rulebook carries element offsets; ``out_s``: Split receiving the output rows; res: fp32 rows or a Split."""
+    split_in = isinstance(x, Split)
+    nbr = rb.nbr
     taps, cap = nbr.shape
-    cin = x.shape[1]
-    cout = cout or w.shape[-1]
+    if split_in:
+        if x.zero_row < 0:
+            raise L.Ff3dError("sparse_conv: a split input needs its all-zero row (Split.empty(..., zero_row=True))")
+        cin, x_rows = x.channels, x.t.shape[0]
+    else:
+        _chk_f32(x, "sparse_conv.x")
+        cin, x_rows = x.shape[1], x.shape[0]
+    cout = cout or (out_s.channels if out is None else w.shape[-1])
     d = GemmDesc()
     d.mode, d.M, d.m_dev, d.cin, d.cout, d.taps = GEMM_SPARSE, cap, n_dev.data_ptr(), cin, cout, taps
-    d.x, d.ldx = x.data_ptr(), x.stride(0)
+    if split_in:
+        _attach_split(d, xs=x, xs_rows=x_rows)
+    else:
+        d.x, d.ldx = x.data_ptr(), x.stride(0)
     d.w, d.ldw, d.bias = w.w.data_ptr(), w.shape[-1], (bias.data_ptr() if bias is not None else None)
-    d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
-    d.y, d.ldy, d.act = out.data_ptr(), (out.stride(0) if y_off is None else 0), act
+    if isinstance(res, Split):
+        _attach_split(d, res_s=res)
+    else:
+        d.res, d.ldres = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
+    if out is not None:
+        d.y, d.ldy = out.data_ptr(), (out.stride(0) if rb.y_off is None else 0)
+    d.act = act
     d.nbr, d.nbr_stride = nbr.data_ptr(), nbr.stride(0)
-    d.y_off = y_off.data_ptr() if y_off is not None else None
+    d.y_off = rb.y_off.data_ptr() if rb.y_off is not None else None
+    d.y_row = rb.y_row.data_ptr() if rb.y_row is not None else None
     d.tile_mask = rb.tile_mask.data_ptr() if rb.tile_mask is not None else None
+    _attach_split(d, out_s=out_s)
     t0 = prof.begin()
-    _gemm(d, w, "sparse")
+    _gemm_any(d, w, "sparse", split_in)
     prof.end(t0, f"spconv[{taps}t {cin}->{cout}]", None, None, n_dev, dict(nbr=nbr, cin=cin, cout=cout, taps=taps,
-                                                                            x_rows=x.shape[0], tile_mask=rb.tile_mask))
+                                                                            x_rows=x_rows, tile_mask=rb.tile_mask))
     _count()
     return out
 
@@ -473,11 +633,11 @@ def next_pow2(v):
 class Rulebook:
     """Output-stationary rulebook of one sparse conv in mask-sorted tile order: ``nbr`` [taps, cap] (input row feeding
     tile position j through tap t, -1 = none), ``tile_mask`` [ceil(cap/128)] (OR of the tap masks of each 128-row tile:
-    the gather-GEMM skips the other taps), ``y_off`` (element offset of tile position j's output row; None when the
-    rows are stored in tile order)."""
+    the gather-GEMM skips the other taps), ``y_row`` (output ROW of tile position j: strided convs run over their own
+    mask order and write the new level's rows through it) or ``y_off`` (element offset into the NHWC BEV grid)."""
 
-    def __init__(self, nbr, tile_mask, y_off=None):
-        self.nbr, self.tile_mask, self.y_off = nbr, tile_mask, y_off
+    def __init__(self, nbr, tile_mask, y_off=None, y_row=None):
+        self.nbr, self.tile_mask, self.y_off, self.y_row = nbr, tile_mask, y_off, y_row
 
 
 SUBM_K, SUBM_S, SUBM_P = (3, 3, 3), (1, 1, 1), (1, 1, 1)
@@ -530,7 +690,7 @@ class SparseLevel:
                                     _ptr(nbr), _ptr(tile_mask), _ptr(y_off), y_mode, ldy, bev[0], bev[1], bev[2], _stream()),
               "ff3d_sp_nbr_build")
         _count()
-        return Rulebook(nbr, tile_mask, y_off)
+        return Rulebook(nbr, tile_mask, y_off if y_mode == 2 else None, y_off if y_mode == 1 else None)
 
     def sort_by_mask(self):
         """Re-store the level in SubM tap-mask order (all SubM convs of the level then run on homogeneous tiles).

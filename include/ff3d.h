@@ -100,7 +100,7 @@ int ff3d_sp_down_build(const int* coors_in, const int* n_in_dev, int cap_in, int
  *   ff3d_sort_pairs      stable LSD radix sort of (key, value) with a device-side count; vals_in NULL -> 0..n-1
  *   ff3d_sp_level_permute  store a level in sorted order: coors_out[i] = coors_in[perm[i]], hash values := new rows
  *   ff3d_sp_nbr_build    nbr[t][j] for tile position j (source row o = perm ? perm[j] : j), tile_mask[j/128] = OR of
- *                        the natural-order tap masks of the tile's rows, and the row map y_off (y_mode 1: o*ldy;
+ *                        the natural-order tap masks of the tile's rows, and the row map y_off (y_mode 1: the ROW o, for desc->y_row;
  *                        y_mode 2: NHWC BEV element offset ((b*bev_h + y)*bev_w + x)*ldy + z*bev_c; 0: none)
  *   ff3d_sp_gather_rows  dst[i,:cols] = src[perm[i],:cols] (voxel features into the sorted level-1 order) */
 int ff3d_sp_down_sites(const int* coors_in, const int* n_in_dev, int cap_in, int batch, int D, int H, int W,
@@ -165,6 +165,13 @@ typedef struct ff3d_gemm_desc {
   const uint32_t* tile_mask;       /* SPARSE, optional: [ceil(M/128)] OR of the tap masks (bit t = tap t) of each 128-row
                                       tile (ff3d_sp_nbr_build); taps whose bit is clear are skipped for the tile.  Every
                                       (row, tap) with nbr >= 0 must have its bit set.  NULL = all taps. */
+  /* ---- split activations (round 2): a row of C channels stored as fp16 [hi(C) | lo(C)], value = hi + lo / 2048 ----- */
+  const void* xs; int ldxs;        /* A rows in split form: halves [xs_rows, ldxs], hi plane at column 0, lo plane at xs_lo  */
+  int xs_lo; int xs_rows;          /* (ff3d_tmagemm only; x may then be NULL).  xs_rows = rows addressable through xs        */
+  const void* res_s; int ldres_s; int res_s_lo;   /* residual rows in split form (ff3d_tmagemm; instead of res)            */
+  void* ys; int ldys; int ys_lo;   /* optional split copy of the output rows (both kernels); y may be NULL in ff3d_tmagemm  */
+  const int* y_row;                /* SPARSE, optional: output ROW of tile position m (strided convs over mask-sorted rows)  */
+  int zero_row;                    /* SPARSE + xs: index of an all-zero row of xs, read for absent neighbours                */
 } ff3d_gemm_desc;
 
 int ff3d_igemm(const ff3d_gemm_desc* desc, ff3d_stream_t stream);
@@ -190,6 +197,19 @@ int ff3d_tcgemm_stages(int cin, int taps);
 int ff3d_tcgemm_f16(const ff3d_gemm_desc* desc, const void* wimg16, int ntile, int* overflow_dev, ff3d_stream_t stream);
 int ff3d_tcgemm_f16_ntile(int cin, int cout);
 int ff3d_tcgemm_f16_stages(int cin, int taps);
+/* TMA-fed variant on PRE-SPLIT activations (desc->xs): the A operand is moved global -> swizzled shared memory by the TMA
+ * unit (2-D tile loads for ROWS, 4-D NHWC box loads with out-of-bounds zero fill for stride-1 CONV2D, tile::gather4 of the
+ * rulebook rows for SPARSE), no conversion and no producer warps; weights = the ff3d_tcgemm_f16 images.  Outputs: fp32 rows
+ * (y) and / or split rows (ys) for the next TMA layer; residual from fp32 (res) or split (res_s) rows.
+ * ff3d_tmagemm_supported: cin a multiple of 64, cout 64 or a multiple of 128, no x2, conv stride 1. */
+int ff3d_tmagemm(const ff3d_gemm_desc* desc, const void* wimg16, int ntile, int* overflow_dev, ff3d_stream_t stream);
+int ff3d_tmagemm_supported(const ff3d_gemm_desc* desc);
+void ff3d_tmagemm_conv_patch(int Ho, int Wo, int* bw_out, int* bh_out);
+/* fp32 rows [rows, C] -> split rows (for activations produced by non-GEMM kernels) and back (for non-GEMM consumers) */
+int ff3d_split_rows(const float* x, int ldx, const int* n_dev, long long rows, int C, void* ys, int ldys, int ys_lo,
+                    int* overflow_dev, ff3d_stream_t stream);
+int ff3d_unsplit_rows(const void* xs, int ldxs, int xs_lo, const int* n_dev, long long rows, int C, float* y, int ldy,
+                      ff3d_stream_t stream);
 
 /* Depthwise 3x3 stride 1 pad 1, NHWC, folded BN + activation (torchvision InvertedResidual dw conv,
  * focal_encoder.py:36-38). x [B,H,W,C] (ldx), w [9, C], bias [C]. */

@@ -661,3 +661,178 @@ def test_class_select():
         c_full += nc * k
         c_out += k
     assert torch.equal(out[:, c_out:c_out + nc], full[:, c_full:c_full + nc])
+
+
+# ------------------------------------------------------------------------------------------------ TMA-fed GEMM (split activations)
+def _split_ref(x):
+    """host restatement of the split format: (hi, lo) halves with x ~= hi + lo / 2048"""
+    hi = x.clamp(-65504, 65504).half()
+    lo = ((x - hi.float()) * 2048.0).clamp(-65504, 65504).half()
+    return hi, lo
+
+
+def test_split_rows_round_trip(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000, 192, generator=g) * torch.logspace(-6, 3, 192)[None]
+    xs = ops.split_rows(x.cuda(), zero_row=True)
+    assert xs.zero_row == 1000 and bool((xs.t[1000] == 0).all())
+    hi, lo = _split_ref(x)
+    assert torch.equal(xs.t[:1000, :192].cpu(), hi) and torch.equal(xs.t[:1000, 192:].cpu(), lo)
+    back = ops.unsplit_rows(xs, 1000).cpu()
+    assert ((back - x).abs() <= x.abs() * 2.0 ** -21 + 2.0 ** -36).all()
+    assert int(ops.gemm_flag().item()) == 0
+    ops.split_rows(torch.full((8, 64), 1.0e6, device="cuda"))            # beyond the fp16 range: the flag must trip
+    assert int(ops.gemm_flag().item()) == 1
+    ops.gemm_flag().zero_()
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 128, 128), (4096, 1024, 256), (129, 64, 64), (70000, 256, 128), (2400, 18816, 512)])
+def test_tma_linear_vs_fp64(ops, M, K, N):
+    """ff3d_tmagemm ROWS mode (2-D TMA tile loads of the split A rows): fp32-grade accuracy, fp32 + split outputs,
+    fp32 and split residuals."""
+    if not ops.tma_enabled():
+        pytest.skip("TMA path disabled (FF3D_GEMM=tf32 / FF3D_TMA=0)")
+    g = torch.Generator().manual_seed(M + K + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    pw = _pack_lin(w)
+    assert ops.tma_ok(pw, K, N)
+    xs = ops.split_rows(x.cuda())
+    xq = ops.unsplit_rows(xs, M).cpu().double()                          # the 22-bit values the kernel really multiplies
+    ref = xq @ w.double().t() + b.double()
+    ys = ops.Split.empty((M,), N, "cuda")
+    y = ops.linear(xs, pw, b.cuda(), act=1, res=res.cuda(), out_s=ys).cpu()
+    want = torch.relu(ref + res.double())
+    tol = 6e-5 * max(1.0, (K / 1024) ** 0.5)
+    assert (y.double() - want).abs().max().item() < tol
+    assert (ops.unsplit_rows(ys, M).cpu() - y).abs().max().item() <= (y.abs() * 2.0 ** -21 + 2.0 ** -30).max().item()
+    # split residual, split-only output, activation after the residual add disabled
+    rs = ops.split_rows(res.cuda())
+    rq = ops.unsplit_rows(rs, M).cpu().double()
+    ys2 = ops.Split.empty((M,), N, "cuda")
+    assert ops.linear(xs, pw, b.cuda(), act=1, res=rs, res_after_act=True, out_s=ys2, want_out=False) is None
+    want2 = torch.relu(ref) + rq
+    assert (ops.unsplit_rows(ys2, M).cpu().double() - want2).abs().max().item() < tol + 1e-5
+    assert int(ops.gemm_flag().item()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,k,H,W", [(64, 128, 3, 13, 11), (128, 128, 3, 32, 32), (256, 64, 1, 20, 17), (128, 256, 3, 45, 45),
+                                            (512, 128, 3, 24, 24), (64, 64, 7, 9, 30)])
+def test_tma_conv2d_vs_fp64(ops, cin, cout, k, H, W):
+    """ff3d_tmagemm CONV2D mode: 4-D TMA box loads, zero padding = out-of-bounds fill, patches that overhang the map."""
+    if not ops.tma_enabled():
+        pytest.skip("TMA path disabled")
+    g = torch.Generator().manual_seed(cin + cout + k + H)
+    B = 2
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (k * k * cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(B, cout, H, W, generator=g)
+    pw = _pack_conv(w)
+    assert ops.tma_ok(pw, cin, cout)
+    xs = ops.split_rows(x.permute(0, 2, 3, 1).contiguous().cuda())
+    xq = ops.unsplit_rows(xs, B * H * W).cpu().view(B, H, W, cin).permute(0, 3, 1, 2).double()
+    ref = F.conv2d(xq, w.double(), b.double(), padding=k // 2) + res.double()
+    out = torch.empty((B, H, W, cout), device="cuda")
+    ys = ops.Split.empty((B, H, W), cout, "cuda")
+    ops.conv2d(xs, pw, b.cuda(), out, k, act=2, res=res.permute(0, 2, 3, 1).contiguous().cuda(), out_s=ys)
+    want = ref.clamp(0, 6)
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    assert (got - want).abs().max().item() < 3e-5
+    back = ops.unsplit_rows(ys, B * H * W).cpu().view(B, H, W, cout).permute(0, 3, 1, 2)
+    assert (back.double() - got).abs().max().item() < 1e-5
+    assert int(ops.gemm_flag().item()) == 0
+
+
+def test_tma_conv2d_channel_slices(ops):
+    """concat-free views: the conv reads channels [64, 192) of a 256-channel split buffer and writes its fp32 and split
+    outputs into channel slices of wider buffers."""
+    if not ops.tma_enabled():
+        pytest.skip("TMA path disabled")
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 18, 21
+    x = torch.randn(B, H, W, 256, generator=g)
+    w = torch.randn(128, 128, 3, 3, generator=g) / (9 * 128) ** 0.5
+    pw = _pack_conv(w)
+    xs = ops.split_rows(x.cuda()).slice(64, 192)
+    xq = ops.unsplit_rows(xs, B * H * W).cpu().view(B, H, W, 128).permute(0, 3, 1, 2).double()
+    ref = F.conv2d(xq, w.double(), padding=1)
+    out = torch.zeros((B, H, W, 384), device="cuda")
+    out_s = ops.Split.empty((B, H, W), 384, "cuda")
+    out_s.t.zero_()
+    ops.conv2d(xs, pw, None, out[..., 128:256], 3, out_s=out_s.slice(256, 384))
+    assert (out[..., 128:256].permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item() < 3e-5
+    assert bool((out[..., :128] == 0).all()) and bool((out[..., 256:] == 0).all())
+    back = ops.unsplit_rows(out_s.slice(256, 384), B * H * W).cpu().view(B, H, W, 128).permute(0, 3, 1, 2)
+    assert (back.double() - ref).abs().max().item() < 1e-4
+    assert bool((out_s.t[..., :256] == 0).all()) and bool((out_s.t[..., 384:640] == 0).all())
+
+
+@pytest.mark.parametrize("Ci,Co", [(64, 64), (64, 128), (128, 128)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_tma_sparse_conv_matches_oracle(ops, Ci, Co, subm):
+    """ff3d_tmagemm SPARSE mode: tile::gather4 of the rulebook rows (absent neighbours -> the all-zero row), per-tile tap
+    skipping, row-mapped / split outputs and split residuals -- mask-sorted clustered level vs the oracle."""
+    if not ops.tma_enabled():
+        pytest.skip("TMA path disabled")
+    from oracle import sparse as osp
+    from focalformer3d_b200.model import pack_taps
+    g = torch.Generator().manual_seed(Ci + Co)
+    B, shape = 2, (9, 60, 60)
+    cells = []
+    for b in range(B):
+        yx = torch.randint(0, 60, (2500, 2), generator=g)
+        z = torch.randint(2, 5, (2500, 1), generator=g)
+        cells.append(torch.cat([torch.full((2500, 1), b), z, yx], 1))
+    idx = torch.unique(torch.cat(cells), dim=0).int()
+    idx = idx[torch.randperm(idx.shape[0], generator=g)]
+    n = idx.shape[0]
+    cap = n + 37
+    coors = torch.zeros((cap, 4), dtype=torch.int32)
+    coors[:n] = idx
+    feat = torch.randn(n, Ci, generator=g)
+    x = torch.zeros((cap, Ci))
+    x[:n] = feat
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    lvl = ops.SparseLevel(coors.cuda(), n_dev, cap, B, shape)
+    lvl.build_hash()
+    perm = lvl.sort_by_mask()
+    xg = ops.gather_rows(x.cuda(), perm, n_dev, Ci)
+    xs = ops.split_rows(xg, n_dev=n_dev, zero_row=True)
+    xq = ops.unsplit_rows(xs, cap, n_dev=n_dev).cpu()[:n]
+    sorted_idx = lvl.coors[:n].cpu()
+    k, s, p = ((3, 3, 3), (1, 1, 1), (1, 1, 1)) if subm else ((3, 3, 3), (2, 2, 2), (1, 1, 1))
+    wt = torch.randn(*k, Ci, Co, generator=g) / (27 * Ci) ** 0.5
+    bias = torch.randn(Co, generator=g)
+    oconv = osp.SpConv3d(Ci, Co, k, s[0], p[0], subm=subm)
+    oconv.weight.data.copy_(wt)
+    with torch.no_grad():
+        ref = oconv(osp.SparseTensor(xq, sorted_idx, shape, B))
+    wpk = pack_taps(wt.reshape(-1, Ci, Co), "cuda")
+    assert ops.tma_ok(wpk, Ci, Co)
+    if subm:
+        rb = lvl.subm_map()
+        ys = ops.Split.empty((cap,), Co, "cuda", zero_row=True)
+        if Ci == Co:                                                    # residual block: res = the split input itself
+            ops.sparse_conv(xs, rb, n_dev, wpk, bias.cuda(), None, act=1, res=xs, out_s=ys)
+            want = torch.relu(ref.features + bias + xq)
+        else:
+            ops.sparse_conv(xs, rb, n_dev, wpk, bias.cuda(), None, act=1, out_s=ys)
+            want = torch.relu(ref.features + bias)
+        got = ops.unsplit_rows(ys, cap, n_dev=n_dev).cpu()[:n]
+        assert (got - want).abs().max().item() < 1e-4                   # oracle rows are in (sorted) input order for SubM
+        assert bool((ys.t[cap] == 0).all())
+    else:
+        overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nl, rb = lvl.downsample(k, s, p, 4 * cap, overflow, ldy=Co)
+        no = int(nl.n_dev.item())
+        assert no == ref.indices.shape[0] and rb.y_row is not None
+        out = torch.zeros((nl.cap, Co), device="cuda")
+        ys = ops.Split.empty((nl.cap,), Co, "cuda", zero_row=True)
+        ops.sparse_conv(xs, rb, nl.n_dev, wpk, bias.cuda(), out, act=0, out_s=ys)
+        got = _to_dense(out.cpu(), nl.coors.cpu(), no, nl.shape, B)
+        want = _to_dense(ref.features + bias, ref.indices, no, ref.spatial_shape, B)
+        assert (got - want).abs().max().item() < 1e-4
+        back = ops.unsplit_rows(ys, nl.cap, n_dev=nl.n_dev).cpu()
+        assert (back[:no] - out.cpu()[:no]).abs().max().item() < 1e-5
+    assert int(ops.gemm_flag().item()) == 0
