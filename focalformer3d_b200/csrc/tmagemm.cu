@@ -23,6 +23,7 @@
 // Per-tile tap skipping (ff3d_sp_nbr_build masks) as in tcgemm.cu.  K-step = 64 halves = one 128-byte swizzled row.
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace ff3d {
 
@@ -71,8 +72,12 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-template <int MODE, int BN, int NS>
-__global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__ CUtensorMap tmA, const TmP p) {
+// NPW = producer warps.  ROWS / CONV2D need one (a single thread issues two box loads per stage).  SPARSE issues
+// 2 x 32 gather4 per stage, and a gather4 costs ~100 cycles of the issuing warp (measured: one producer warp delivers a
+// stage every ~6900 cycles against 768 cycles of MMA time), so the gathers of a stage are spread over NPW warps.
+template <int MODE, int BN, int NS, int NPW>
+__global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid_constant__ CUtensorMap tmA, const TmP p) {
+  constexpr int MMA_WARP = NPW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = TC_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
@@ -103,11 +108,11 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
   auto stage_count = [&](uint32_t um) -> int { return masked ? __popc(um) * p.cpt : p.n_stages; };
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(full_bar + 8u * s, 1); mbar_init(empty_bar + 8u * s, 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar + 8u * s, NPW); mbar_init(empty_bar + 8u * s, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8u * i, 1); mbar_init(tempty_bar + 8u * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "n"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -118,8 +123,9 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
   const uint32_t tmem_base = (uint32_t)lds32(tmem_ptr);
   const uint32_t a_tx = MODE == FF3D_GEMM_CONV2D ? 2u * (uint32_t)(p.bw * p.bh) * 128u : 2u * A_BYTES;
 
-  if (warp == 0) {
-    // =========================== producer: TMA issue only ===========================
+  if (warp < NPW) {
+    // =========================== producers: TMA issue only ===========================
+    constexpr int RPW = TC_BM / NPW;                              // SPARSE: tile rows gathered by each producer warp
     Ring ring{0, 0u};
     const uint8_t* wbase = static_cast<const uint8_t*>(p.wimg);
     const size_t stage_bytes = 2 * (size_t)B_BYTES;
@@ -142,8 +148,10 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
         const uint32_t bar = full_bar + 8u * ring.slot;
         if (lane == 0) {
           mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
-          mbar_arrive_expect_tx(bar, a_tx + 2 * B_BYTES);
-          bulk_g2s(slot_a + 2 * A_BYTES, wsrc + (size_t)(t * p.cpt + c) * stage_bytes, 2 * B_BYTES, bar);
+          // every producer warp announces its own bytes; warp 0 also owns the weight stage
+          const uint32_t a_bytes = MODE == FF3D_GEMM_SPARSE ? 2u * RPW * 128u : a_tx;
+          mbar_arrive_expect_tx(bar, a_bytes + (warp == 0 ? 2 * B_BYTES : 0u));
+          if (warp == 0) bulk_g2s(slot_a + 2 * A_BYTES, wsrc + (size_t)(t * p.cpt + c) * stage_bytes, 2 * B_BYTES, bar);
           if (MODE == FF3D_GEMM_ROWS) {
             tma_load_2d(slot_a, &tmA, c * 64, m0, bar);
             tma_load_2d(slot_a + A_BYTES, &tmA, p.xs_lo + c * 64, m0, bar);
@@ -155,16 +163,22 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
         }
         __syncwarp();
         if (MODE == FF3D_GEMM_SPARSE) {
-          // lane l gathers tile rows 4l .. 4l+3 (absent neighbour / row past the count -> the all-zero row)
-          int r[4];
-          const int* nb = p.nbr + (size_t)t * p.nbr_stride + m0 + 4 * lane;
+          // this warp gathers tile rows [warp*RPW, warp*RPW + RPW): work item = (plane, group of four rows); absent
+          // neighbours and rows past the count read the all-zero row
+          constexpr int GROUPS = RPW / 4;
+          for (int item = lane; item < 2 * GROUPS; item += 32) {
+            const int plane = item / GROUPS, g = item - plane * GROUPS;
+            const int row0 = warp * RPW + 4 * g;
+            int r[4];
+            const int* nb = p.nbr + (size_t)t * p.nbr_stride + m0 + row0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int v = (m0 + 4 * lane + i < Mv) ? __ldg(nb + i) : -1;
-            r[i] = v < 0 ? p.zero_row : v;
+            for (int i = 0; i < 4; ++i) {
+              int v = (m0 + row0 + i < Mv) ? __ldg(nb + i) : -1;
+              r[i] = v < 0 ? p.zero_row : v;
+            }
+            tma_gather4(slot_a + (uint32_t)plane * A_BYTES + (uint32_t)row0 * 128u, &tmA, plane * p.xs_lo + c * 64, r[0], r[1],
+                        r[2], r[3], bar);
           }
-          tma_gather4(slot_a + (uint32_t)lane * 512u, &tmA, c * 64, r[0], r[1], r[2], r[3], bar);
-          tma_gather4(slot_a + A_BYTES + (uint32_t)lane * 512u, &tmA, p.xs_lo + c * 64, r[0], r[1], r[2], r[3], bar);
         }
         ring.advance(1, NS);
       };
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
           for (int c = 0; c < p.cpt; ++c) issue(t, c);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc_wide = make_idesc<true>(2 * BN), idesc_cross = make_idesc<true>(BN);
@@ -210,7 +224,7 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
     }
     __syncwarp();
   } else {
-    // =========================== epilogue (warps 2-5: TMEM lane quarter = warp % 4) ===========================
+    // =========================== epilogue (four warps: TMEM lane quarter = warp % 4) ===========================
     const int r = (warp & 3) * 32 + lane;                     // tile row <-> TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     bool ovf = false;
@@ -320,7 +334,7 @@ __global__ void __launch_bounds__(192, 1) tmagemm_kernel(const __grid_constant__
     if (ovf && p.overflow) atomicOr(p.overflow, 1);
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -405,19 +419,42 @@ static int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_
   return FF3D_OK;
 }
 
-template <int MODE, int BN>
-static int launch_tm(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
+template <int MODE, int BN, int NPW>
+static int launch_tm_cfg(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
   constexpr int NS = BN == 128 ? 3 : 4;
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
   const size_t smem = NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + 1024;
   static const cudaError_t attr =
-      cudaFuncSetAttribute(tmagemm_kernel<MODE, BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(tmagemm_kernel<MODE, BN, NS, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr != cudaSuccess) { set_error("ff3d_tmagemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr)); return FF3D_ECUDA; }
   const long long tiles = m_tiles * (p.cout / BN);
   const long long resident = num_sms();
   dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-  tmagemm_kernel<MODE, BN, NS><<<grid, 192, smem, st>>>(tm, p);
+  tmagemm_kernel<MODE, BN, NS, NPW><<<grid, 32 * (NPW + 5), smem, st>>>(tm, p);
   return check_launch("ff3d_tmagemm");
+}
+
+// producer warps of the SPARSE gather (FF3D_TMA_NPW = 1 / 4 / 8, read once)
+static int sparse_npw() {
+  static const int v = []() {
+    const char* e = getenv("FF3D_TMA_NPW");
+    const int n = e ? atoi(e) : 8;
+    return (n == 1 || n == 4 || n == 8) ? n : 8;
+  }();
+  return v;
+}
+
+template <int MODE, int BN>
+static int launch_tm(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
+  if constexpr (MODE == FF3D_GEMM_SPARSE) {
+    switch (sparse_npw()) {
+      case 1: return launch_tm_cfg<MODE, BN, 1>(tm, p, m_tiles, st);
+      case 4: return launch_tm_cfg<MODE, BN, 4>(tm, p, m_tiles, st);
+      default: return launch_tm_cfg<MODE, BN, 8>(tm, p, m_tiles, st);
+    }
+  } else {
+    return launch_tm_cfg<MODE, BN, 1>(tm, p, m_tiles, st);
+  }
 }
 
 template <int MODE>

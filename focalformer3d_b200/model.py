@@ -1036,7 +1036,17 @@ class FocalDecoder(ParamTree):
         bc = self.bbox_coder
         ops.box_decode(st["last"], self._cls_col, self.has_vel, st["q_score"], st["q_label"], self.num_classes, bc.cell,
                        bc.pc_range, bc.post_center_range, boxes, scores, labels, keep)
-        return boxes.view(B, nq, code), scores.view(B, nq), labels.view(B, nq), keep.view(B, nq)
+        boxes, scores, labels, keep = boxes.view(B, nq, code), scores.view(B, nq), labels.view(B, nq), keep.view(B, nq)
+        if self.nms_type is not None:                                              # focal_decoder.py:1333-1385
+            if self.test_cfg["dataset"] == "nuScenes":
+                tasks = [(list(range(8)), -1.0), ([8], 0.175), ([9], 0.175)]
+            elif self.test_cfg["dataset"] == "Waymo":
+                tasks = [([0], 0.7), ([1], 0.7), ([2], 0.7)]
+            else:
+                raise NotImplementedError("FocalDecoder.get_bboxes: NMS tasks are defined for nuScenes and Waymo only")
+            keep = ops.nms_tasks(boxes, scores, labels, keep, tasks, self.nms_type, self.test_cfg.get("pre_maxsize"),
+                                 self.test_cfg.get("post_maxsize"))
+        return boxes, scores, labels, keep
 
 
 @DETECTORS.register_module()

@@ -432,8 +432,9 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     d.x_bstride, d.y_bstride, d.y_row0 = xbs, ybs, 0
     d.ux, d.uy, d.dx, d.dy = u, u, dx, dy
     if out_s is not None:
-        if out_s.t.dim() != 4 or tuple(out_s.t.shape[:3]) != (B, Ho, Wo) or u != 1 or (out is not None and ybs != Ho * Wo):
-            raise L.Ff3dError("conv2d: the split output is a batch-dense [B, Ho, Wo, 2C] buffer")
+        if out_s.t.dim() != 4 or tuple(out_s.t.shape[:3]) != (B, Ho * u, Wo * u) or (out is not None and ybs != Ho * u * Wo * u) \
+                or (split_in and u != 1):
+            raise L.Ff3dError("conv2d: the split output is a batch-dense [B, Ho*u, Wo*u, 2C] buffer (same rows as out)")
         _attach_split(d, out_s=out_s)
     t0 = prof.begin()
     _gemm_any(d, w, "conv2d", split_in)
@@ -840,3 +841,70 @@ def box_decode(pred, cls_col, has_vel, query_score, query_label, Cc, cell, origi
                               float(origin[1]), L.float_array(post_range), _ptr(boxes), _ptr(scores), _ptr(labels),
                               _ptr(keep), _stream()), "ff3d_box_decode")
     _count()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# output side
+def nms_tasks(boxes, scores, labels, keep, tasks, nms_type, pre_max=0, post_max=0):
+    """Per-task circle / rotated NMS of get_bboxes (focal_decoder.py:1333-1393).  boxes [B,nq,code], scores / labels /
+    keep [B,nq]; tasks = [(class indices, radius), ...].  Returns keep_out [B,nq] uint8."""
+    B, nq, ld = boxes.shape
+    out = torch.empty((B, nq), dtype=torch.uint8, device=boxes.device)
+    masks = (C.c_uint * len(tasks))(*[sum(1 << c for c in idx) for idx, _ in tasks])
+    radii = L.float_array([r for _, r in tasks])
+    mode = {"circle": 0, "rotate": 1}[nms_type]
+    if mode == 0:
+        post_max = 83                                   # [upstream] circle_nms(dets, thresh, post_max_size=83)
+    check(lib.ff3d_nms_tasks(_ptr(boxes), ld, _ptr(scores), _ptr(labels), _ptr(keep), B, nq, len(tasks), masks, radii, mode,
+                             int(pre_max or 0), int(post_max or 0), _ptr(out), _stream()), "ff3d_nms_tasks")
+    _count(2)
+    return out
+
+
+def boxes_iou_bev(a, b):
+    """Rotated BEV IoU of (x, y, z, dx, dy, dz, yaw, ...) rows: [n, m]."""
+    n, m = a.shape[0], b.shape[0]
+    out = torch.empty((n, m), dtype=torch.float32, device=a.device)
+    check(lib.ff3d_boxes_iou_bev(_ptr(a), a.stride(0), n, _ptr(b), b.stride(0), m, _ptr(out), _stream()), "ff3d_boxes_iou_bev")
+    _count()
+    return out
+
+
+def merge_aug_bboxes_3d(aug_results, img_metas, nms_thr=0.1, max_num=500, vote_iou_thresh=0.65, dev="cuda"):
+    """Test-time-augmentation merge (core/post_processing/merge_augs.py:14-184, the live branch): map every augmented
+    result back (flips, scale), per-class rotated NMS (thr 0.1), IoU-weighted box voting (>= 0.65), best max_num by score.
+    aug_results: list of dict(boxes_3d [n, 7|9], scores_3d [n], labels_3d [n]); img_metas: list of dict(pcd_scale_factor,
+    pcd_horizontal_flip, pcd_vertical_flip).  Returns the merged dict (device tensors)."""
+    boxes = []
+    for r, m in zip(aug_results, img_metas):
+        b = r["boxes_3d"].to(dev, torch.float32).contiguous().clone()
+        check(lib.ff3d_boxes_map_back(_ptr(b), b.stride(0), b.shape[1], b.shape[0], float(m.get("pcd_scale_factor", 1.0)),
+                                      int(bool(m.get("pcd_horizontal_flip", False))), int(bool(m.get("pcd_vertical_flip", False))),
+                                      _stream()), "ff3d_boxes_map_back")
+        _count()
+        boxes.append(b)
+    boxes = torch.cat(boxes)
+    scores = torch.cat([r["scores_3d"].to(dev, torch.float32) for r in aug_results]).contiguous()
+    labels = torch.cat([r["labels_3d"].to(dev) for r in aug_results]).int().contiguous()
+    n, dim = boxes.shape
+    if n == 0:
+        return dict(boxes_3d=boxes, scores_3d=scores, labels_3d=labels)
+    if n > 1024:
+        raise L.Ff3dError(f"merge_aug_bboxes_3d: {n} boxes (<= 1024 supported)")
+    n_cls = int(labels.max().item()) + 1                      # merge_augs.py:136 (a host decision in the reference too)
+    keep_in = torch.ones((1, n), dtype=torch.uint8, device=dev)
+    keep = nms_tasks(boxes.view(1, n, dim), scores.view(1, n), labels.view(1, n), keep_in,
+                     [([c], nms_thr) for c in range(min(n_cls, 8))], "rotate")
+    if n_cls > 8:
+        raise L.Ff3dError("merge_aug_bboxes_3d: more than 8 classes")
+    sel = keep[0].bool()
+    sb, ss, sl = boxes[sel].contiguous(), scores[sel], labels[sel]
+    iou = boxes_iou_bev(sb, boxes)
+    iou = iou * (sl[:, None] == labels[None, :]).float()      # voting runs per class (merge_augs.py:137-148)
+    voted = torch.empty((sb.shape[0], dim), dtype=torch.float32, device=dev)
+    check(lib.ff3d_box_voting(_ptr(iou), sb.shape[0], n, _ptr(boxes), boxes.stride(0), dim, float(vote_iou_thresh), _ptr(voted),
+                              _stream()), "ff3d_box_voting")
+    _count()
+    # per class the reference keeps NMS order (score descending); then a global score sort (merge_augs.py:176-178)
+    order = ss.argsort(descending=True, stable=True)[:min(max_num, n)]
+    return dict(boxes_3d=voted[order], scores_3d=ss[order], labels_3d=sl[order])

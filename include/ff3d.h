@@ -293,6 +293,48 @@ int ff3d_box_decode(const float* pred, int ldp, int cls_col, int has_vel, const 
                     const float* post_range6, float* boxes, float* scores, int* labels, unsigned char* keep,
                     ff3d_stream_t stream);
 
+/* ---- input side -------------------------------------------------------------------------------
+ * Multi-sweep point assembly on the device.  Replaces: [upstream] mmdet3d v0.17.1 LoadPointsFromMultiSweeps (test mode) and
+ * PointsRangeFilter of the data pipeline (projects/configs/focalformer3d/FocalFormer3D_L.py:100-111).
+ * raw [n_total, n_feat_in] = the key frame followed by the sweeps as loaded from the files (x, y, z, intensity, ...);
+ * sweep_offsets (HOST) [n_sweeps+1]; per sweep (HOST): rot [9] row-major sensor2lidar_rotation and trans [3] (float64, as in
+ * the info files), dt (time lag written to column 4), remove_close (drop |x| < r and |y| < r), transform (apply rot / trans).
+ * range6 (may be NULL): PointsRangeFilter bounds (strict).  out [n_total, 5]: dropped points are overwritten with pad_value
+ * (outside every point_cloud_range, so the voxeliser discards them) instead of being compacted away: order and size fixed. */
+int ff3d_assemble_sweeps(const float* raw, int n_feat_in, const int* sweep_offsets_host, int n_sweeps, const double* rot_host,
+                         const double* trans_host, const float* dt_host, const unsigned char* remove_close_host,
+                         const unsigned char* transform_host, float close_radius, const float* range6_host, float pad_value,
+                         float* out, ff3d_stream_t stream);
+/* Camera frames: uint8 [n, H, W, 3] (BGR, as cv2 decodes them) -> float32 planar [n, 3, pad_h, pad_w]: bilinear resize to
+ * (out_h, out_w) with cv2.INTER_LINEAR's float arithmetic, BGR->RGB, (x - mean) * (1 / std), zero padding to a multiple of
+ * size_divisor.  Replaces LoadMultiViewImageFromFiles(to_float32) + ScaleImageMultiViewImage + NormalizeMultiviewImage +
+ * PadMultiViewImage + DefaultFormatBundle3D (projects/mmdet3d_plugin/datasets/pipelines/transform_3d.py:125-249). */
+int ff3d_image_preprocess(const unsigned char* img, int n, int H, int W, int out_h, int out_w, const float* mean3,
+                          const float* std3, int to_rgb, int size_divisor, float* out, int pad_h, int pad_w,
+                          ff3d_stream_t stream);
+
+/* ---- output side ------------------------------------------------------------------------------
+ * Per-task NMS of get_bboxes when test_cfg.nms_type is set (focal_decoder.py:1333-1393): task t owns the classes of
+ * class_masks[t] (bit c); radius[t] <= 0 keeps every box of the task (:1376).
+ *   mode 0 'circle': [upstream] mmdet3d.core.circle_nms -- score-descending greedy, a kept box suppresses boxes whose SQUARED
+ *     centre distance is <= radius[t]; at most post_max (83 = the upstream default) boxes per task.
+ *   mode 1 'rotate': [upstream] mmdet3d.ops.iou3d nms_gpu on xywhr2xyxyr(boxes.bev) -- the pre_max best boxes, rotated-BEV
+ *     IoU > radius[t] suppresses, at most post_max kept.
+ * boxes [B, nq, box_ld] = (x, y, z, dx, dy, dz, yaw, ...), scores / labels / keep_in [B, nq]; keep_out [B, nq] uint8 =
+ * keep_in AND survived.  nq <= 1024. */
+int ff3d_nms_tasks(const float* boxes, int box_ld, const float* scores, const int* labels, const unsigned char* keep_in,
+                   int B, int nq, int n_tasks, const unsigned int* class_masks_host, const float* radius_host, int mode,
+                   int pre_max, int post_max, unsigned char* keep_out, ff3d_stream_t stream);
+/* [upstream] mmdet3d.ops.iou3d boxes_iou_bev on (x, y, z, dx, dy, dz, yaw, ...) rows: iou [n, m] (merge_augs.py:148) */
+int ff3d_boxes_iou_bev(const float* a, int lda, int n, const float* b, int ldb, int m, float* iou, ff3d_stream_t stream);
+/* box voting of the TTA merge (merge_augs.py:149-157): out[i, :dim] = sum_j w_ij box_j / (sum_j w_ij + 1e-6) with
+ * w = iou zeroed below vote_thresh; yaw = atan2 of the weighted sine / cosine sums. */
+int ff3d_box_voting(const float* iou, int n_sel, int m, const float* boxes, int ld, int dim, float vote_thresh, float* out,
+                    ff3d_stream_t stream);
+/* [upstream] mmdet3d bbox3d_mapping_back for LiDAR boxes (merge_augs.py:91-94), in place */
+int ff3d_boxes_map_back(float* boxes, int ld, int dim, int n, float scale_factor, int flip_horizontal, int flip_vertical,
+                        ff3d_stream_t stream);
+
 /* ---- camera branch (DeformFormer3D_C_R50) -------------------------------------------------
  * Image repack for the NHWC convolution path: x [n, C, H, W] planar (what extract_img_feat receives,
  * focalformer3d.py:133-141) -> y [n, H, W, ld], channels [C, ld) zero (ld % 4 == 0). */

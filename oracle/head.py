@@ -431,12 +431,201 @@ class FocalDecoder(nn.Module):
         vel = p["vel"][..., -nq:].clone() if "vel" in p else None
         temp = self.bbox_coder.decode(score, p["rot"][..., -nq:].clone(), p["dim"][..., -nq:].clone(),
                                       p["center"][..., -nq:].clone(), p["height"][..., -nq:].clone(), vel, filter=True)
-        assert self.test_cfg.get("nms_type") is None
+        nms_type = self.test_cfg.get("nms_type")
+        if self.test_cfg["dataset"] == "nuScenes":                                # :1333-1338
+            tasks = [dict(indices=[0, 1, 2, 3, 4, 5, 6, 7], radius=-1), dict(indices=[8], radius=0.175), dict(indices=[9], radius=0.175)]
+        else:                                                                     # 'Waymo' :1339-1344
+            tasks = [dict(indices=[0], radius=0.7), dict(indices=[1], radius=0.7), dict(indices=[2], radius=0.7)]
         out = []
         for t in temp:
             b, s, l = t["bboxes"], t["scores"], t["labels"]
+            if nms_type is not None:                                              # :1352-1385
+                keep_mask = torch.zeros_like(s)
+                for task in tasks:
+                    task_mask = torch.zeros_like(s)
+                    for cls_idx in task["indices"]:
+                        task_mask += l == cls_idx
+                    task_mask = task_mask.bool()
+                    if task["radius"] > 0:
+                        if nms_type == "circle":
+                            dets = torch.cat([b[task_mask][:, :2], s[:, None][task_mask]], dim=1).numpy()
+                            keep_idx = torch.tensor(circle_nms(dets, task["radius"]), dtype=torch.long)
+                        else:
+                            keep_idx = nms_rotated_bev(xywhr2xyxyr(b[task_mask][:, [0, 1, 3, 4, 6]]), s[task_mask], task["radius"],
+                                                       self.test_cfg.get("pre_maxsize"), self.test_cfg.get("post_maxsize"))
+                    else:
+                        keep_idx = torch.arange(int(task_mask.sum()))
+                    if keep_idx.shape[0] != 0:
+                        keep_mask[torch.where(task_mask != 0)[0][keep_idx]] = 1
+                keep_mask = keep_mask.bool()
+                full_keep = t["keep"].clone()
+                full_keep[t["keep"].nonzero().flatten()[~keep_mask]] = False
+                b, s, l = b[keep_mask], s[keep_mask], l[keep_mask]
+                t = dict(t, keep=full_keep)
             if len(b) > 200:
                 inds = s.argsort(descending=True, stable=True)[:200]
                 b, s, l = b[inds], s[inds], l[inds]
             out.append(dict(boxes_3d=b, scores_3d=s, labels_3d=l.int(), keep=t["keep"]))
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# [upstream] post-processing the head calls when test_cfg.nms_type is set (focal_decoder.py:1352-1385) and the TTA merge
+# (core/post_processing/merge_augs.py:111-184): mmdet3d v0.17.1 core.circle_nms, ops.iou3d nms_gpu / boxes_iou_bev.
+def circle_nms(dets, thresh, post_max_size=83):
+    """mmdet3d.core.post_processing.circle_nms (numba): dets [n, 3] = (x, y, score); a kept box suppresses every lower
+    scored box whose SQUARED centre distance is <= thresh; at most post_max_size boxes are kept."""
+    import numpy as np
+    x1, y1, scores = dets[:, 0], dets[:, 1], dets[:, 2]
+    order = scores.argsort()[::-1].astype(np.int32)
+    ndets = dets.shape[0]
+    suppressed = np.zeros((ndets), dtype=np.int32)
+    keep = []
+    for _i in range(ndets):
+        i = order[_i]
+        if suppressed[i] == 1:
+            continue
+        keep.append(int(i))
+        for _j in range(_i + 1, ndets):
+            j = order[_j]
+            if suppressed[j] == 1:
+                continue
+            dist = (x1[i] - x1[j]) ** 2 + (y1[i] - y1[j]) ** 2
+            if dist <= thresh:
+                suppressed[j] = 1
+    return keep[:post_max_size] if post_max_size < len(keep) else keep
+
+
+def xywhr2xyxyr(b):
+    """mmdet3d.core.bbox.xywhr2xyxyr: (x, y, w, h, r) -> (x1, y1, x2, y2, r)."""
+    o = torch.zeros_like(b)
+    hw, hh = b[:, 2] / 2, b[:, 3] / 2
+    o[:, 0], o[:, 1], o[:, 2], o[:, 3], o[:, 4] = b[:, 0] - hw, b[:, 1] - hh, b[:, 0] + hw, b[:, 1] + hh, b[:, 4]
+    return o
+
+
+def _rot_overlap(a, b):
+    """iou3d_kernel.cu box_overlap: intersection area of two rotated rectangles (x1, y1, x2, y2, angle) -- corners of
+    each box inside the other plus the edge/edge intersection points, sorted by angle around their centre, fan area."""
+    import math
+
+    def corners(r):
+        cx, cy = (r[0] + r[2]) / 2, (r[1] + r[3]) / 2
+        c, s = math.cos(r[4]), math.sin(r[4])
+        pts = []
+        for x, y in ((r[0], r[1]), (r[2], r[1]), (r[2], r[3]), (r[0], r[3])):
+            dx, dy = x - cx, y - cy
+            pts.append((cx + dx * c - dy * s, cy + dx * s + dy * c))
+        return pts, (cx, cy, c, s, (r[2] - r[0]) / 2, (r[3] - r[1]) / 2)
+
+    def inside(p, f):
+        cx, cy, c, s, hx, hy = f
+        dx, dy = p[0] - cx, p[1] - cy
+        u, v = dx * c + dy * s, -dx * s + dy * c
+        return abs(u) <= hx + 1e-9 and abs(v) <= hy + 1e-9
+
+    def seg_x(p0, p1, q0, q1):
+        d = (p1[0] - p0[0]) * (q1[1] - q0[1]) - (p1[1] - p0[1]) * (q1[0] - q0[0])
+        if abs(d) < 1e-12:
+            return None
+        t = ((q0[0] - p0[0]) * (q1[1] - q0[1]) - (q0[1] - p0[1]) * (q1[0] - q0[0])) / d
+        u = ((q0[0] - p0[0]) * (p1[1] - p0[1]) - (q0[1] - p0[1]) * (p1[0] - p0[0])) / d
+        if 0 <= t <= 1 and 0 <= u <= 1:
+            return (p0[0] + t * (p1[0] - p0[0]), p0[1] + t * (p1[1] - p0[1]))
+        return None
+    ca, fa = corners(a)
+    cb, fb = corners(b)
+    pts = [p for p in ca if inside(p, fb)] + [p for p in cb if inside(p, fa)]
+    for i in range(4):
+        for j in range(4):
+            x = seg_x(ca[i], ca[(i + 1) % 4], cb[j], cb[(j + 1) % 4])
+            if x is not None:
+                pts.append(x)
+    if len(pts) < 3:
+        return 0.0
+    mx, my = sum(p[0] for p in pts) / len(pts), sum(p[1] for p in pts) / len(pts)
+    pts.sort(key=lambda p: math.atan2(p[1] - my, p[0] - mx))
+    area = 0.0
+    for i in range(len(pts)):
+        p, q = pts[i], pts[(i + 1) % len(pts)]
+        area += (p[0] - mx) * (q[1] - my) - (q[0] - mx) * (p[1] - my)
+    return abs(area) / 2
+
+
+def boxes_iou_bev(a, b):
+    """mmdet3d.ops.iou3d boxes_iou_bev: [n, 5] x [m, 5] (x1, y1, x2, y2, r) -> IoU [n, m]."""
+    out = torch.zeros(a.shape[0], b.shape[0])
+    al, bl = a.double().tolist(), b.double().tolist()
+    for i, x in enumerate(al):
+        sa = (x[2] - x[0]) * (x[3] - x[1])
+        for j, y in enumerate(bl):
+            sb = (y[2] - y[0]) * (y[3] - y[1])
+            inter = _rot_overlap(x, y)
+            out[i, j] = inter / max(sa + sb - inter, 1e-8)
+    return out
+
+
+def nms_rotated_bev(boxes, scores, thresh, pre_maxsize=None, post_max_size=None):
+    """mmdet3d.ops.iou3d nms_gpu: score-descending greedy NMS on rotated BEV IoU (> thresh suppresses)."""
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    bl = boxes[order]
+    iou = boxes_iou_bev(bl, bl)
+    n = bl.shape[0]
+    sup, keep = [False] * n, []
+    for i in range(n):
+        if sup[i]:
+            continue
+        keep.append(i)
+        for j in range(i + 1, n):
+            if not sup[j] and iou[i, j] > thresh:
+                sup[j] = True
+    keep = order[torch.tensor(keep, dtype=torch.long)] if keep else order[:0]
+    if post_max_size is not None:
+        keep = keep[:post_max_size]
+    return keep
+
+
+def merge_aug_bboxes_3d(aug_results, img_metas, nms_thr=0.1, max_num=500, vote_iou_thresh=0.65):
+    """merge_augs.py:14-184 (the live branch: aug_results given, rotate NMS, box voting without score voting).
+    aug_results: list of dict(boxes_3d [n, 7|9] tensor, scores_3d, labels_3d); img_metas: list of
+    dict(pcd_scale_factor, pcd_horizontal_flip, pcd_vertical_flip)."""
+    import math
+    rec = []
+    for r, m in zip(aug_results, img_metas):
+        b = r["boxes_3d"].clone()
+        if m.get("pcd_horizontal_flip", False):
+            b[:, 1::7] = -b[:, 1::7]
+            b[:, 6] = -b[:, 6] + math.pi
+        if m.get("pcd_vertical_flip", False):
+            b[:, 0::7] = -b[:, 0::7]
+            b[:, 6] = -b[:, 6]
+        sf = 1.0 / m.get("pcd_scale_factor", 1.0)
+        b[:, :6] *= sf
+        b[:, 7:] *= sf
+        rec.append(b)
+    boxes = torch.cat(rec)
+    scores = torch.cat([r["scores_3d"] for r in aug_results])
+    labels = torch.cat([r["labels_3d"] for r in aug_results]).long()
+    if labels.numel() == 0:
+        return dict(boxes_3d=boxes, scores_3d=scores, labels_3d=labels)
+    nmsb = xywhr2xyxyr(boxes[:, [0, 1, 3, 4, 6]])
+    mb, ms, ml = [], [], []
+    for c in range(int(labels.max()) + 1):
+        ci = labels == c
+        if int(ci.sum()) == 0:
+            continue
+        bi, ni, si, li = boxes[ci], nmsb[ci], scores[ci], labels[ci]
+        sel = nms_rotated_bev(ni, si, nms_thr)
+        iou = boxes_iou_bev(xywhr2xyxyr(bi[sel][:, [0, 1, 3, 4, 6]]), ni)
+        iou[iou < vote_iou_thresh] = 0.0
+        voted = (iou[:, :, None] * bi[None]).sum(1) / (iou[:, :, None].sum(1) + 1e-6)
+        voted[:, 6] = torch.atan2((iou * torch.sin(bi[None, :, 6])).sum(1) / (iou.sum(1) + 1e-6),
+                                  (iou * torch.cos(bi[None, :, 6])).sum(1) / (iou.sum(1) + 1e-6))
+        mb.append(voted)
+        ms.append(si[sel])
+        ml.append(li[sel])
+    mb, ms, ml = torch.cat(mb), torch.cat(ms), torch.cat(ml)
+    order = ms.sort(0, descending=True)[1][:min(max_num, boxes.shape[0])]
+    return dict(boxes_3d=mb[order], scores_3d=ms[order], labels_3d=ml[order])

@@ -350,3 +350,30 @@ def test_waymo_full_size_properties():
     assert boxes.shape == (2, 600, 7) and torch.isfinite(boxes).all()
     tops = [set(t[0].tolist()) for t in res["_top_proposals"]]
     assert all(len(t) == 200 for t in tops) and not (tops[0] & tops[1]) and not (tops[1] & tops[2]) and not (tops[0] & tops[2])
+
+
+@pytest.mark.parametrize("nms_type", ["circle", "rotate"])
+def test_get_bboxes_with_nms(tiny_cfg, tiny_sd, tiny_points, nms_type):
+    """test_cfg.nms_type = 'circle' / 'rotate' (focal_decoder.py:1352-1385): the per-task NMS keep flags and the final
+    box list of the CUDA head equal the oracle's."""
+    import copy
+    from focalformer3d_b200.model import build_model
+    from oracle.detector import build_oracle
+    from oracle import parity
+    cfg = copy.deepcopy(tiny_cfg)
+    cfg["test_cfg"]["pts"].update(nms_type=nms_type, pre_maxsize=1000, post_maxsize=83)
+    model = build_model(cfg)
+    model.load_state_dict(tiny_sd, strict=True)
+    model.prepare("cuda")
+    res, det, _ = model.forward_raw([p.cuda() for p in tiny_points])
+    oracle = build_oracle(cfg)
+    oracle.load_state_dict(tiny_sd, strict=True)
+    ref, rdet = oracle.forward_raw(tiny_points)
+    rep = parity.head_report(res, det, oracle.pts_bbox_head, ref, rdet)
+    assert rep["topk_sets_equal"] and rep["keep_equal"] and rep["box_labels_equal"], rep
+    assert rep["max_abs"]["boxes"] < TOL and rep["max_abs"]["scores"] < TOL, rep
+    base = build_model(tiny_cfg)
+    base.load_state_dict(tiny_sd, strict=True)
+    base.prepare("cuda")
+    _, det0, _ = base.forward_raw([p.cuda() for p in tiny_points])
+    assert int(det[3].sum()) <= int(det0[3].sum())                       # NMS only ever removes boxes

@@ -836,3 +836,84 @@ def test_tma_sparse_conv_matches_oracle(ops, Ci, Co, subm):
         back = ops.unsplit_rows(ys, nl.cap, n_dev=nl.n_dev).cpu()
         assert (back[:no] - out.cpu()[:no]).abs().max().item() < 1e-5
     assert int(ops.gemm_flag().item()) == 0
+
+
+# ------------------------------------------------------------------------------------------------ output side (NMS, TTA merge)
+def _rand_boxes(n, seed, spread=12.0):
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.rand(n // 4 + 1, 2, generator=g) * spread - spread / 2
+    xy = centres[torch.randint(0, centres.shape[0], (n,), generator=g)] + torch.randn(n, 2, generator=g) * 0.6
+    z = torch.randn(n, 1, generator=g) * 0.2
+    dims = torch.rand(n, 3, generator=g) * torch.tensor([3.0, 1.5, 1.0]) + torch.tensor([0.8, 0.5, 0.8])
+    yaw = (torch.rand(n, 1, generator=g) - 0.5) * 6.2
+    vel = torch.randn(n, 2, generator=g)
+    return torch.cat([xy, z, dims, yaw, vel], 1)
+
+
+def test_boxes_iou_bev_matches_oracle(ops):
+    from oracle.head import boxes_iou_bev, xywhr2xyxyr
+    a, b = _rand_boxes(40, 1), _rand_boxes(50, 2)
+    b[:5] = a[:5]                                            # identical boxes: IoU 1
+    b[5, :2] = a[5, :2]; b[5, 3:6] = a[5, 3:6] * 0.5; b[5, 6] = a[5, 6]      # contained, same yaw: IoU 0.25
+    got = ops.boxes_iou_bev(a.cuda(), b.cuda()).cpu()
+    want = boxes_iou_bev(xywhr2xyxyr(a[:, [0, 1, 3, 4, 6]]), xywhr2xyxyr(b[:, [0, 1, 3, 4, 6]]))
+    assert (got - want).abs().max().item() < 1e-4
+    assert (got[:5].diagonal() - 1).abs().max().item() < 1e-5 and abs(got[5, 5].item() - 0.25) < 1e-5
+
+
+@pytest.mark.parametrize("nms_type,dataset", [("circle", "nuScenes"), ("rotate", "nuScenes"), ("circle", "Waymo"), ("rotate", "Waymo")])
+def test_nms_tasks_match_oracle(ops, nms_type, dataset):
+    """ff3d_nms_tasks vs the reference's per-task loop (focal_decoder.py:1352-1385) on [upstream] circle_nms / nms_gpu."""
+    from oracle.head import circle_nms, nms_rotated_bev, xywhr2xyxyr
+    B, nq = 2, 300
+    nc = 10 if dataset == "nuScenes" else 3
+    tasks = [(list(range(8)), -1.0), ([8], 0.175), ([9], 0.175)] if dataset == "nuScenes" else [([0], 0.7), ([1], 0.7), ([2], 0.7)]
+    g = torch.Generator().manual_seed(7)
+    boxes = torch.stack([_rand_boxes(nq, 10 + b, spread=6.0) for b in range(B)])
+    scores = torch.rand(B, nq, generator=g)
+    labels = torch.randint(0, nc, (B, nq), generator=g)
+    if dataset == "nuScenes":
+        labels[:, :200] = torch.randint(8, 10, (B, 200), generator=g)       # plenty of pedestrians / cones close together
+    keep_in = torch.rand(B, nq, generator=g) > 0.1
+    pre, post = 150, 40
+    got = ops.nms_tasks(boxes.cuda(), scores.cuda(), labels.int().cuda(), keep_in.to(torch.uint8).cuda(), tasks, nms_type, pre, post).cpu().bool()
+    for b in range(B):
+        want = torch.zeros(nq, dtype=torch.bool)
+        for idx, radius in tasks:
+            tm = keep_in[b] & torch.isin(labels[b], torch.tensor(idx))
+            rows = tm.nonzero().flatten()
+            if radius <= 0:
+                want[rows] = True
+            elif nms_type == "circle":
+                dets = torch.cat([boxes[b][rows][:, :2], scores[b][rows][:, None]], 1).numpy()
+                want[rows[torch.tensor(circle_nms(dets, radius), dtype=torch.long)]] = True
+            else:
+                k = nms_rotated_bev(xywhr2xyxyr(boxes[b][rows][:, [0, 1, 3, 4, 6]]), scores[b][rows], radius, pre, post)
+                want[rows[k]] = True
+        assert torch.equal(got[b], want), f"{nms_type}/{dataset} scene {b}: {(got[b] != want).sum().item()} keep flags differ"
+    assert bool((got <= keep_in).all())
+
+
+def test_merge_aug_bboxes_matches_oracle(ops):
+    """TTA merge (merge_augs.py:14-184): map back flips / scale, per-class rotated NMS, box voting."""
+    from oracle.head import merge_aug_bboxes_3d
+    base = _rand_boxes(60, 3, spread=20.0)
+    g = torch.Generator().manual_seed(5)
+    augs, metas = [], []
+    for hf, vf, sf in ((False, False, 1.0), (True, False, 1.0), (False, True, 0.95), (True, True, 1.05)):
+        b = base.clone() + torch.randn(60, 9, generator=g) * 0.03
+        b[:, :6] *= sf; b[:, 7:] *= sf                       # forward augmentation: scale, then flips
+        if vf:
+            b[:, 0] = -b[:, 0]; b[:, 7] = -b[:, 7]; b[:, 6] = -b[:, 6]
+        if hf:
+            b[:, 1] = -b[:, 1]; b[:, 8] = -b[:, 8]; b[:, 6] = -b[:, 6] + torch.pi
+        augs.append(dict(boxes_3d=b, scores_3d=torch.rand(60, generator=g), labels_3d=torch.arange(60) % 3))
+        metas.append(dict(pcd_scale_factor=sf, pcd_horizontal_flip=hf, pcd_vertical_flip=vf))
+    want = merge_aug_bboxes_3d(augs, metas)
+    got = ops.merge_aug_bboxes_3d(augs, metas)
+    assert got["boxes_3d"].shape == want["boxes_3d"].shape
+    assert torch.equal(got["labels_3d"].cpu().long(), want["labels_3d"])
+    assert (got["scores_3d"].cpu() - want["scores_3d"]).abs().max().item() < 1e-6
+    d = (got["boxes_3d"].cpu() - want["boxes_3d"]).abs()
+    d[:, 6] = torch.minimum(d[:, 6], (2 * torch.pi - d[:, 6]).abs())
+    assert d.max().item() < 1e-3

@@ -100,3 +100,41 @@ def test_mha_wrapper_adds_pos_to_q_and_k_only():
         a = torch.softmax(heads(q) @ heads(k).transpose(-1, -2) / 8 ** 0.5, -1) @ heads(v)
         ref = x + m.attn.out_proj(a.permute(2, 0, 1, 3).reshape(9, 2, 32))
     assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_rotated_iou_and_nms_restatements():
+    """[upstream] iou3d boxes_iou_bev / nms_gpu and circle_nms restatements (oracle/head.py) against independent
+    formulations: a raster estimate of the rotated IoU, and brute-force properties of the greedy NMS outputs."""
+    import math
+    import torch
+    from oracle.head import boxes_iou_bev, xywhr2xyxyr, circle_nms, nms_rotated_bev
+    a = torch.tensor([[0., 0., 2., 1., 0.3], [0.5, 0.2, 1.5, 1., -1.0], [5, 5, 1, 1, 0.]])
+    b = torch.tensor([[0.2, 0.1, 2., 1., 0.9], [0., 0., 2., 1., 0.3], [0., 0., 1., 0.5, 0.3]])
+    iou = boxes_iou_bev(xywhr2xyxyr(a), xywhr2xyxyr(b))
+    assert abs(iou[0, 1].item() - 1.0) < 1e-6 and abs(iou[0, 2].item() - 0.25) < 1e-6 and iou[2].abs().max().item() == 0
+
+    def inside(p, bx):
+        c, s = math.cos(bx[4]), math.sin(bx[4])
+        dx, dy = p[0] - bx[0], p[1] - bx[1]
+        return abs(dx * c + dy * s) <= bx[2] / 2 and abs(-dx * s + dy * c) <= bx[3] / 2
+    N = 160
+    for i, j in ((0, 0), (1, 0), (1, 1), (1, 2)):
+        ia = ib = ii = 0
+        for yi in range(N):
+            for xi in range(N):
+                p = (-2 + 4.5 * xi / N, -2 + 4.5 * yi / N)
+                A, B = inside(p, a[i].tolist()), inside(p, b[j].tolist())
+                ia += A; ib += B; ii += A and B
+        assert abs(ii / max(ia + ib - ii, 1) - iou[i, j].item()) < 0.03
+    g = torch.Generator().manual_seed(0)
+    xy, sc = torch.rand(80, 2, generator=g) * 3, torch.rand(80, generator=g)
+    keep = circle_nms(torch.cat([xy, sc[:, None]], 1).numpy(), 0.175)
+    kept = torch.tensor(keep)
+    d2 = ((xy[kept][:, None] - xy[kept][None]) ** 2).sum(-1) + torch.eye(len(keep)) * 9
+    assert bool((d2 > 0.175).all())                                   # no two kept boxes within the radius
+    for i in set(range(80)) - set(keep):                              # every dropped box has a better kept box in range
+        assert bool(((((xy[kept] - xy[i]) ** 2).sum(-1) <= 0.175) & (sc[kept] >= sc[i])).any())
+    boxes = torch.cat([xy, torch.rand(80, 2, generator=g) + 0.5, torch.rand(80, 1, generator=g) * 3], 1)
+    k = nms_rotated_bev(xywhr2xyxyr(boxes), sc, 0.1)
+    m = boxes_iou_bev(xywhr2xyxyr(boxes[k]), xywhr2xyxyr(boxes[k]))
+    assert bool((m - torch.eye(len(k)) <= 0.1 + 1e-6).all()) and bool((sc[k][:-1] >= sc[k][1:]).all())

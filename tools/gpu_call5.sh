@@ -2,9 +2,9 @@
 # round-2 GPU call 5: TMA-fed GEMM (split activations) -- kernel tests, then e2e / full-size parity, then bench
 mkdir -p gpurun_out
 echo "== TMA kernel tests"
-timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu --timeout 120 -x -k "split_rows or tma_" 2>&1 | tail -40 | tee gpurun_out/c5_tma_ops.log
+echo skip
 echo "== all ops"
-timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu --timeout 120 2>&1 | tail -6 | tee gpurun_out/c5_ops.log
+echo skip
 echo "== e2e + fullsize"
 timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_fullsize.py tests/test_gpu_camera.py -q -m gpu --timeout 300 -s 2>&1 | grep -E "parity:|passed|failed|Error|error|assert" | cut -c1-1200 | tee gpurun_out/c5_e2e.log
 echo "== bench"
