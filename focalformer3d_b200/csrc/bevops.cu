@@ -1,5 +1,5 @@
 // Small HBM-bound NHWC helpers: depthwise 3x3, LayerNorm, row adds.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ff3d {
 
@@ -297,6 +297,35 @@ extern "C" int ff3d_add_bcast_rows(const float* a, const float* p, float* y, int
   add_bcast_rows_kernel<<<grid_for(per4 * B, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(p), reinterpret_cast<float4*>(y), B, per4);
   return check_launch("ff3d_add_bcast_rows");
+}
+
+// y = a + p in split form only: ys [B*rows, 2C] fp16 [hi | lo] (the value_proj input of the deformable decoder)
+__global__ void add_bcast_rows_split_kernel(const float4* __restrict__ a, const float4* __restrict__ p, __half* __restrict__ ys,
+                                            int B, long long per4, int C, int* overflow) {
+  using namespace ff3d;
+  long long n4 = per4 * B;
+  bool ovf = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 u = a[i], v = p[i % per4];
+    const float4 s = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    uint32_t h01, h23, l01, l23;
+    split_f16x4(s, h01, h23, l01, l23, ovf);
+    const long long e = i * 4, row = e / C;
+    const int col = (int)(e - row * C);
+    *reinterpret_cast<uint2*>(ys + row * 2 * C + col) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(ys + row * 2 * C + C + col) = make_uint2(l01, l23);
+  }
+  if (ovf && overflow) atomicOr(overflow, 1);
+}
+
+extern "C" int ff3d_add_bcast_rows_split(const float* a, const float* p, void* ys, int B, long long rows, int C,
+                                         int* overflow_dev, ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(C % 8 == 0, "add_bcast_rows_split: C must be a multiple of 8");
+  long long per4 = rows * C / 4;
+  add_bcast_rows_split_kernel<<<grid_for(per4 * B, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(p), static_cast<__half*>(ys), B, per4, C, overflow_dev);
+  return check_launch("ff3d_add_bcast_rows_split");
 }
 
 extern "C" int ff3d_local_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* y,

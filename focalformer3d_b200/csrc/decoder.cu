@@ -1,6 +1,6 @@
 // Decoder-side kernels: sine position embedding, query self-attention core, multi-scale deformable sampling,
 // ROI grid sampling, box-state update and final box decode.  Token-major layout everywhere: [B*Nq, C] rows.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ff3d {
 
@@ -160,8 +160,11 @@ struct RoiP {
   float expand, cell_x, cell_y, origin_x, origin_y, rx0, ry0, rx1, ry1;
 };
 // block = one query, threads = channels; out row = [L][g*g][C]
+// SPLIT: the row is written as fp16 [hi(K) | lo(K)] (K = L*g*g*C) for the TMA-fed roi_mlp.0 GEMM instead of fp32
+template <bool SPLIT>
 __global__ void roi_sample_kernel(const float* __restrict__ qbox, RoiP p, const float* __restrict__ value, int ldv,
-                                  long long v_bstride, Levels lv, float* __restrict__ out, int Nq) {
+                                  long long v_bstride, Levels lv, float* __restrict__ out, __half* __restrict__ outs, int Nq,
+                                  int* overflow) {
   long long bq = blockIdx.x;
   int b = (int)(bq / Nq);
   const float* qb = qbox + bq * p.box_ld;
@@ -173,7 +176,10 @@ __global__ void roi_sample_kernel(const float* __restrict__ qbox, RoiP p, const 
   float sn = sinf(yaw), cs = cosf(yaw);
   const float* vb = value + (long long)b * v_bstride * ldv;
   int G = p.g * p.g;
-  float* orow = out + bq * ((long long)lv.L * G * p.C);
+  const long long K = (long long)lv.L * G * p.C;
+  float* orow = SPLIT ? nullptr : out + bq * K;
+  __half* srow = SPLIT ? outs + bq * 2 * K : nullptr;
+  bool ovf = false;
   for (int n = 0; n < G; ++n) {
     int i = n / p.g, j = n - i * p.g;
     float gx = ((float)i + 0.5f) / (float)p.g * w - w / 2.f;
@@ -190,10 +196,22 @@ __global__ void roi_sample_kernel(const float* __restrict__ qbox, RoiP p, const 
       float px = ((nx + 1.f) * (float)W - 1.f) / 2.f;
       float py = ((ny + 1.f) * (float)H - 1.f) / 2.f;
       const float* base = vb + (long long)lv.start[lvl] * ldv;
-      for (int c = threadIdx.x; c < p.C; c += blockDim.x)
-        orow[((long long)lvl * G + n) * p.C + c] = bilinear_zero(base, ldv, H, W, px, py, c);
+      for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        const float v = bilinear_zero(base, ldv, H, W, px, py, c);
+        const long long k = ((long long)lvl * G + n) * p.C + c;
+        if (SPLIT) {
+          const float cv = fminf(fmaxf(v, -F16_MAX), F16_MAX);
+          ovf = ovf || cv != v;
+          const __half hi = __float2half_rn(cv);
+          srow[k] = hi;
+          srow[K + k] = __float2half_rn(fminf(fmaxf((cv - __half2float(hi)) * 2048.f, -F16_MAX), F16_MAX));
+        } else {
+          orow[k] = v;
+        }
+      }
     }
   }
+  if (SPLIT && ovf && overflow) atomicOr(overflow, 1);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -340,8 +358,24 @@ extern "C" int ff3d_roi_sample(const float* query_box, int box_ld, const float* 
   RoiP p{box_ld, g, C, expand, cell_x, cell_y, origin_x, origin_y, roi_range4[0], roi_range4[1], roi_range4[2],
          roi_range4[3]};
   if (B * Nq <= 0) return FF3D_OK;
-  roi_sample_kernel<<<B * Nq, 128, 0, as_stream(stream)>>>(query_box, p, value, ldv, v_bstride, lv, out, Nq);
+  roi_sample_kernel<false><<<B * Nq, 128, 0, as_stream(stream)>>>(query_box, p, value, ldv, v_bstride, lv, out, nullptr, Nq, nullptr);
   return check_launch("ff3d_roi_sample");
+}
+
+// same sampling, output rows in split form [hi(K) | lo(K)] fp16 (K = L*g*g*C) for ff3d_tmagemm
+extern "C" int ff3d_roi_sample_split(const float* query_box, int box_ld, const float* value, int ldv, long long v_bstride,
+                                     const int* lvl_h, const int* lvl_w, const int* lvl_start, int L, int C, int g, float expand,
+                                     float cell_x, float cell_y, float origin_x, float origin_y, const float* roi_range4,
+                                     void* out_split, int B, int Nq, int* overflow_dev, ff3d_stream_t stream) {
+  using namespace ff3d;
+  Levels lv;
+  FF3D_REQUIRE(fill_levels(&lv, lvl_h, lvl_w, lvl_start, L) == 0, "roi_sample: 1..8 levels supported");
+  RoiP p{box_ld, g, C, expand, cell_x, cell_y, origin_x, origin_y, roi_range4[0], roi_range4[1], roi_range4[2],
+         roi_range4[3]};
+  if (B * Nq <= 0) return FF3D_OK;
+  roi_sample_kernel<true><<<B * Nq, 128, 0, as_stream(stream)>>>(query_box, p, value, ldv, v_bstride, lv, nullptr,
+                                                                static_cast<__half*>(out_split), Nq, overflow_dev);
+  return check_launch("ff3d_roi_sample_split");
 }
 
 extern "C" int ff3d_head_update(float* pred, int ldp, float* query_pos, const float* prev, int ldprev, int rows,

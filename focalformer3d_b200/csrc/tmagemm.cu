@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace ff3d {
 
@@ -32,6 +33,7 @@ struct TmP {
   const int* m_dev;
   int cin, cout, taps;
   int xs_lo;                     // halves between the hi and the lo plane of an A row
+  const __half* xs; int ldxs;    // the split A rows themselves (cp.async gather of the SPARSE mode)
   const void* wimg;
   const float* bias;
   const float* res; int ldres;
@@ -49,7 +51,8 @@ struct TmP {
   const uint32_t* tile_mask;
   int zero_row;
   int* overflow;
-  int n_stages, cpt;
+  int n_stages, cpt;             // pipeline K-steps in the weight images; 64-channel chunks per tap (cin >= 64)
+  int tps, n_units;              // SPARSE, cin < 64: taps packed into one 64-wide K-step; skippable units (taps | stages)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
@@ -72,10 +75,25 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// CPA (SPARSE only): gather the rows with 16-byte cp.async (LDGSTS) copies issued by the NPW producer warps instead of
+// TMA gather4.  Measured: the TMA unit retires one gather4 (4 rows x 128 bytes) every ~55 cycles per SM whatever the number
+// of issuing warps (~1.3 TB/s over the chip), 2-3x short of the MMA rate; LDGSTS moves the same pre-split bytes through the
+// LSU path with ~4 instructions per 16 bytes and no registers; cp.async.mbarrier.arrive.noinc signals each stage exactly
+// when its copies have landed.
 // NPW = producer warps.  ROWS / CONV2D need one (a single thread issues two box loads per stage).  SPARSE issues
 // 2 x 32 gather4 per stage, and a gather4 costs ~100 cycles of the issuing warp (measured: one producer warp delivers a
 // stage every ~6900 cycles against 768 cycles of MMA time), so the gathers of a stage are spread over NPW warps.
-template <int MODE, int BN, int NS, int NPW>
+// 16-byte global -> shared copy without registers (LDGSTS); src_bytes = 0 writes zeros (absent neighbour)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` when all cp.async copies issued so far by this thread have completed; .noinc: the arrival is one of the
+// barrier's expected arrivals (it was counted at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int MODE, int BN, int NS, int NPW, bool CPA = false>
 __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid_constant__ CUtensorMap tmA, const TmP p) {
   constexpr int MMA_WARP = NPW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -100,15 +118,24 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
   if ((int)blockIdx.x >= total_tiles) return;   // uniform for the whole CTA, before any barrier / TMEM use
 
   const bool masked = MODE == FF3D_GEMM_SPARSE && p.tile_mask != nullptr;
+  // unit = one tap (cin >= 64: cpt K-steps) or one packed K-step of tps taps (cin < 64); bit u of the mask = unit u is used
+  // by at least one row of the tile
   auto unit_mask = [&](int tile) -> uint32_t {
     if (!masked) return 0u;
-    const uint32_t um = __ldg(p.tile_mask + tile / n_tiles_n);
+    const uint32_t tm = __ldg(p.tile_mask + tile / n_tiles_n);
+    uint32_t um = tm;
+    if (p.tps > 1) {
+      um = 0;
+      const uint32_t grp_bits = (1u << p.tps) - 1u;
+      for (int u = 0; u < p.n_units; ++u)
+        if ((tm >> (u * p.tps)) & grp_bits) um |= 1u << u;
+    }
     return um ? um : 1u;
   };
   auto stage_count = [&](uint32_t um) -> int { return masked ? __popc(um) * p.cpt : p.n_stages; };
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(full_bar + 8u * s, NPW); mbar_init(empty_bar + 8u * s, 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar + 8u * s, CPA ? NPW * 32 + 1 : NPW); mbar_init(empty_bar + 8u * s, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8u * i, 1); mbar_init(tempty_bar + 8u * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -129,6 +156,71 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
     Ring ring{0, 0u};
     const uint8_t* wbase = static_cast<const uint8_t*>(p.wimg);
     const size_t stage_bytes = 2 * (size_t)B_BYTES;
+    if constexpr (CPA) {
+      // ---- SPARSE gather by cp.async: lane (q, j) copies 16-byte chunk j of rows q, q+4, ... of this warp's RPW-row slice
+      static_assert(MODE == FF3D_GEMM_SPARSE && RPW % 4 == 0, "cp.async gather is the SPARSE producer");
+      constexpr int RI = RPW / 4;
+      const int j = lane & 7, q = lane >> 3;
+      const char* xbase = reinterpret_cast<const char*>(p.xs);
+      const size_t row_bytes = (size_t)p.ldxs * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mtile = tile / n_tiles_n;
+        const int ntile = tile - mtile * n_tiles_n;
+        const uint8_t* wsrc = wbase + (size_t)ntile * p.n_stages * stage_bytes;
+        const int m0 = mtile * TC_BM;
+        uint32_t mm = masked ? unit_mask(tile) : (p.n_units >= 32 ? 0xFFFFFFFFu : ((1u << p.n_units) - 1u));
+        // this lane's tap inside unit u and its channel offset: cin >= 64 -> tap u, the lane's 8 channels of chunk c;
+        // cin < 64 -> the K-step packs tps taps: 16-byte chunk j belongs to tap u*tps + (8j / cin)
+        const int lane_tap = p.tps > 1 ? (j * 8) / p.cin : 0;
+        const int lane_col = p.tps > 1 ? (j * 8) % p.cin : j * 8;
+        int idx[RI], nidx[RI];
+        auto load_idx = [&](int u, int* dst) {
+          const int t = u * p.tps + lane_tap;
+#pragma unroll
+          for (int i = 0; i < RI; ++i) {
+            const int m = m0 + warp * RPW + q + 4 * i;
+            dst[i] = (t < p.taps && m < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m) : -1;
+          }
+        };
+        int u = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        load_idx(u, idx);
+        while (u >= 0) {
+          const int un = mm ? __ffs(mm) - 1 : -1;                 // prefetch the next unit's row indices
+          if (un >= 0) { mm &= mm - 1u; load_idx(un, nidx); }
+          for (int c = 0; c < p.cpt; ++c) {
+            const uint32_t slot_a = smem + (uint32_t)ring.slot * SLOT_BYTES;
+            const uint32_t bar = full_bar + 8u * ring.slot;
+            if (lane == 0) {
+              mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
+              if (warp == 0) {
+                mbar_arrive_expect_tx(bar, 2 * B_BYTES);
+                bulk_g2s(slot_a + 2 * A_BYTES, wsrc + (size_t)(u * p.cpt + c) * stage_bytes, 2 * B_BYTES, bar);
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int plane = 0; plane < 2; ++plane) {
+              const size_t col_bytes = (size_t)(plane * p.xs_lo + c * 64 + lane_col) * 2;
+#pragma unroll
+              for (int i = 0; i < RI; ++i) {
+                const int row = warp * RPW + q + 4 * i;
+                const int r = idx[i];
+                const uint32_t dst = slot_a + (uint32_t)plane * A_BYTES + (uint32_t)(row * 128 + ((j ^ (row & 7)) << 4));
+                cp_async16(dst, xbase + (r < 0 ? 0 : (size_t)r * row_bytes) + col_bytes, r < 0 ? 0u : 16u);
+              }
+            }
+            // the hardware arrives on the stage's barrier once THIS thread's copies have landed (the CUTLASS sm100
+            // cp.async + UMMA pipeline): exact signalling, nothing to wait for here
+            cp_async_arrive_noinc(bar);
+            ring.advance(1, NS);
+          }
+          u = un;
+#pragma unroll
+          for (int i = 0; i < RI; ++i) idx[i] = nidx[i];
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mtile = tile / n_tiles_n;
       const int ntile = tile - mtile * n_tiles_n;
@@ -419,24 +511,27 @@ static int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_
   return FF3D_OK;
 }
 
-template <int MODE, int BN, int NPW>
+template <int MODE, int BN, int NPW, bool CPA>
 static int launch_tm_cfg(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
-  constexpr int NS = BN == 128 ? 3 : 4;
+  constexpr int NS = BN == 128 ? 3 : (BN == 64 ? 4 : 5);          // 64 / 48 / 40 / 36 KB per stage
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
   const size_t smem = NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + 1024;
   static const cudaError_t attr =
-      cudaFuncSetAttribute(tmagemm_kernel<MODE, BN, NS, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(tmagemm_kernel<MODE, BN, NS, NPW, CPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr != cudaSuccess) { set_error("ff3d_tmagemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr)); return FF3D_ECUDA; }
   const long long tiles = m_tiles * (p.cout / BN);
   const long long resident = num_sms();
   dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-  tmagemm_kernel<MODE, BN, NS, NPW><<<grid, 32 * (NPW + 5), smem, st>>>(tm, p);
+  tmagemm_kernel<MODE, BN, NS, NPW, CPA><<<grid, 32 * (NPW + 5), smem, st>>>(tm, p);
   return check_launch("ff3d_tmagemm");
 }
 
-// producer warps of the SPARSE gather (FF3D_TMA_NPW = 1 / 4 / 8, read once)
-static int sparse_npw() {
+// SPARSE gather engine: FF3D_SPARSE_GATHER = "cpasync" (default: LDGSTS copies by 8 producer warps) or "tma" (tile::gather4
+// issued by FF3D_TMA_NPW = 1 / 4 / 8 producer warps); read once
+static int sparse_gather_cfg() {
   static const int v = []() {
+    const char* g = getenv("FF3D_SPARSE_GATHER");
+    if (!g || strcmp(g, "tma") != 0) return 0;                     // cp.async
     const char* e = getenv("FF3D_TMA_NPW");
     const int n = e ? atoi(e) : 8;
     return (n == 1 || n == 4 || n == 8) ? n : 8;
@@ -447,13 +542,14 @@ static int sparse_npw() {
 template <int MODE, int BN>
 static int launch_tm(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
   if constexpr (MODE == FF3D_GEMM_SPARSE) {
-    switch (sparse_npw()) {
-      case 1: return launch_tm_cfg<MODE, BN, 1>(tm, p, m_tiles, st);
-      case 4: return launch_tm_cfg<MODE, BN, 4>(tm, p, m_tiles, st);
-      default: return launch_tm_cfg<MODE, BN, 8>(tm, p, m_tiles, st);
+    switch (p.tps > 1 ? 0 : sparse_gather_cfg()) {
+      case 0: return launch_tm_cfg<MODE, BN, 8, true>(tm, p, m_tiles, st);
+      case 1: return launch_tm_cfg<MODE, BN, 1, false>(tm, p, m_tiles, st);
+      case 4: return launch_tm_cfg<MODE, BN, 4, false>(tm, p, m_tiles, st);
+      default: return launch_tm_cfg<MODE, BN, 8, false>(tm, p, m_tiles, st);
     }
   } else {
-    return launch_tm_cfg<MODE, BN, 1>(tm, p, m_tiles, st);
+    return launch_tm_cfg<MODE, BN, 1, false>(tm, p, m_tiles, st);
   }
 }
 
@@ -461,7 +557,12 @@ template <int MODE>
 static int launch_tm_bn(const CUtensorMap& tm, const TmP& p, long long m_tiles, int bn, cudaStream_t st) {
   if (bn == 128) return launch_tm<MODE, 128>(tm, p, m_tiles, st);
   if (bn == 64) return launch_tm<MODE, 64>(tm, p, m_tiles, st);
-  set_error("ff3d_tmagemm: unsupported N tile %d (64, 128)", bn);
+  if constexpr (MODE == FF3D_GEMM_SPARSE) {
+    // narrow levels of the sparse encoder (C = 16 / 32): cp.async gather only
+    if (bn == 32) return launch_tm_cfg<MODE, 32, 8, true>(tm, p, m_tiles, st);
+    if (bn == 16) return launch_tm_cfg<MODE, 16, 8, true>(tm, p, m_tiles, st);
+  }
+  set_error("ff3d_tmagemm: unsupported N tile %d", bn);
   return FF3D_EINVAL;
 }
 
@@ -486,11 +587,17 @@ extern "C" void ff3d_tmagemm_conv_patch(int Ho, int Wo, int* bw_out, int* bh_out
 
 extern "C" int ff3d_tmagemm_supported(const ff3d_gemm_desc* d) {
   if (!d || !d->xs) return 0;
-  if (d->cin < 64 || d->cin % 64 != 0) return 0;
-  if (!(d->cout % 128 == 0 || d->cout == 64)) return 0;
   if (d->x2) return 0;
+  const bool wide_in = d->cin >= 64 && d->cin % 64 == 0;
+  const bool wide_out = d->cout % 128 == 0 || d->cout == 64;
+  if (d->mode == FF3D_GEMM_SPARSE) {
+    // cp.async gather: also the narrow levels (cin 8 / 16 / 32 pack 8 / 4 / 2 taps into one K-step; cout 16 / 32)
+    if (d->taps > ff3d::TC_MAX_TAPS) return 0;
+    if (!(wide_in || d->cin == 8 || d->cin == 16 || d->cin == 32)) return 0;
+    return (wide_out || d->cout == 16 || d->cout == 32) ? 1 : 0;
+  }
+  if (!wide_in || !wide_out) return 0;
   if (d->mode == FF3D_GEMM_CONV2D && (d->stride != 1 || (d->ux > 1) || (d->uy > 1))) return 0;
-  if (d->mode == FF3D_GEMM_SPARSE && d->taps > ff3d::TC_MAX_TAPS) return 0;
   return 1;
 }
 
@@ -499,8 +606,9 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   FF3D_REQUIRE(d != nullptr && wimg16 != nullptr, "ff3d_tmagemm: null argument");
   FF3D_REQUIRE(ff3d_tmagemm_supported(d), "ff3d_tmagemm: unsupported layer (needs split A rows, cin %% 64 == 0, cout 64 or a "
                                           "multiple of 128, conv stride 1; got cin=%d cout=%d mode=%d)", d->cin, d->cout, d->mode);
-  if (bn == 0) bn = d->cout % 128 == 0 ? 128 : 64;
-  FF3D_REQUIRE((bn == 64 || bn == 128) && d->cout % bn == 0, "ff3d_tmagemm: N tile %d does not divide cout=%d", bn, d->cout);
+  if (bn == 0) bn = d->cout % 128 == 0 ? 128 : d->cout;
+  FF3D_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128) && d->cout % bn == 0,
+               "ff3d_tmagemm: N tile %d does not divide cout=%d", bn, d->cout);
   FF3D_REQUIRE(d->y != nullptr || d->ys != nullptr, "ff3d_tmagemm: no output");
   FF3D_REQUIRE((reinterpret_cast<uintptr_t>(d->xs) & 15) == 0 && d->ldxs % 8 == 0 && d->xs_lo % 8 == 0,
                "ff3d_tmagemm: split A rows must be 16-byte aligned (base, row stride, plane offset)");
@@ -518,6 +626,7 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   TmP p = {};
   p.mode = d->mode; p.M = d->M; p.m_dev = d->m_dev;
   p.cin = d->cin; p.cout = d->cout; p.taps = d->taps; p.xs_lo = d->xs_lo;
+  p.xs = static_cast<const __half*>(d->xs); p.ldxs = d->ldxs;
   p.wimg = wimg16; p.bias = d->bias;
   p.res = d->res; p.ldres = d->ldres;
   p.res_s = static_cast<const __half*>(d->res_s); p.ldres_s = d->ldres_s; p.res_s_lo = d->res_s_lo;
@@ -528,8 +637,10 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   p.tile_mask = d->mode == FF3D_GEMM_SPARSE ? d->tile_mask : nullptr;
   p.zero_row = d->zero_row;
   p.overflow = overflow_dev;
-  p.cpt = d->cin / 64;
-  p.n_stages = d->taps * p.cpt;
+  p.tps = d->cin >= 64 ? 1 : 64 / d->cin;
+  p.cpt = d->cin >= 64 ? d->cin / 64 : 1;
+  p.n_units = d->cin >= 64 ? d->taps : (d->taps + p.tps - 1) / p.tps;
+  p.n_stages = p.n_units * p.cpt;
   cudaStream_t st = as_stream(stream);
   CUtensorMap tm;
   const cuuint64_t row_bytes = (cuuint64_t)d->ldxs * 2;
@@ -544,13 +655,17 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   }
   if (d->mode == FF3D_GEMM_SPARSE) {
     FF3D_REQUIRE(d->nbr != nullptr && d->nbr_stride >= d->M, "ff3d_tmagemm: sparse mode needs nbr [taps, >= M]");
-    FF3D_REQUIRE(d->zero_row >= 0 && d->xs_rows > d->zero_row, "ff3d_tmagemm: sparse mode needs an all-zero row inside xs");
+    FF3D_REQUIRE(d->xs_rows > 0 && (sparse_gather_cfg() == 0 || (d->zero_row >= 0 && d->xs_rows > d->zero_row)),
+                 "ff3d_tmagemm: the gather4 engine needs an all-zero row inside xs");
     FF3D_REQUIRE(!d->y_off || d->y, "ff3d_tmagemm: y_off addresses the fp32 output");
-    cuuint64_t dims[2] = {(cuuint64_t)(d->xs_lo + d->cin), (cuuint64_t)d->xs_rows};
-    cuuint64_t str[1] = {row_bytes};
-    cuuint32_t box[2] = {64, 1};                                       // gather4: one row per box, four boxes per instruction
-    int rc = make_map(&tm, d->xs, 2, dims, str, box);
-    if (rc) return rc;
+    memset(&tm, 0, sizeof(tm));
+    if (p.tps == 1 && sparse_gather_cfg() != 0) {                      // the tensor map is only read by the gather4 engine
+      cuuint64_t dims[2] = {(cuuint64_t)(d->xs_lo + d->cin), (cuuint64_t)d->xs_rows};
+      cuuint64_t str[1] = {row_bytes};
+      cuuint32_t box[2] = {64, 1};                                     // gather4: one row per box, four boxes per instruction
+      int rc = make_map(&tm, d->xs, 2, dims, str, box);
+      if (rc) return rc;
+    }
     return launch_tm_bn<FF3D_GEMM_SPARSE>(tm, p, cdiv(d->M, TC_BM), bn, st);
   }
   FF3D_REQUIRE(d->mode == FF3D_GEMM_CONV2D && d->taps == d->kh * d->kw && (long long)d->B * d->Ho * d->Wo == d->M,

@@ -82,6 +82,7 @@ SIGNATURES = {
     "ff3d_mha_core": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ff3d_msda": (_I, [_P, _I, _I, _LL, _IP, _IP, _IP, _I, _I, _P, _F, _F, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "ff3d_roi_sample": (_I, [_P, _I, _P, _I, _LL, _IP, _IP, _IP, _I, _I, _I, _F, _F, _F, _F, _F, _FP, _P, _I, _I, _P]),
+    "ff3d_roi_sample_split": (_I, [_P, _I, _P, _I, _LL, _IP, _IP, _IP, _I, _I, _I, _F, _F, _F, _F, _F, _FP, _P, _I, _I, _P, _P]),
     "ff3d_head_update": (_I, [_P, _I, _P, _P, _I, _I, _P]),
     "ff3d_box_decode": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _F, _F, _F, _F, _FP, _P, _P, _P, _P, _P]),
     "ff3d_assemble_sweeps": (_I, [_P, _I, _IP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _FP, C.POINTER(C.c_ubyte),
@@ -93,6 +94,7 @@ SIGNATURES = {
     "ff3d_boxes_map_back": (_I, [_P, _I, _I, _I, _F, _I, _I, _P]),
     "ff3d_add_rows": (_I, [_P, _P, _P, _LL, _P]),
     "ff3d_add_bcast_rows": (_I, [_P, _P, _P, _I, _LL, _I, _P]),
+    "ff3d_add_bcast_rows_split": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
     "ff3d_class_select": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P]),
     "ff3d_local_attention": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ff3d_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

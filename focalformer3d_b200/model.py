@@ -185,13 +185,16 @@ class SparseEncoder(ParamTree):
         lvl.build_hash()
         perm = lvl.sort_by_mask()
         feats = ops.gather_rows(vox["mean"], perm, lvl.n_dev, vox["mean"].shape[1])
+        if ops.tma_ok(self.pk["conv_input"][0], feats.shape[1], self.pk["conv_input"][0].shape[-1], sparse=True):
+            feats = ops.split_rows(feats, n_dev=lvl.n_dev, zero_row=True)
 
         def conv(x, rb, n_dev, wb, cap_out, act, res=None):
-            """One sparse conv.  Activations of a level whose channel count the TMA-fed kernel tiles (C % 64 == 0) live in
-            split form (ops.Split, written by the producing conv's epilogue); narrower levels stay fp32 rows."""
+            """One sparse conv.  With the TMA / cp.async kernel every level lives in split form (ops.Split: a row of C
+            channels = fp16 [hi | lo], written by the producing conv's epilogue, gathered with 16-byte cp.async copies);
+            otherwise (FF3D_GEMM=tf32, FF3D_TMA=0) fp32 rows on the register-path kernel."""
             w, b = wb
             cout = w.shape[-1]
-            if ops.tma_enabled() and cout % 64 == 0:            # the consumers of a C % 64 == 0 level take split rows
+            if ops.tma_enabled() and (cout % 64 == 0 or isinstance(x, ops.Split)):
                 ys = ops.Split.empty((cap_out,), cout, dev, zero_row=True)
                 ops.sparse_conv(x, rb, n_dev, w, b, None, act=act, res=res, out_s=ys)
                 return ys

@@ -249,7 +249,8 @@ class Split:
         if zero_row:
             assert len(shape) == 1
             t = torch.empty((shape[0] + 1, 2 * C), dtype=torch.float16, device=dev)
-            t[shape[0]].zero_()
+            if GATHER4:                        # only the tile::gather4 engine reads it (cp.async zero-fills in flight)
+                t[shape[0]].zero_()
             return Split(t, C, zero_row=shape[0])
         return Split(torch.empty(shape + (2 * C,), dtype=torch.float16, device=dev), C)
 
@@ -296,6 +297,7 @@ def unsplit_rows(xs, rows, n_dev=None):
 
 
 USE_TMA = _os.environ.get("FF3D_TMA", "1") != "0"     # FF3D_TMA=0: never take the TMA-fed kernel (debugging aid)
+GATHER4 = _os.environ.get("FF3D_SPARSE_GATHER", "cpasync") == "tma"    # sparse rows by TMA tile::gather4 instead of cp.async
 
 
 def _attach_split(d, xs=None, res_s=None, out_s=None, xs_rows=0):
@@ -312,7 +314,7 @@ def _gemm_any(d, w, what, x_is_split):
     if x_is_split:
         if not (USE_TC and USE_TMA and w.kind == "f16" and lib.ff3d_tmagemm_supported(C.byref(d))):
             raise L.Ff3dError(f"{what}: split input given but the layer is not TMA-tileable (cin={d.cin} cout={d.cout})")
-        bn = w.bn if w.bn in (64, 128) else 0
+        bn = w.bn if w.bn in (16, 32, 64, 128) else 0
         check(lib.ff3d_tmagemm(C.byref(d), _ptr(w.img), bn, _ptr(gemm_flag(w.img.device)), _stream()), f"ff3d_tmagemm({what})")
     else:
         _gemm(d, w, what)
@@ -323,10 +325,16 @@ def tma_enabled():
     return bool(USE_TC and USE_TMA and GEMM_KIND == "f16")
 
 
-def tma_ok(w, cin, cout):
-    """Can a layer with these weights take split A rows (ff3d_tmagemm)?"""
-    return bool(USE_TC and USE_TMA and w.img is not None and w.kind == "f16" and cin % 64 == 0 and cin >= 64
-                and (cout % 128 == 0 or cout == 64) and w.bn in (64, 128))
+def tma_ok(w, cin, cout, sparse=False):
+    """Can a layer with these weights take split A rows (ff3d_tmagemm)?  Dense layers: cin a multiple of 64, cout 64 or a
+    multiple of 128; sparse layers (cp.async gather) also the narrow levels cin 8 / 16 / 32, cout 16 / 32."""
+    if not (USE_TC and USE_TMA and w.img is not None and w.kind == "f16"):
+        return False
+    wide = cin % 64 == 0 and cin >= 64 and (cout % 128 == 0 or cout == 64) and w.bn in (64, 128)
+    if sparse:
+        return bool(wide or ((cin in (8, 16, 32) or (cin % 64 == 0 and cin >= 64))
+                             and (cout in (16, 32, 64) or cout % 128 == 0) and w.bn in (16, 32, 64, 128)))
+    return bool(wide)
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -273,6 +273,13 @@ int ff3d_roi_sample(const float* query_box, int box_ld, const float* value, int 
                     float cell_x, float cell_y, float origin_x, float origin_y, const float* roi_range4, float* out,
                     int B, int Nq, ff3d_stream_t stream);
 
+/* same sampling with the output rows in split form: out_split [B*Nq, 2*K] fp16 = [hi(K) | lo(K)], K = L*g*g*C (the A
+ * operand of the TMA-fed roi_mlp.0 GEMM: no 180 MB fp32 operand, no in-kernel conversion) */
+int ff3d_roi_sample_split(const float* query_box, int box_ld, const float* value, int ldv, long long v_bstride,
+                          const int* lvl_h, const int* lvl_w, const int* lvl_start, int L, int C, int g, float expand,
+                          float cell_x, float cell_y, float origin_x, float origin_y, const float* roi_range4,
+                          void* out_split, int B, int Nq, int* overflow_dev, ff3d_stream_t stream);
+
 /* Box-state update after the prediction heads (focal_decoder.py:945-957). pred [rows, ldp] rows =
  * (center2, height1, dim3, rot2, [vel2], class logits...): center += query_pos; query_pos = center;
  * with prev != NULL (roi_based_reg): dim[:2] += prev.dim[:2], rot += prev.rot. */
@@ -366,6 +373,9 @@ int ff3d_local_attention(const float* q, int ldq, const float* k, int ldk, const
 int ff3d_add_rows(const float* a, const float* b, float* y, long long n, ff3d_stream_t stream);
 /* y[b, r, :] = a[b, r, :] + p[r, :]   (value + cached BEV positional embedding, focal_decoder.py:886) */
 int ff3d_add_bcast_rows(const float* a, const float* p, float* y, int B, long long rows, int C, ff3d_stream_t stream);
+/* the same sum written in split form only: ys [B*rows, 2C] fp16 [hi | lo] (input of the TMA-fed value_proj GEMM) */
+int ff3d_add_bcast_rows_split(const float* a, const float* p, void* ys, int B, long long rows, int C, int* overflow_dev,
+                              ff3d_stream_t stream);
 
 #ifdef __cplusplus
 }
