@@ -4,9 +4,12 @@
 namespace ff3d {
 
 // thread = (pixel, 4 channels); weights [9, C]; 9 float4 loads per output float4 (neighbours hit L1/L2)
+// SPLIT: the output is written in split form (fp16 [hi(C) | lo(C)] rows, for a TMA-fed 1x1 conv) instead of fp32
+template <bool SPLIT>
 __global__ void dwconv3x3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                  const float* __restrict__ bias, float* __restrict__ y, int ldy, int B, int H, int W,
-                                 int C, int act) {
+                                 int C, int act, __half* __restrict__ ys, int* overflow) {
+  bool ovf = false;
   int c4n = C >> 2;
   long long total = (long long)B * H * W * c4n;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -34,8 +37,16 @@ __global__ void dwconv3x3_kernel(const float* __restrict__ x, int ldx, const flo
     }
     acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
     acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
-    *reinterpret_cast<float4*>(y + pix * ldy + c) = acc;
+    if (SPLIT) {
+      uint32_t h01, h23, l01, l23;
+      split_f16x4(acc, h01, h23, l01, l23, ovf);
+      *reinterpret_cast<uint2*>(ys + pix * 2 * C + c) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(ys + pix * 2 * C + C + c) = make_uint2(l01, l23);
+    } else {
+      *reinterpret_cast<float4*>(y + pix * ldy + c) = acc;
+    }
   }
+  if (SPLIT && ovf && overflow) atomicOr(overflow, 1);
 }
 
 // one warp per row, C <= 1024, C % 32 == 0 handled generally with a strided loop; two-pass (mean, then variance)
@@ -269,8 +280,20 @@ extern "C" int ff3d_dwconv3x3(const float* x, int ldx, const float* w, const flo
   using namespace ff3d;
   FF3D_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "dwconv3x3: C/ldx/ldy must be multiples of 4");
   long long total = (long long)B * H * W * (C / 4);
-  dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, ldx, w, bias, y, ldy, B, H, W, C, act);
+  dwconv3x3_kernel<false><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, ldx, w, bias, y, ldy, B, H, W, C, act, nullptr,
+                                                                                nullptr);
   return check_launch("ff3d_dwconv3x3");
+}
+
+// same conv, output in split form only: ys [B*H*W, 2C] fp16 [hi | lo]
+extern "C" int ff3d_dwconv3x3_split(const float* x, int ldx, const float* w, const float* bias, void* ys, int B, int H, int W,
+                                    int C, int act, int* overflow_dev, ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(C % 8 == 0 && ldx % 4 == 0, "dwconv3x3_split: C must be a multiple of 8, ldx of 4");
+  long long total = (long long)B * H * W * (C / 4);
+  dwconv3x3_kernel<true><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, ldx, w, bias, nullptr, 0, B, H, W, C, act,
+                                                                               static_cast<__half*>(ys), overflow_dev);
+  return check_launch("ff3d_dwconv3x3_split");
 }
 
 extern "C" int ff3d_layernorm(const float* x, const float* gamma, const float* beta, float* y, int rows, int C, float eps,

@@ -561,6 +561,10 @@ static int launch_tm_bn(const CUtensorMap& tm, const TmP& p, long long m_tiles, 
     // narrow levels of the sparse encoder (C = 16 / 32): cp.async gather only
     if (bn == 32) return launch_tm_cfg<MODE, 32, 8, true>(tm, p, m_tiles, st);
     if (bn == 16) return launch_tm_cfg<MODE, 16, 8, true>(tm, p, m_tiles, st);
+  } else {
+    // narrow dense outputs (e.g. the 128 -> 10(16) heat-map conv)
+    if (bn == 32) return launch_tm_cfg<MODE, 32, 1, false>(tm, p, m_tiles, st);
+    if (bn == 16) return launch_tm_cfg<MODE, 16, 1, false>(tm, p, m_tiles, st);
   }
   set_error("ff3d_tmagemm: unsupported N tile %d", bn);
   return FF3D_EINVAL;
@@ -590,13 +594,14 @@ extern "C" int ff3d_tmagemm_supported(const ff3d_gemm_desc* d) {
   if (d->x2) return 0;
   const bool wide_in = d->cin >= 64 && d->cin % 64 == 0;
   const bool wide_out = d->cout % 128 == 0 || d->cout == 64;
+  const bool narrow_out = d->cout == 16 || d->cout == 32;
   if (d->mode == FF3D_GEMM_SPARSE) {
     // cp.async gather: also the narrow levels (cin 8 / 16 / 32 pack 8 / 4 / 2 taps into one K-step; cout 16 / 32)
     if (d->taps > ff3d::TC_MAX_TAPS) return 0;
     if (!(wide_in || d->cin == 8 || d->cin == 16 || d->cin == 32)) return 0;
-    return (wide_out || d->cout == 16 || d->cout == 32) ? 1 : 0;
+    return (wide_out || narrow_out) ? 1 : 0;
   }
-  if (!wide_in || !wide_out) return 0;
+  if (!wide_in || !(wide_out || narrow_out)) return 0;
   if (d->mode == FF3D_GEMM_CONV2D && (d->stride != 1 || (d->ux > 1) || (d->uy > 1))) return 0;
   return 1;
 }

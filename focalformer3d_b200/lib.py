@@ -74,6 +74,7 @@ SIGNATURES = {
     "ff3d_tcgemm_ntile": (_I, [_I, _I]),
     "ff3d_tcgemm_stages": (_I, [_I, _I]),
     "ff3d_dwconv3x3": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ff3d_dwconv3x3_split": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ff3d_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "ff3d_hip_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "ff3d_hip_stage": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P,

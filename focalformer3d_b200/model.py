@@ -516,16 +516,22 @@ class _IR:
         s, b = bn_scale_shift(sd, f"{name}.conv.{i + 2}", eps)
         self.proj = (pack_conv2d(sd[f"{name}.conv.{i + 1}.weight"], s, dev), vec(b, dev))
 
-    def run(self, x, out, res=None):
+    def run(self, x, out, res=None, x_s=None, out_s=None):
+        """x [B,H,W,cin] fp32 view (x_s: the same in split form for the TMA-fed expand conv); out fp32 view; out_s: Split that
+        also receives the output.  The depthwise conv writes split rows when the project conv can take them."""
         B, H, W, _ = x.shape
         hid = self.dw[0].shape[1]
         if self.expand is not None:
             t = torch.empty((B, H, W, hid), dtype=torch.float32, device=x.device)
-            ops.conv2d(x, self.expand[0], self.expand[1], t, 1, act=ACT_RELU6)
+            use_tma = x_s is not None and ops.tma_ok(self.expand[0], self.expand[0].shape[1], hid)
+            ops.conv2d(x_s if use_tma else x, self.expand[0], self.expand[1], t, 1, act=ACT_RELU6)
             x = t
-        t2 = torch.empty((B, H, W, hid), dtype=torch.float32, device=x.device)
-        ops.dwconv3x3(x, self.dw[0], self.dw[1], t2, act=ACT_RELU6)
-        ops.conv2d(t2, self.proj[0], self.proj[1], out, 1, act=ACT_NONE, res=res)
+        if ops.tma_ok(self.proj[0], hid, self.proj[0].shape[-1]):
+            t2 = ops.dwconv3x3_split(x, self.dw[0], self.dw[1], act=ACT_RELU6)
+        else:
+            t2 = torch.empty((B, H, W, hid), dtype=torch.float32, device=x.device)
+            ops.dwconv3x3(x, self.dw[0], self.dw[1], t2, act=ACT_RELU6)
+        ops.conv2d(t2, self.proj[0], self.proj[1], out, 1, act=ACT_NONE, res=res, out_s=out_s)
         return out
 
 
@@ -694,21 +700,26 @@ class FocalEncoder(ParamTree):
         feat = cat1[..., :hc]
         sw = self.pk["shared"][0]
         shared_in = neck_s if (neck_s is not None and ops.tma_ok(sw, sw.shape[1], hc)) else pts_feats
-        ops.conv2d(shared_in, sw, self.pk["shared"][1], feat, 3, act=ACT_NONE)                     # :204
+        tma = ops.tma_enabled()
+        feat_s = ops.Split.empty((B, H, W), hc, dev) if tma else None      # split copies feed the TMA-fed 3x3 / 1x1 consumers
+        ops.conv2d(shared_in, sw, self.pk["shared"][1], feat, 3, act=ACT_NONE, out_s=feat_s)       # :204
         conv_feat = feat
+        self.split_feats = dict(conv_feat=feat_s, stages=[])
         stages = []
         for i in range(self.num_layers):
             iml, outp, integ = self.pk[f"fusion_blocks.{i}"]
             cat2 = torch.empty((B, H, W, 2 * hc), dtype=torch.float32, device=dev)
             cat2[..., hc:].copy_(feat)                                       # cat((P_Aug, lidar_feat)) :78
-            iml.run(feat, cat1[..., hc:], res=feat)                          # P2P = P_IML(lidar) :76 -> cat((lidar, P2P))
+            iml.run(feat, cat1[..., hc:], res=feat, x_s=feat_s)              # P2P = P_IML(lidar) :76 -> cat((lidar, P2P))
             outp.run(cat1, cat2[..., :hc])                                   # :77
             last = i == self.num_layers - 1
             nxt = torch.empty((B, H, W, hc if last else 2 * hc), dtype=torch.float32, device=dev)
             new_feat = nxt[..., :hc]
-            integ.run(cat2, new_feat)                                        # :78
+            new_s = ops.Split.empty((B, H, W), hc, dev) if tma else None
+            integ.run(cat2, new_feat, out_s=new_s)                           # :78
             stages.append(new_feat)
-            feat, cat1 = new_feat, nxt
+            self.split_feats["stages"].append(new_s)
+            feat, feat_s, cat1 = new_feat, new_s, nxt
         extra = None
         if not stages and extra_out is not None:
             # DeformFormer3D (num_layers=None): the shared-conv output itself is the decoder's level-0 feature
@@ -717,7 +728,10 @@ class FocalEncoder(ParamTree):
             extra = extra_out
         if self.extra_feat and stages:
             extra = extra_out if extra_out is not None else torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
-            ops.conv2d(stages[-1], self.pk["extra"][0], self.pk["extra"][1], extra, 3, act=ACT_NONE)   # :218-219
+            ew = self.pk["extra"][0]
+            last_s = self.split_feats["stages"][-1]
+            ops.conv2d(last_s if (last_s is not None and ops.tma_ok(ew, hc, hc)) else stages[-1], ew, self.pk["extra"][1], extra, 3,
+                       act=ACT_NONE)                                                               # :218-219
         return conv_feat, stages, extra
 
 
@@ -903,9 +917,11 @@ class FocalDecoder(ParamTree):
         return ops.linear(h, st["pos"][1][0], st["pos"][1][1])
 
     # ---- forward
-    def forward(self, conv_feat, stage_feats, ms_value, geom):
+    def forward(self, conv_feat, stage_feats, ms_value, geom, split_feats=None):
         """conv_feat / stage_feats: NHWC views [B,H,W,hc]; ms_value [B, n_tokens, hc] with level 0 (= extra feature)
-        already written.  Returns the reference's head dict (channel-major tensors) plus raw token-major state."""
+        already written; split_feats: optional dict(conv_feat=Split, stages=[Split...]) -- split copies of the same maps
+        for the TMA-fed heat-map convs.  Returns the reference's head dict (channel-major tensors) plus raw token-major
+        state."""
         pk = self.pk
         B, H, W, hc = conv_feat.shape
         dev = conv_feat.device
@@ -914,6 +930,9 @@ class FocalDecoder(ParamTree):
         nq = k * n_sel
         feats = ([conv_feat] if (self.reuse_first or self.single_stage) else []) + list(stage_feats)
         assert len(feats) == n_sel
+        sf = split_feats or {}
+        feats_s = ([sf.get("conv_feat")] if (self.reuse_first or self.single_stage) else []) + list(sf.get("stages") or [])
+        feats_s = feats_s + [None] * (len(feats) - len(feats_s))
         # --- HIP stages (:588-791)
         acc_mask = torch.ones((B, nc, H, W), dtype=torch.float32, device=dev)
         q_feat = torch.empty((B * nq, hc), dtype=torch.float32, device=dev)
@@ -921,24 +940,31 @@ class FocalDecoder(ParamTree):
         q_score = torch.empty((B * nq, nc), dtype=torch.float32, device=dev)
         q_label = torch.empty((B * nq,), dtype=torch.int32, device=dev)
         dense_heatmaps, nms_heats, tops = [], [], []
-        def heat_logits(hw, x):
+        def heat_logits(hw, x, x_s=None):
+            """ConvModule 3x3 + BN + ReLU, Conv 3x3 -> class logits (focal_decoder.py:202-221).  With a split copy of the
+            input both convs run TMA-fed and the intermediate map exists in split form only."""
             w1, b1, w2, b2 = hw
+            lg = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)       # padded channels = 0
+            if x_s is not None and ops.tma_ok(w1, hc, hc) and ops.tma_ok(w2, hc, w2.shape[-1]):
+                t_s = ops.Split.empty((B, H, W), hc, dev)
+                ops.conv2d(x_s, w1, b1, None, 3, act=ACT_RELU, out_s=t_s)
+                ops.conv2d(t_s, w2, b2, lg, 3, act=ACT_NONE)
+                return lg
             t = torch.empty((B, H, W, hc), dtype=torch.float32, device=dev)
             ops.conv2d(x, w1, b1, t, 3, act=ACT_RELU)
-            lg = torch.empty((B, H, W, w2.shape[-1]), dtype=torch.float32, device=dev)       # padded channels = 0
             ops.conv2d(t, w2, b2, lg, 3, act=ACT_NONE)
             return lg
 
         if "heat_first" in pk:
-            dense_heatmaps.append(heat_logits(pk["heat_first"], conv_feat))
+            dense_heatmaps.append(heat_logits(pk["heat_first"], conv_feat, sf.get("conv_feat")))
         for s in range(n_sel):
             logits2 = None
             if self.single_stage:      # heatmap = (sigmoid(heatmap_head(x)) + sigmoid(heatmap_head_img(x))) / 2   :547-549
-                logits = heat_logits(pk["heat"][0], feats[0])
-                logits2 = heat_logits(pk["heat"][1], feats[0])
+                logits = heat_logits(pk["heat"][0], feats[0], feats_s[0])
+                logits2 = heat_logits(pk["heat"][1], feats[0], feats_s[0])
                 dense_heatmaps.append(logits)
             else:
-                logits = heat_logits(pk["heat"][s], feats[s])
+                logits = heat_logits(pk["heat"][s], feats[s], feats_s[s])
             nms_heat = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
             top = torch.empty((B, k), dtype=torch.int32, device=dev)
             ops.hip_stage(logits, acc_mask, nms_heat, feats[s], pk["cls_w"], pk["cls_b"], k, self.nms_kernel_size,
@@ -962,16 +988,25 @@ class FocalDecoder(ParamTree):
             st = pk["stage"][i]
             qpe = self._pos_mlp(i, q_pos, W, H)                                           # :869-872
             bev_pe = self._bev_pos_embed(i, geom, W, H, dev)
-            valin = torch.empty_like(ms_value)
-            ops.add_bcast_rows(ms_value, bev_pe, valin)                                    # :886
-            vproj = ops.linear(valin.view(B * geom.n_tokens, hc), st["vproj"][0], st["vproj"][1])
+            if ops.tma_ok(st["vproj"][0], hc, st["vproj"][0].shape[-1]):
+                # value + positional embedding written once in split form; the 3 layers' value_proj = one TMA-fed GEMM
+                vproj = ops.linear(ops.add_bcast_rows_split(ms_value, bev_pe), st["vproj"][0], st["vproj"][1])     # :886
+            else:
+                valin = torch.empty_like(ms_value)
+                ops.add_bcast_rows(ms_value, bev_pe, valin)                                # :886
+                vproj = ops.linear(valin.view(B * geom.n_tokens, hc), st["vproj"][0], st["vproj"][1])
             vproj = vproj.view(B, geom.n_tokens, -1)
             ops.mark(f"pos+value_proj{i}")
             if self.roi_feats and prev is not None:                                        # :890-922
                 g = self.roi_feats
-                roi = torch.empty((B * nq, self.n_levels * g * g * hc), dtype=torch.float32, device=dev)
-                ops.roi_sample(prev, ms_value, geom, hc, g, self.roi_expand_ratio[i], self.bbox_coder.cell,
-                               self.bbox_coder.pc_range, self.roi_range, roi, B, nq)
+                K_roi = self.n_levels * g * g * hc
+                if ops.tma_ok(pk["roi"][0][0], K_roi, pk["roi"][0][0].shape[-1]):
+                    roi = ops.roi_sample_split(prev, ms_value, geom, hc, g, self.roi_expand_ratio[i], self.bbox_coder.cell,
+                                               self.bbox_coder.pc_range, self.roi_range, B, nq)
+                else:
+                    roi = torch.empty((B * nq, K_roi), dtype=torch.float32, device=dev)
+                    ops.roi_sample(prev, ms_value, geom, hc, g, self.roi_expand_ratio[i], self.bbox_coder.cell,
+                                   self.bbox_coder.pc_range, self.roi_range, roi, B, nq)
                 h1 = ops.linear(roi, pk["roi"][0][0], pk["roi"][0][1], act=ACT_RELU)
                 h2 = ops.linear(h1, pk["roi"][1][0], pk["roi"][1][1], act=ACT_RELU)
                 x = ops.linear(h2, pk["roi"][2][0], pk["roi"][2][1], act=ACT_RELU, res=x, res_after_act=True)
@@ -1208,7 +1243,7 @@ class FocalFormer3D(nn.Module):
         else:
             conv_feat, stage_feats, extra = self.imgpts_neck(neck, extra_out=extra_view, neck_s=neck_s)
         ops.mark("focal_encoder")
-        res = head(conv_feat, stage_feats, ms_value, geom)
+        res = head(conv_feat, stage_feats, ms_value, geom, split_feats=getattr(self.imgpts_neck, "split_feats", None))
         det = head.get_bboxes()
         ops.mark("heads+decode")
         self._overflow = overflow

@@ -330,7 +330,7 @@ def tma_ok(w, cin, cout, sparse=False):
     multiple of 128; sparse layers (cp.async gather) also the narrow levels cin 8 / 16 / 32, cout 16 / 32."""
     if not (USE_TC and USE_TMA and w.img is not None and w.kind == "f16"):
         return False
-    wide = cin % 64 == 0 and cin >= 64 and (cout % 128 == 0 or cout == 64) and w.bn in (64, 128)
+    wide = cin % 64 == 0 and cin >= 64 and (cout % 128 == 0 or cout in (16, 32, 64)) and w.bn in (16, 32, 64, 128)
     if sparse:
         return bool(wide or ((cin in (8, 16, 32) or (cin % 64 == 0 and cin >= 64))
                              and (cout in (16, 32, 64) or cout % 128 == 0) and w.bn in (16, 32, 64, 128)))
@@ -502,6 +502,18 @@ def dwconv3x3(x, w, bias, out, act=ACT_RELU6):
         raise L.Ff3dError("dwconv3x3: batch-dense views required")
     check(lib.ff3d_dwconv3x3(_ptr(x), ldx, _ptr(w), _ptr(bias), _ptr(out), ldy, B, H, W, Cc, act, _stream()),
           "ff3d_dwconv3x3")
+    _count()
+    return out
+
+
+def dwconv3x3_split(x, w, bias, act=ACT_RELU6):
+    """dwconv3x3 whose output goes straight into split form ([B,H,W,2C] fp16) for a TMA-fed 1x1 conv."""
+    B, H, W, Cc, ldx, xbs = _nhwc_geom(x, "dwconv.x")
+    if xbs != H * W:
+        raise L.Ff3dError("dwconv3x3_split: batch-dense view required")
+    out = Split.empty((B, H, W), Cc, x.device)
+    check(lib.ff3d_dwconv3x3_split(_ptr(x), ldx, _ptr(w), _ptr(bias), C.c_void_p(out.ptr), B, H, W, Cc, act,
+                                   _ptr(gemm_flag(x.device)), _stream()), "ff3d_dwconv3x3_split")
     _count()
     return out
 
@@ -821,6 +833,31 @@ def roi_sample(query_box, value, geom, Cc, g, expand, cell, origin, roi_range, o
                               geom.w, geom.s, geom.L, Cc, g, float(expand), float(cell[0]), float(cell[1]),
                               float(origin[0]), float(origin[1]), L.float_array(roi_range), _ptr(out), B, Nq, _stream()),
           "ff3d_roi_sample")
+    _count()
+    return out
+
+
+def roi_sample_split(query_box, value, geom, Cc, g, expand, cell, origin, roi_range, B, Nq):
+    """roi_sample with the [B*Nq, L*g*g*C] operand written straight in split form (fp16 [hi | lo]) for the TMA-fed
+    roi_mlp.0 GEMM: same bytes as the fp32 operand, no conversion inside the GEMM."""
+    ldv = value.stride(1)
+    K = geom.L * g * g * Cc
+    out = Split.empty((B * Nq,), K, value.device)
+    check(lib.ff3d_roi_sample_split(_ptr(query_box), query_box.stride(0), _ptr(value), ldv, value.stride(0) // ldv, geom.h,
+                                    geom.w, geom.s, geom.L, Cc, g, float(expand), float(cell[0]), float(cell[1]),
+                                    float(origin[0]), float(origin[1]), L.float_array(roi_range), C.c_void_p(out.ptr), B, Nq,
+                                    _ptr(gemm_flag(value.device)), _stream()), "ff3d_roi_sample_split")
+    _count()
+    return out
+
+
+def add_bcast_rows_split(a, p):
+    """Split of (a[b] + p) for a [B, rows, C] contiguous, p [rows, C]: [B*rows, 2C] fp16 [hi | lo]."""
+    assert a.is_contiguous() and p.is_contiguous()
+    B, rows, Cc = a.shape
+    out = Split.empty((B * rows,), Cc, a.device)
+    check(lib.ff3d_add_bcast_rows_split(_ptr(a), _ptr(p), C.c_void_p(out.ptr), B, rows, Cc, _ptr(gemm_flag(a.device)), _stream()),
+          "ff3d_add_bcast_rows_split")
     _count()
     return out
 

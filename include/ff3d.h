@@ -216,6 +216,10 @@ int ff3d_unsplit_rows(const void* xs, int ldxs, int xs_lo, const int* n_dev, lon
 int ff3d_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy, int B, int H, int W,
                    int C, int act, ff3d_stream_t stream);
 
+/* same depthwise conv with the output in split form only: ys [B*H*W, 2C] fp16 [hi | lo] (A operand of the TMA-fed project conv) */
+int ff3d_dwconv3x3_split(const float* x, int ldx, const float* w, const float* bias, void* ys, int B, int H, int W, int C, int act,
+                         int* overflow_dev, ff3d_stream_t stream);
+
 /* y = LayerNorm(x) * gamma + beta over the last dim C (nn.LayerNorm, eps) -- [upstream] mmcv BaseTransformerLayer norms */
 int ff3d_layernorm(const float* x, const float* gamma, const float* beta, float* y, int rows, int C, float eps,
                    ff3d_stream_t stream);
