@@ -4,23 +4,27 @@
 namespace ff3d {
 
 // thread = (pixel, 4 channels); weights [9, C]; 9 float4 loads per output float4 (neighbours hit L1/L2)
-// SPLIT: the output is written in split form (fp16 [hi(C) | lo(C)] rows, for a TMA-fed 1x1 conv) instead of fp32
+// SPLIT: the output is written in split form (fp16 [hi(C) | lo(C)] rows, for a TMA-fed 1x1 conv) instead of fp32; a
+// thread then owns 8 channels so that both planes get 16-byte stores
 template <bool SPLIT>
 __global__ void dwconv3x3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                  const float* __restrict__ bias, float* __restrict__ y, int ldy, int B, int H, int W,
                                  int C, int act, __half* __restrict__ ys, int* overflow) {
+  constexpr int V = SPLIT ? 2 : 1;                       // float4 vectors per thread
   bool ovf = false;
-  int c4n = C >> 2;
-  long long total = (long long)B * H * W * c4n;
+  int cvn = C / (4 * V);
+  long long total = (long long)B * H * W * cvn;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(e % c4n);
-    long long pix = e / c4n;
+    int cv = (int)(e % cvn);
+    long long pix = e / cvn;
     int xw = (int)(pix % W);
     long long r = pix / W;
     int yh = (int)(r % H);
     int b = (int)(r / H);
-    int c = c4 * 4;
-    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = cv * 4 * V;
+    float4 acc[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc[u] = bias ? __ldg(reinterpret_cast<const float4*>(bias + c + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       int iy = yh + ky - 1;
@@ -29,21 +33,28 @@ __global__ void dwconv3x3_kernel(const float* __restrict__ x, int ldx, const flo
       for (int kx = 0; kx < 3; ++kx) {
         int ix = xw + kx - 1;
         if (ix < 0 || ix >= W) continue;
-        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * ldx + c));
-        float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + c));
-        acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
-        acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * ldx + c + 4 * u));
+          float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + c + 4 * u));
+          acc[u].x = fmaf(v.x, k.x, acc[u].x); acc[u].y = fmaf(v.y, k.y, acc[u].y);
+          acc[u].z = fmaf(v.z, k.z, acc[u].z); acc[u].w = fmaf(v.w, k.w, acc[u].w);
+        }
       }
     }
-    acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
-    acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
-    if (SPLIT) {
-      uint32_t h01, h23, l01, l23;
-      split_f16x4(acc, h01, h23, l01, l23, ovf);
-      *reinterpret_cast<uint2*>(ys + pix * 2 * C + c) = make_uint2(h01, h23);
-      *reinterpret_cast<uint2*>(ys + pix * 2 * C + C + c) = make_uint2(l01, l23);
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      acc[u].x = apply_act(acc[u].x, act); acc[u].y = apply_act(acc[u].y, act);
+      acc[u].z = apply_act(acc[u].z, act); acc[u].w = apply_act(acc[u].w, act);
+    }
+    if constexpr (SPLIT) {
+      uint32_t hw[4], lw[4];
+      split_f16x4(acc[0], hw[0], hw[1], lw[0], lw[1], ovf);
+      split_f16x4(acc[1], hw[2], hw[3], lw[2], lw[3], ovf);
+      *reinterpret_cast<uint4*>(ys + pix * 2 * C + c) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(ys + pix * 2 * C + C + c) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     } else {
-      *reinterpret_cast<float4*>(y + pix * ldy + c) = acc;
+      *reinterpret_cast<float4*>(y + pix * ldy + c) = acc[0];
     }
   }
   if (SPLIT && ovf && overflow) atomicOr(overflow, 1);
@@ -290,7 +301,7 @@ extern "C" int ff3d_dwconv3x3_split(const float* x, int ldx, const float* w, con
                                     int C, int act, int* overflow_dev, ff3d_stream_t stream) {
   using namespace ff3d;
   FF3D_REQUIRE(C % 8 == 0 && ldx % 4 == 0, "dwconv3x3_split: C must be a multiple of 8, ldx of 4");
-  long long total = (long long)B * H * W * (C / 4);
+  long long total = (long long)B * H * W * (C / 8);
   dwconv3x3_kernel<true><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, ldx, w, bias, nullptr, 0, B, H, W, C, act,
                                                                                static_cast<__half*>(ys), overflow_dev);
   return check_launch("ff3d_dwconv3x3_split");

@@ -23,70 +23,69 @@ __global__ void sine_embed_kernel(const float* __restrict__ pos, float w, float 
 // ------------------------------------------------------------------------------------------------------------
 // softmax(q k^T / sqrt(d)) v, one warp per query, K/V of one (batch, head) staged in shared memory
 constexpr int MHA_MAXQ = 1024;
+// One LANE per query (round 2; the round-1 kernel put one warp on a query with the lanes over the keys: two LDS per FMA,
+// shared-memory-issue bound at ~90 us for 4 x 8 x 600 x 600).  Here the K / V rows of the (scene, head) sit in shared
+// memory as 64-byte rows and every lane of a warp reads the SAME row -- one broadcast LDS.128 feeds 32 lanes x 4 values,
+// 8 LDS per 32 FMA -- while q, the output accumulators and the soft-max state stay in registers.  Two passes over the
+// keys (row maximum, then exp / sum / weighted values with the scores recomputed): plain soft-max arithmetic in fp32.
 template <int D>
-__global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+__global__ void __launch_bounds__(128) mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                                        int ldk, const float* __restrict__ v, int ldv,
                                                        float* __restrict__ out, int ldo, int Nq, int heads) {
-  extern __shared__ float sm[];
-  float* Ks = sm;                      // [Nq][D+1]
-  float* Vs = sm + (size_t)Nq * (D + 1);
+  extern __shared__ __align__(16) float sm[];
+  float* Ks = sm;                      // [Nq][D]
+  float* Vs = sm + (size_t)Nq * D;
   const int bh = blockIdx.x;
   const int b = bh / heads, h = bh - b * heads;
   const size_t row0 = (size_t)b * Nq;
-  for (int e = threadIdx.x; e < Nq * D; e += blockDim.x) {
-    int j = e / D, c = e - j * D;
-    Ks[j * (D + 1) + c] = k[(row0 + j) * ldk + h * D + c];
-    Vs[j * (D + 1) + c] = v[(row0 + j) * ldv + h * D + c];
+  for (int e = threadIdx.x; e < Nq * (D / 4); e += blockDim.x) {
+    const int j = e / (D / 4), c4 = e - j * (D / 4);
+    reinterpret_cast<float4*>(Ks)[e] = __ldg(reinterpret_cast<const float4*>(k + (row0 + j) * ldk + h * D) + c4);
+    reinterpret_cast<float4*>(Vs)[e] = __ldg(reinterpret_cast<const float4*>(v + (row0 + j) * ldv + h * D) + c4);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int qi = blockIdx.y * blockDim.x + threadIdx.x;
+  if (qi >= Nq) return;
   const float scale = rsqrtf((float)D);
-  for (int qi = blockIdx.y * nwarp + warp; qi < Nq; qi += gridDim.y * nwarp) {
-    float qr[D];
+  float qr[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) qr[c] = q[(row0 + qi) * ldq + h * D + c] * scale;
-    float sc[MHA_MAXQ / 32];
-    float mx = -INFINITY;
+  for (int c = 0; c < D; c += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(q + (row0 + qi) * ldq + h * D + c));
+    qr[c] = t.x * scale; qr[c + 1] = t.y * scale; qr[c + 2] = t.z * scale; qr[c + 3] = t.w * scale;
+  }
+  auto score = [&](int j) -> float {
+    const float4* kr = reinterpret_cast<const float4*>(Ks + (size_t)j * D);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int t = 0; t < MHA_MAXQ / 32; ++t) {
-      int j = lane + t * 32;
-      float s = -INFINITY;
-      if (j < Nq) {
-        s = 0.f;
-#pragma unroll
-        for (int c = 0; c < D; ++c) s = fmaf(qr[c], Ks[j * (D + 1) + c], s);
-      }
-      sc[t] = s;
-      mx = fmaxf(mx, s);
+    for (int c = 0; c < D / 4; ++c) {
+      const float4 t = kr[c];
+      s0 = fmaf(qr[4 * c], t.x, s0); s1 = fmaf(qr[4 * c + 1], t.y, s1);
+      s2 = fmaf(qr[4 * c + 2], t.z, s2); s3 = fmaf(qr[4 * c + 3], t.w, s3);
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    float acc[D];
+    return (s0 + s1) + (s2 + s3);
+  };
+  float mx = -INFINITY;
+  for (int j = 0; j < Nq; ++j) mx = fmaxf(mx, score(j));
+  float sum = 0.f;
+  float acc[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = 0.f;
+  for (int c = 0; c < D; ++c) acc[c] = 0.f;
+  for (int j = 0; j < Nq; ++j) {
+    const float pj = expf(score(j) - mx);
+    sum += pj;
+    const float4* vr = reinterpret_cast<const float4*>(Vs + (size_t)j * D);
 #pragma unroll
-    for (int t = 0; t < MHA_MAXQ / 32; ++t) {
-      int j = lane + t * 32;
-      if (j < Nq) {
-        float pj = expf(sc[t] - mx);
-        sum += pj;
-#pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] = fmaf(pj, Vs[j * (D + 1) + c], acc[c]);
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-#pragma unroll
-    for (int c = 0; c < D; ++c)
-      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-    float inv = 1.f / sum;
-    if (lane < D) {
-      float r = 0.f;
-#pragma unroll
-      for (int c = 0; c < D; ++c)
-        if (c == lane) r = acc[c];
-      out[(row0 + qi) * ldo + h * D + lane] = r * inv;
+    for (int c = 0; c < D / 4; ++c) {
+      const float4 t = vr[c];
+      acc[4 * c] = fmaf(pj, t.x, acc[4 * c]); acc[4 * c + 1] = fmaf(pj, t.y, acc[4 * c + 1]);
+      acc[4 * c + 2] = fmaf(pj, t.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(pj, t.w, acc[4 * c + 3]);
     }
   }
+  const float inv = 1.f / sum;
+  float* op = out + (row0 + qi) * ldo + h * D;
+#pragma unroll
+  for (int c = 0; c < D; c += 4)
+    *reinterpret_cast<float4*>(op + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -160,53 +159,75 @@ struct RoiP {
   float expand, cell_x, cell_y, origin_x, origin_y, rx0, ry0, rx1, ry1;
 };
 // block = one query, threads = channels; out row = [L][g*g][C]
-// SPLIT: the row is written as fp16 [hi(K) | lo(K)] (K = L*g*g*C) for the TMA-fed roi_mlp.0 GEMM instead of fp32
+// bilinear sample of 4 consecutive channels (grid_sample align_corners=False, zero padding), base = token (0, 0)
+__device__ __forceinline__ float4 bilinear_zero4(const float* __restrict__ base, long long ld, int H, int W, float px, float py,
+                                                 int col) {
+  const float x0f = floorf(px), y0f = floorf(py);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const float fx = px - x0f, fy = py - y0f;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int xi = x0 + dx, yi = y0 + dy;
+      if (xi >= 0 && xi < W && yi >= 0 && yi < H) {
+        const float wgt = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy);
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + ((long long)yi * W + xi) * ld + col));
+        v.x = fmaf(wgt, t.x, v.x); v.y = fmaf(wgt, t.y, v.y); v.z = fmaf(wgt, t.z, v.z); v.w = fmaf(wgt, t.w, v.w);
+      }
+    }
+  return v;
+}
+
+// One warp per (query, grid point): the lanes cover the channels four at a time (one 512-byte row per corner and level),
+// out row = [L][g*g][C].  SPLIT: the row is written as fp16 [hi(K) | lo(K)] (K = L*g*g*C) for the TMA-fed roi_mlp.0 GEMM.
 template <bool SPLIT>
-__global__ void roi_sample_kernel(const float* __restrict__ qbox, RoiP p, const float* __restrict__ value, int ldv,
-                                  long long v_bstride, Levels lv, float* __restrict__ out, __half* __restrict__ outs, int Nq,
-                                  int* overflow) {
-  long long bq = blockIdx.x;
-  int b = (int)(bq / Nq);
-  const float* qb = qbox + bq * p.box_ld;
-  // decode_box (transfusion_bbox_coder.py:54-69) on (centre, expanded log-dims, sin/cos)
-  float cx = qb[0] * p.cell_x + p.origin_x;
-  float cy = qb[1] * p.cell_y + p.origin_y;
-  float w = expf(qb[3] * p.expand), l = expf(qb[4] * p.expand);
-  float yaw = atan2f(qb[6], qb[7]);
-  float sn = sinf(yaw), cs = cosf(yaw);
-  const float* vb = value + (long long)b * v_bstride * ldv;
-  int G = p.g * p.g;
+__global__ void __launch_bounds__(256) roi_sample_kernel(const float* __restrict__ qbox, RoiP p, const float* __restrict__ value,
+                                                         int ldv, long long v_bstride, Levels lv, float* __restrict__ out,
+                                                         __half* __restrict__ outs, int Nq, long long n_items, int* overflow) {
+  const int lane = threadIdx.x & 31;
+  const int G = p.g * p.g;
   const long long K = (long long)lv.L * G * p.C;
-  float* orow = SPLIT ? nullptr : out + bq * K;
-  __half* srow = SPLIT ? outs + bq * 2 * K : nullptr;
   bool ovf = false;
-  for (int n = 0; n < G; ++n) {
-    int i = n / p.g, j = n - i * p.g;
-    float gx = ((float)i + 0.5f) / (float)p.g * w - w / 2.f;
-    float gy = ((float)j + 0.5f) / (float)p.g * l - l / 2.f;
+  for (long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; item < n_items;
+       item += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const long long bq = item / G;
+    const int n = (int)(item - bq * G);
+    const int b = (int)(bq / Nq);
+    const float* qb = qbox + bq * p.box_ld;
+    // decode_box (transfusion_bbox_coder.py:54-69) on (centre, expanded log-dims, sin/cos)
+    const float cx = qb[0] * p.cell_x + p.origin_x;
+    const float cy = qb[1] * p.cell_y + p.origin_y;
+    const float w = expf(qb[3] * p.expand), l = expf(qb[4] * p.expand);
+    const float yaw = atan2f(qb[6], qb[7]);
+    const float sn = sinf(yaw), cs = cosf(yaw);
+    const float* vb = value + (long long)b * v_bstride * ldv;
+    const int i = n / p.g, j = n - i * p.g;
+    const float gx = ((float)i + 0.5f) / (float)p.g * w - w / 2.f;
+    const float gy = ((float)j + 0.5f) / (float)p.g * l - l / 2.f;
     // [upstream] mmdet3d v0.17.1 rotation_3d_in_axis(axis=2): x' = x cos + y sin, y' = -x sin + y cos
-    float wx = gx * cs + gy * sn + cx;
-    float wy = -gx * sn + gy * cs + cy;
+    const float wx = gx * cs + gy * sn + cx;
+    const float wy = -gx * sn + gy * cs + cy;
     float nx = (wx - p.rx0) / (p.rx1 - p.rx0) * 2.f - 1.f;
     float ny = (wy - p.ry0) / (p.ry1 - p.ry0) * 2.f - 1.f;
     nx = fminf(fmaxf(nx, -2.f), 2.f);
     ny = fminf(fmaxf(ny, -2.f), 2.f);
     for (int lvl = 0; lvl < lv.L; ++lvl) {
-      int H = lv.h[lvl], W = lv.w[lvl];
-      float px = ((nx + 1.f) * (float)W - 1.f) / 2.f;
-      float py = ((ny + 1.f) * (float)H - 1.f) / 2.f;
+      const int H = lv.h[lvl], W = lv.w[lvl];
+      const float px = ((nx + 1.f) * (float)W - 1.f) / 2.f;
+      const float py = ((ny + 1.f) * (float)H - 1.f) / 2.f;
       const float* base = vb + (long long)lv.start[lvl] * ldv;
-      for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-        const float v = bilinear_zero(base, ldv, H, W, px, py, c);
+      for (int c = lane * 4; c < p.C; c += 128) {
+        const float4 v = bilinear_zero4(base, ldv, H, W, px, py, c);
         const long long k = ((long long)lvl * G + n) * p.C + c;
         if (SPLIT) {
-          const float cv = fminf(fmaxf(v, -F16_MAX), F16_MAX);
-          ovf = ovf || cv != v;
-          const __half hi = __float2half_rn(cv);
-          srow[k] = hi;
-          srow[K + k] = __float2half_rn(fminf(fmaxf((cv - __half2float(hi)) * 2048.f, -F16_MAX), F16_MAX));
+          uint32_t h01, h23, l01, l23;
+          split_f16x4(v, h01, h23, l01, l23, ovf);
+          *reinterpret_cast<uint2*>(outs + bq * 2 * K + k) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(outs + bq * 2 * K + K + k) = make_uint2(l01, l23);
         } else {
-          orow[k] = v;
+          *reinterpret_cast<float4*>(out + bq * K + k) = v;
         }
       }
     }
@@ -311,25 +332,24 @@ extern "C" int ff3d_mha_core(const float* q, int ldq, const float* k, int ldk, c
   using namespace ff3d;
   FF3D_REQUIRE(d == 16 || d == 32, "mha_core: head dim %d unsupported (16, 32)", d);
   FF3D_REQUIRE(Nq >= 1 && Nq <= MHA_MAXQ, "mha_core: Nq=%d unsupported (<= %d)", Nq, MHA_MAXQ);
-  size_t smem = (size_t)2 * Nq * (d + 1) * sizeof(float);
+  size_t smem = (size_t)2 * Nq * d * sizeof(float);
   FF3D_REQUIRE(smem <= 220 * 1024, "mha_core: K/V tile does not fit shared memory");
-  // query chunks per (batch, head): ~64 queries each, but never more CTAs than fit in ONE wave (two 81 KB CTAs per SM)
-  // -- 4 x 8 x 10 = 320 CTAs on 296 slots ran a nearly empty second wave
-  int ny = cdiv(Nq, 64);
-  const int one_wave = (2 * num_sms()) / (B * heads);
-  if (ny > one_wave && one_wave >= 1) ny = one_wave;
-  dim3 grid(B * heads, ny);
+  FF3D_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                     reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "mha_core: q / k / v / out rows must be 16-byte aligned");
+  // one lane per query, 128 queries per CTA: B * heads * ceil(Nq / 128) CTAs (4 x 8 x 5 = 160 for the flagship)
+  dim3 grid(B * heads, cdiv(Nq, 128));
   cudaStream_t st = as_stream(stream);
   // the shared-memory size depends on Nq: opt in to the device maximum once (thread-safe static initialisers)
-  FF3D_REQUIRE(smem <= 227 * 1024, "mha_core: Nq=%d needs %zu bytes of shared memory", Nq, smem);
   if (d == 16) {
     static const cudaError_t attr = cudaFuncSetAttribute(mha_core_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     (void)attr;
-    mha_core_kernel<16><<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, heads);
+    mha_core_kernel<16><<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, heads);
   } else {
     static const cudaError_t attr = cudaFuncSetAttribute(mha_core_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     (void)attr;
-    mha_core_kernel<32><<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, heads);
+    mha_core_kernel<32><<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, heads);
   }
   return check_launch("ff3d_mha_core");
 }
@@ -358,7 +378,11 @@ extern "C" int ff3d_roi_sample(const float* query_box, int box_ld, const float* 
   RoiP p{box_ld, g, C, expand, cell_x, cell_y, origin_x, origin_y, roi_range4[0], roi_range4[1], roi_range4[2],
          roi_range4[3]};
   if (B * Nq <= 0) return FF3D_OK;
-  roi_sample_kernel<false><<<B * Nq, 128, 0, as_stream(stream)>>>(query_box, p, value, ldv, v_bstride, lv, out, nullptr, Nq, nullptr);
+  FF3D_REQUIRE(C % 4 == 0 && ldv % 4 == 0, "roi_sample: C and ldv must be multiples of 4");
+  const long long items = (long long)B * Nq * g * g;
+  long long nb = (items * 32 + 255) / 256, cap = (long long)num_sms() * 16;
+  roi_sample_kernel<false><<<(int)(nb > cap ? cap : nb), 256, 0, as_stream(stream)>>>(query_box, p, value, ldv, v_bstride, lv, out,
+                                                                                      nullptr, Nq, items, nullptr);
   return check_launch("ff3d_roi_sample");
 }
 
@@ -373,8 +397,11 @@ extern "C" int ff3d_roi_sample_split(const float* query_box, int box_ld, const f
   RoiP p{box_ld, g, C, expand, cell_x, cell_y, origin_x, origin_y, roi_range4[0], roi_range4[1], roi_range4[2],
          roi_range4[3]};
   if (B * Nq <= 0) return FF3D_OK;
-  roi_sample_kernel<true><<<B * Nq, 128, 0, as_stream(stream)>>>(query_box, p, value, ldv, v_bstride, lv, nullptr,
-                                                                static_cast<__half*>(out_split), Nq, overflow_dev);
+  FF3D_REQUIRE(C % 4 == 0 && ldv % 4 == 0, "roi_sample: C and ldv must be multiples of 4");
+  const long long items = (long long)B * Nq * g * g;
+  long long nb = (items * 32 + 255) / 256, cap = (long long)num_sms() * 16;
+  roi_sample_kernel<true><<<(int)(nb > cap ? cap : nb), 256, 0, as_stream(stream)>>>(
+      query_box, p, value, ldv, v_bstride, lv, nullptr, static_cast<__half*>(out_split), Nq, items, overflow_dev);
   return check_launch("ff3d_roi_sample_split");
 }
 

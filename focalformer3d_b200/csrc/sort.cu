@@ -26,9 +26,14 @@ __global__ void __launch_bounds__(256) rs_hist_kernel(const uint32_t* __restrict
   for (int d = threadIdx.x; d < RS_BINS; d += blockDim.x) h[d] = 0;
   __syncthreads();
   const int base = blockIdx.x * RS_ELEMS;
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
   for (int k = threadIdx.x; k < RS_ELEMS; k += blockDim.x) {
     const int i = base + k;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & (RS_BINS - 1)], 1);
+    // warp-aggregated counting: tap masks are heavily skewed (a few digits dominate), and 32 lanes adding to the same
+    // shared-memory word serialise; one add per distinct digit of the warp instead
+    const int d = i < n ? (int)((keys[i] >> shift) & (RS_BINS - 1)) : RS_BINS + (int)(threadIdx.x & 31);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (i < n && (peers & lt) == 0u) atomicAdd(&h[d], __popc(peers));
   }
   __syncthreads();
   for (int d = threadIdx.x; d < RS_BINS; d += blockDim.x) H[(size_t)d * nblk + blockIdx.x] = h[d];
@@ -92,7 +97,9 @@ __global__ void __launch_bounds__(256) rs_scatter_kernel(const uint32_t* __restr
   for (int r = 0; r < RS_ROUNDS; ++r) {
     const int i = wbase + r * 32 + lane;
     kreg[r] = i < n ? keys_in[i] : 0u;
-    if (i < n) atomicAdd(&wh[w][(kreg[r] >> shift) & (RS_BINS - 1)], 1);
+    const int d = i < n ? (int)((kreg[r] >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (i < n && (peers & ((1u << lane) - 1u)) == 0u) wh[w][d] += __popc(peers);     // this warp's private row: no atomics
   }
   __syncthreads();
   for (int d = tid; d < RS_BINS; d += blockDim.x) {

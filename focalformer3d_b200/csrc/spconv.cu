@@ -94,6 +94,119 @@ __global__ void sp_down_sites_kernel(const int* __restrict__ coors_in, const int
   }
 }
 
+// ---- site creation without a global row counter (round 2) -----------------------------------------------------------
+// sp_down_sites_kernel above hands out rows with one atomicAdd per warp on a single counter: ~250 us for 1.5 M proposals
+// (ncu), the largest rulebook kernel.  Row numbers of a new level are arbitrary (the level is re-stored in tap-mask
+// order right afterwards), so: (1) insert the proposed keys, nothing else; (2) count the occupied slots per 2048-slot
+// block; (3) scan the block counts; (4) number the occupied slots in slot order and decode their coordinates from the key.
+// Deterministic, no contended atomics.
+constexpr int SITE_BLK = 2048;     // hash slots per block (256 threads x 8)
+
+__global__ void sp_sites_insert_kernel(const int* __restrict__ coors_in, const int* __restrict__ n_in_dev, int cap_in, Down g,
+                                       uint32_t* hkeys_out, int hmask_out, volatile int* overflow) {
+  const int n = min(*n_in_dev, cap_in);
+  const int kvol = g.k[0] * g.k[1] * g.k[2];
+  const long long total = (long long)n * kvol;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / kvol);
+    const int t = (int)(e - (long long)i * kvol);
+    const int kz = t / (g.k[1] * g.k[2]), ky = (t / g.k[2]) % g.k[1], kx = t % g.k[2];
+    const int4 c = reinterpret_cast<const int4*>(coors_in)[i];
+    const int vz = c.y + g.p[0] - kz, vy = c.z + g.p[1] - ky, vx = c.w + g.p[2] - kx;
+    if (vz < 0 || vy < 0 || vx < 0) continue;
+    if (vz % g.s[0] || vy % g.s[1] || vx % g.s[2]) continue;
+    const int oz = vz / g.s[0], oy = vy / g.s[1], ox = vx / g.s[2];
+    if (oz >= g.Do || oy >= g.Ho || ox >= g.Wo) continue;
+    bool ins;
+    if (hash_insert(hkeys_out, hmask_out, lin_key(c.x, oz, oy, ox, g.Do, g.Ho, g.Wo), &ins) < 0) *overflow = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) sp_sites_count_kernel(const uint32_t* __restrict__ hkeys, int hsize, int* bcount) {
+  __shared__ int sh[8];
+  const int base = blockIdx.x * SITE_BLK + threadIdx.x * 8;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c += (base + k < hsize && hkeys[base + k] != kEmptyKey) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    bcount[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of the block counts in place, total -> bcount[nb]
+__global__ void __launch_bounds__(1024) sp_sites_scan_kernel(int* bcount, int nb) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? bcount[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int incl = sh[threadIdx.x];
+    if (i < nb) bcount[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bcount[nb] = carry;
+}
+
+__global__ void __launch_bounds__(256) sp_sites_assign_kernel(const uint32_t* __restrict__ hkeys, int hsize,
+                                                              const int* __restrict__ bcount, int nb, Down g, int* coors_out,
+                                                              int* hvals, int* n_out_dev, int cap_out, int* overflow) {
+  __shared__ int sh[256];
+  const int base = blockIdx.x * SITE_BLK + threadIdx.x * 8;
+  uint32_t key[8];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    key[k] = base + k < hsize ? hkeys[base + k] : kEmptyKey;
+    c += key[k] != kEmptyKey ? 1 : 0;
+  }
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int row = bcount[blockIdx.x] + sh[threadIdx.x] - c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (key[k] == kEmptyKey) continue;
+    if (row < cap_out) {
+      uint32_t r = key[k];
+      const int x = (int)(r % (uint32_t)g.Wo); r /= (uint32_t)g.Wo;
+      const int y = (int)(r % (uint32_t)g.Ho); r /= (uint32_t)g.Ho;
+      const int z = (int)(r % (uint32_t)g.Do); r /= (uint32_t)g.Do;
+      reinterpret_cast<int4*>(coors_out)[row] = make_int4((int)r, z, y, x);
+      hvals[base + k] = row;
+    } else {
+      hvals[base + k] = -1;
+    }
+    ++row;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int total = bcount[nb];
+    *n_out_dev = total < cap_out ? total : cap_out;
+    if (total > cap_out) *overflow = 1;
+  }
+}
+
 __global__ void sp_clamp_count_kernel(int* n_dev, int cap) {
   if (*n_dev > cap) *n_dev = cap;
 }
@@ -363,20 +476,26 @@ extern "C" int ff3d_sp_nbr_build(const int* coors_out, const int* perm, const in
 extern "C" int ff3d_sp_down_sites(const int* coors_in, const int* n_in_dev, int cap_in, int batch, int D, int H, int W,
                                   const int* k3, const int* s3, const int* p3, int* coors_out, int* n_out_dev, int cap_out,
                                   int Do, int Ho, int Wo, uint32_t* hkeys_out, int* hvals_out, int hsize_out,
-                                  int* overflow_dev, ff3d_stream_t stream) {
+                                  int* overflow_dev, int* scratch, ff3d_stream_t stream) {
   using namespace ff3d;
   FF3D_REQUIRE(is_pow2(hsize_out) && hsize_out >= 2 * cap_out, "sp_down_sites: bad hash size");
   FF3D_REQUIRE((long long)batch * Do * Ho * Wo < 0xFFFFFFFFLL, "sp_down_sites: grid too large for 32-bit keys");
+  FF3D_REQUIRE(scratch != nullptr, "sp_down_sites: scratch (ff3d_sp_down_sites_scratch_ints(hsize) ints) is missing");
   Down g;
   const int kvol = fill_down(g, k3, s3, p3, D, H, W, Do, Ho, Wo);
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(hkeys_out, 0xFF, sizeof(uint32_t) * (size_t)hsize_out, st);
-  cudaMemsetAsync(n_out_dev, 0, sizeof(int), st);
-  sp_down_sites_kernel<<<persistent_blocks((long long)cap_in * kvol, 256), 256, 0, st>>>(
-      coors_in, n_in_dev, cap_in, g, coors_out, n_out_dev, cap_out, hkeys_out, hvals_out, hsize_out - 1, overflow_dev);
-  sp_clamp_count_kernel<<<1, 1, 0, st>>>(n_out_dev, cap_out);
+  sp_sites_insert_kernel<<<persistent_blocks((long long)cap_in * kvol, 256), 256, 0, st>>>(coors_in, n_in_dev, cap_in, g, hkeys_out,
+                                                                                         hsize_out - 1, overflow_dev);
+  const int nb = cdiv(hsize_out, SITE_BLK);
+  sp_sites_count_kernel<<<nb, 256, 0, st>>>(hkeys_out, hsize_out, scratch);
+  sp_sites_scan_kernel<<<1, 1024, 0, st>>>(scratch, nb);
+  sp_sites_assign_kernel<<<nb, 256, 0, st>>>(hkeys_out, hsize_out, scratch, nb, g, coors_out, hvals_out, n_out_dev, cap_out,
+                                            overflow_dev);
   return check_launch("ff3d_sp_down_sites");
 }
+
+extern "C" int ff3d_sp_down_sites_scratch_ints(int hsize) { return (hsize + ff3d::SITE_BLK - 1) / ff3d::SITE_BLK + 2; }
 
 extern "C" int ff3d_sp_gather_rows(const float* src, int ld_src, const int* perm, const int* n_dev, int cap, float* dst,
                                    int ld_dst, int cols, ff3d_stream_t stream) {

@@ -744,11 +744,12 @@ class SparseLevel:
         coors_o = torch.empty((cap_out, 4), dtype=torch.int32, device=dev)
         n_o = torch.empty((1,), dtype=torch.int32, device=dev)
         lvl = SparseLevel(coors_o, n_o, cap_out, self.batch, oshape)
+        scratch = torch.empty((lib.ff3d_sp_down_sites_scratch_ints(lvl.hsize),), dtype=torch.int32, device=dev)
         check(lib.ff3d_sp_down_sites(_ptr(self.coors), _ptr(self.n_dev), self.cap, self.batch, D, H, W, L.int_array(k3),
                                      L.int_array(s3), L.int_array(p3), _ptr(coors_o), _ptr(n_o), cap_out, oshape[0],
                                      oshape[1], oshape[2], _ptr(lvl.hkeys), _ptr(lvl.hvals), lvl.hsize, _ptr(overflow),
-                                     _stream()), "ff3d_sp_down_sites")
-        _count(4)
+                                     _ptr(scratch), _stream()), "ff3d_sp_down_sites")
+        _count(5)
         if sort_level:
             lvl.sort_by_mask()
         perm = self._sorted_perm(lvl.coors, n_o, cap_out, k3, s3, p3)

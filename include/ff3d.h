@@ -94,7 +94,8 @@ int ff3d_sp_down_build(const int* coors_in, const int* n_in_dev, int cap_in, int
  * that the 128-row tiles of the gather-GEMM are homogeneous and the kernel skips, per tile, every tap no row of the tile
  * uses (ff3d_gemm_desc.tile_mask).  Same [upstream] get_indice_pairs semantics as above (i = o*s - p + k); only the ROW
  * ORDER -- implementation-defined in spconv -- changes.
- *   ff3d_sp_down_sites   the site-creation half of ff3d_sp_down_build (output coordinates + hash, allocation order)
+ *   ff3d_sp_down_sites   the site-creation half of ff3d_sp_down_build: insert the proposed output keys, then number the
+ *                        occupied hash slots in slot order (block counts + scan: no contended row counter, deterministic)
  *   ff3d_sp_tap_keys     keys[o] = tap mask of output row o (probing the INPUT level's hash) with the bits permuted into
  *                        rarity order (corner taps most significant); kvol = k0*k1*k2 <= 27 key bits
  *   ff3d_sort_pairs      stable LSD radix sort of (key, value) with a device-side count; vals_in NULL -> 0..n-1
@@ -106,7 +107,8 @@ int ff3d_sp_down_build(const int* coors_in, const int* n_in_dev, int cap_in, int
 int ff3d_sp_down_sites(const int* coors_in, const int* n_in_dev, int cap_in, int batch, int D, int H, int W,
                        const int* k3, const int* s3, const int* p3, int* coors_out, int* n_out_dev, int cap_out,
                        int Do, int Ho, int Wo, uint32_t* hkeys_out, int* hvals_out, int hsize_out, int* overflow_dev,
-                       ff3d_stream_t stream);
+                       int* scratch /* ff3d_sp_down_sites_scratch_ints(hsize_out) ints */, ff3d_stream_t stream);
+int ff3d_sp_down_sites_scratch_ints(int hsize);
 int ff3d_sp_tap_keys(const int* coors_out, const int* n_out_dev, int cap_out, int D, int H, int W,
                      const uint32_t* hkeys_in, const int* hvals_in, int hsize_in, const int* k3, const int* s3,
                      const int* p3, uint32_t* keys, ff3d_stream_t stream);
