@@ -344,7 +344,8 @@ __global__ void add_bcast_rows_split_kernel(const float4* __restrict__ a, const 
     const float4 s = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
     uint32_t h01, h23, l01, l23;
     split_f16x4(s, h01, h23, l01, l23, ovf);
-    const long long e = i * 4, row = e / C;
+    const long long e = i * 4;
+    const long long row = (e >> 31) ? e / C : (long long)((unsigned)e / (unsigned)C);      // 32-bit division when it fits
     const int col = (int)(e - row * C);
     *reinterpret_cast<uint2*>(ys + row * 2 * C + col) = make_uint2(h01, h23);
     *reinterpret_cast<uint2*>(ys + row * 2 * C + C + col) = make_uint2(l01, l23);

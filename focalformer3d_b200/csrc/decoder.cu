@@ -23,11 +23,12 @@ __global__ void sine_embed_kernel(const float* __restrict__ pos, float w, float 
 // ------------------------------------------------------------------------------------------------------------
 // softmax(q k^T / sqrt(d)) v, one warp per query, K/V of one (batch, head) staged in shared memory
 constexpr int MHA_MAXQ = 1024;
-// One LANE per query (round 2; the round-1 kernel put one warp on a query with the lanes over the keys: two LDS per FMA,
-// shared-memory-issue bound at ~90 us for 4 x 8 x 600 x 600).  Here the K / V rows of the (scene, head) sit in shared
-// memory as 64-byte rows and every lane of a warp reads the SAME row -- one broadcast LDS.128 feeds 32 lanes x 4 values,
-// 8 LDS per 32 FMA -- while q, the output accumulators and the soft-max state stay in registers.  Two passes over the
-// keys (row maximum, then exp / sum / weighted values with the scores recomputed): plain soft-max arithmetic in fp32.
+// One LANE per query, the keys split over the four warps of the CTA (round 2; the round-1 kernel put one warp on a query
+// with the lanes over the keys: two LDS per FMA, shared-memory-issue bound at ~90 us for 4 x 8 x 600 x 600).  The K / V
+// rows of the (scene, head) sit in shared memory as 64-byte rows and every lane of a warp reads the SAME row -- one
+// broadcast LDS.128 feeds 32 lanes x 4 values -- while q, the output accumulators and the soft-max state stay in registers.
+// Each warp runs a two-pass soft-max (row maximum, then exp / sum / weighted values) over its quarter of the keys; the four
+// partial (max, sum, acc) states of a query are merged through shared memory (the flash-attention rescaling, in fp32).
 template <int D>
 __global__ void __launch_bounds__(128) mha_core_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                                        int ldk, const float* __restrict__ v, int ldv,
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(128) mha_core_kernel(const float* __restrict__
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;                      // [Nq][D]
   float* Vs = sm + (size_t)Nq * D;
+  float* part = Vs + (size_t)Nq * D;   // [4 warps][32 queries][D + 2]: partial acc, max, sum
   const int bh = blockIdx.x;
   const int b = bh / heads, h = bh - b * heads;
   const size_t row0 = (size_t)b * Nq;
@@ -44,13 +46,17 @@ __global__ void __launch_bounds__(128) mha_core_kernel(const float* __restrict__
     reinterpret_cast<float4*>(Vs)[e] = __ldg(reinterpret_cast<const float4*>(v + (row0 + j) * ldv + h * D) + c4);
   }
   __syncthreads();
-  const int qi = blockIdx.y * blockDim.x + threadIdx.x;
-  if (qi >= Nq) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.y * 32 + lane;
+  const bool qvalid = qi < Nq;
+  const int per = (Nq + 3) / 4;
+  const int j0 = warp * per, j1 = min(Nq, j0 + per);
   const float scale = rsqrtf((float)D);
   float qr[D];
 #pragma unroll
   for (int c = 0; c < D; c += 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(q + (row0 + qi) * ldq + h * D + c));
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qvalid) t = __ldg(reinterpret_cast<const float4*>(q + (row0 + qi) * ldq + h * D + c));
     qr[c] = t.x * scale; qr[c + 1] = t.y * scale; qr[c + 2] = t.z * scale; qr[c + 3] = t.w * scale;
   }
   auto score = [&](int j) -> float {
@@ -65,12 +71,14 @@ __global__ void __launch_bounds__(128) mha_core_kernel(const float* __restrict__
     return (s0 + s1) + (s2 + s3);
   };
   float mx = -INFINITY;
-  for (int j = 0; j < Nq; ++j) mx = fmaxf(mx, score(j));
+#pragma unroll 4
+  for (int j = j0; j < j1; ++j) mx = fmaxf(mx, score(j));
   float sum = 0.f;
   float acc[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) acc[c] = 0.f;
-  for (int j = 0; j < Nq; ++j) {
+#pragma unroll 2
+  for (int j = j0; j < j1; ++j) {
     const float pj = expf(score(j) - mx);
     sum += pj;
     const float4* vr = reinterpret_cast<const float4*>(Vs + (size_t)j * D);
@@ -81,11 +89,33 @@ __global__ void __launch_bounds__(128) mha_core_kernel(const float* __restrict__
       acc[4 * c + 2] = fmaf(pj, t.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(pj, t.w, acc[4 * c + 3]);
     }
   }
-  const float inv = 1.f / sum;
-  float* op = out + (row0 + qi) * ldo + h * D;
+  float* mine = part + ((size_t)warp * 32 + lane) * (D + 2);
 #pragma unroll
-  for (int c = 0; c < D; c += 4)
-    *reinterpret_cast<float4*>(op + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+  for (int c = 0; c < D; ++c) mine[c] = acc[c];
+  mine[D] = mx;
+  mine[D + 1] = sum;
+  __syncthreads();
+  if (warp == 0 && qvalid) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) m = fmaxf(m, part[((size_t)w * 32 + lane) * (D + 2) + D]);
+    float tot = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float* pw = part + ((size_t)w * 32 + lane) * (D + 2);
+      const float f = pw[D] == -INFINITY ? 0.f : expf(pw[D] - m);      // a warp with no keys contributes nothing
+      tot = fmaf(f, pw[D + 1], tot);
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[c] = fmaf(f, pw[c], acc[c]);
+    }
+    const float inv = 1.f / tot;
+    float* op = out + (row0 + qi) * ldo + h * D;
+#pragma unroll
+    for (int c = 0; c < D; c += 4)
+      *reinterpret_cast<float4*>(op + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -332,14 +362,14 @@ extern "C" int ff3d_mha_core(const float* q, int ldq, const float* k, int ldk, c
   using namespace ff3d;
   FF3D_REQUIRE(d == 16 || d == 32, "mha_core: head dim %d unsupported (16, 32)", d);
   FF3D_REQUIRE(Nq >= 1 && Nq <= MHA_MAXQ, "mha_core: Nq=%d unsupported (<= %d)", Nq, MHA_MAXQ);
-  size_t smem = (size_t)2 * Nq * d * sizeof(float);
+  size_t smem = ((size_t)2 * Nq * d + (size_t)4 * 32 * (d + 2)) * sizeof(float);
   FF3D_REQUIRE(smem <= 220 * 1024, "mha_core: K/V tile does not fit shared memory");
   FF3D_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 &&
                    ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                      reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                "mha_core: q / k / v / out rows must be 16-byte aligned");
-  // one lane per query, 128 queries per CTA: B * heads * ceil(Nq / 128) CTAs (4 x 8 x 5 = 160 for the flagship)
-  dim3 grid(B * heads, cdiv(Nq, 128));
+  // one lane per query, 32 queries per CTA, keys split over its 4 warps: B * heads * ceil(Nq / 32) CTAs (4 x 8 x 19 = 608)
+  dim3 grid(B * heads, cdiv(Nq, 32));
   cudaStream_t st = as_stream(stream);
   // the shared-memory size depends on Nq: opt in to the device maximum once (thread-safe static initialisers)
   if (d == 16) {

@@ -104,21 +104,30 @@ constexpr int SITE_BLK = 2048;     // hash slots per block (256 threads x 8)
 
 __global__ void sp_sites_insert_kernel(const int* __restrict__ coors_in, const int* __restrict__ n_in_dev, int cap_in, Down g,
                                        uint32_t* hkeys_out, int hmask_out, volatile int* overflow) {
+  // one thread per input site: per axis the (<= 3) taps whose output coordinate is integral and in range, then the
+  // (<= 27, typically 1-8) combinations -- no 64-bit index arithmetic, no wasted (site, tap) iterations
   const int n = min(*n_in_dev, cap_in);
-  const int kvol = g.k[0] * g.k[1] * g.k[2];
-  const long long total = (long long)n * kvol;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e / kvol);
-    const int t = (int)(e - (long long)i * kvol);
-    const int kz = t / (g.k[1] * g.k[2]), ky = (t / g.k[2]) % g.k[1], kx = t % g.k[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int4 c = reinterpret_cast<const int4*>(coors_in)[i];
-    const int vz = c.y + g.p[0] - kz, vy = c.z + g.p[1] - ky, vx = c.w + g.p[2] - kx;
-    if (vz < 0 || vy < 0 || vx < 0) continue;
-    if (vz % g.s[0] || vy % g.s[1] || vx % g.s[2]) continue;
-    const int oz = vz / g.s[0], oy = vy / g.s[1], ox = vx / g.s[2];
-    if (oz >= g.Do || oy >= g.Ho || ox >= g.Wo) continue;
-    bool ins;
-    if (hash_insert(hkeys_out, hmask_out, lin_key(c.x, oz, oy, ox, g.Do, g.Ho, g.Wo), &ins) < 0) *overflow = 1;
+    const int in3[3] = {c.y, c.z, c.w};
+    const int lim[3] = {g.Do, g.Ho, g.Wo};
+    int o[3][3], cnt[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      cnt[a] = 0;
+      for (int k = 0; k < g.k[a]; ++k) {
+        const int v = in3[a] + g.p[a] - k;
+        if (v < 0 || v % g.s[a]) continue;
+        const int ov = v / g.s[a];
+        if (ov < lim[a] && cnt[a] < 3) o[a][cnt[a]++] = ov;
+      }
+    }
+    for (int a0 = 0; a0 < cnt[0]; ++a0)
+      for (int a1 = 0; a1 < cnt[1]; ++a1)
+        for (int a2 = 0; a2 < cnt[2]; ++a2) {
+          bool ins;
+          if (hash_insert(hkeys_out, hmask_out, lin_key(c.x, o[0][a0], o[1][a1], o[2][a2], g.Do, g.Ho, g.Wo), &ins) < 0) *overflow = 1;
+        }
   }
 }
 
@@ -485,7 +494,7 @@ extern "C" int ff3d_sp_down_sites(const int* coors_in, const int* n_in_dev, int 
   const int kvol = fill_down(g, k3, s3, p3, D, H, W, Do, Ho, Wo);
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(hkeys_out, 0xFF, sizeof(uint32_t) * (size_t)hsize_out, st);
-  sp_sites_insert_kernel<<<persistent_blocks((long long)cap_in * kvol, 256), 256, 0, st>>>(coors_in, n_in_dev, cap_in, g, hkeys_out,
+  sp_sites_insert_kernel<<<persistent_blocks(cap_in, 128), 128, 0, st>>>(coors_in, n_in_dev, cap_in, g, hkeys_out,
                                                                                          hsize_out - 1, overflow_dev);
   const int nb = cdiv(hsize_out, SITE_BLK);
   sp_sites_count_kernel<<<nb, 256, 0, st>>>(hkeys_out, hsize_out, scratch);

@@ -96,6 +96,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 template <int MODE, int BN, int NS, int NPW, bool CPA = false>
 __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid_constant__ CUtensorMap tmA, const TmP p) {
   constexpr int MMA_WARP = NPW;
+  // Chunked accumulation (dense modes, one producer warp): the tensor core's fp32 accumulate TRUNCATES, once per MMA
+  // (16 products); over a long K that is a systematic bias (measured at K = 8192, all-positive products: -4.7e-5 relative,
+  // 10x the fp32 SIMT kernel, gone when the same K is summed as 8 chunks).  So the K loop is cut into chunks of CHUNK
+  // stages (32 MMA steps): every chunk accumulates into its own TMEM buffer (the two buffers alternate) and the epilogue
+  // warps -- idle during the main loop anyway -- add each finished chunk into fp32 REGISTERS with round-to-nearest.
+  constexpr bool CHUNKED = (NPW == 1);
+  constexpr int CHUNK = 8;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = TC_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
@@ -289,14 +296,21 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
     if (lane == 0) {
       const uint32_t idesc_wide = make_idesc<true>(2 * BN), idesc_cross = make_idesc<true>(BN);
       Ring ring{0, 0u};
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int ab = it & 1;
+      int gc = 0;                                        // accumulator hand-overs so far (tiles, or chunks when CHUNKED)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nst = stage_count(unit_mask(tile));
-        mbar_wait(tempty_bar + 8u * ab, (uint32_t)(((it >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(ab * ACC_COLS), d_cross = d_main + BN;
+        uint32_t d_main = 0, d_cross = 0;
+        int ab = 0;
         for (int s = 0; s < nst; ++s) {
+          const int sc = CHUNKED ? s % CHUNK : s;        // stage inside the current accumulation run
+          if (sc == 0) {
+            // the epilogue that last read this accumulator buffer (two hand-overs ago) has drained it
+            ab = gc & 1;
+            mbar_wait(tempty_bar + 8u * ab, (uint32_t)(((gc >> 1) & 1) ^ 1));
+            tc_fence_after();
+            d_main = tmem_base + (uint32_t)(ab * ACC_COLS);
+            d_cross = d_main + BN;
+          }
           mbar_wait(full_bar + 8u * ring.slot, ring.phase);
           tc_fence_after();
           const uint32_t a_hi = smem + (uint32_t)ring.slot * SLOT_BYTES, a_lo = a_hi + A_BYTES;
@@ -305,13 +319,16 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 halves = 32 bytes) per 128-byte swizzled row
             const uint64_t dbh = make_desc(b_hi + k * 32);   // as an N = 2*BN operand it runs on into B_lo
-            umma<true>(d_main, make_desc(a_hi + k * 32), dbh, idesc_wide, (s | k) ? 1u : 0u);   // main += A_hi*B_hi ; cross += A_hi*B_lo
-            umma<true>(d_cross, make_desc(a_lo + k * 32), dbh, idesc_cross, 1u);                // cross += A_lo*B_hi
+            umma<true>(d_main, make_desc(a_hi + k * 32), dbh, idesc_wide, (sc | k) ? 1u : 0u);   // main += A_hi*B_hi ; cross += A_hi*B_lo
+            umma<true>(d_cross, make_desc(a_lo + k * 32), dbh, idesc_cross, 1u);                 // cross += A_lo*B_hi
           }
           umma_commit(empty_bar + 8u * ring.slot);
           ring.advance(1, NS);
+          if (s == nst - 1 || (CHUNKED && sc == CHUNK - 1)) {
+            umma_commit(tfull_bar + 8u * ab);            // this run's accumulator is complete
+            ++gc;
+          }
         }
-        umma_commit(tfull_bar + 8u * ab);
       }
     }
     __syncwarp();
@@ -320,11 +337,12 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
     const int r = (warp & 3) * 32 + lane;                     // tile row <-> TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     bool ovf = false;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    int gc = 0;                                          // accumulator hand-overs consumed so far
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mtile = tile / n_tiles_n;
       const int n0 = (tile - mtile * n_tiles_n) * BN;
-      const int ab = it & 1;
+      const int nst = stage_count(unit_mask(tile));
+      const int n_runs = CHUNKED ? (nst + CHUNK - 1) / CHUNK : 1;
       // output row of this thread
       bool rvalid;
       long long row = 0, rrow = 0;
@@ -349,10 +367,36 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
         else yp = p.y + row * p.ldy;
       }
       __half* ysp = (rvalid && p.ys) ? p.ys + row * p.ldys : nullptr;
-      mbar_wait(tfull_bar + 8u * ab, (uint32_t)((it >> 1) & 1));
+      // running sums of the chunks (CHUNKED): one fp32 register per output column of this thread's row
+      float racc[CHUNKED ? BN : 1];
+      if constexpr (CHUNKED) {
+        for (int run = 0; run < n_runs - 1; ++run) {
+          const int abr = gc & 1;
+          mbar_wait(tfull_bar + 8u * abr, (uint32_t)((gc >> 1) & 1));
+          tc_fence_after();
+          const uint32_t accr = lane_base + (uint32_t)(abr * ACC_COLS);
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16], v2[16];
+            tmem_ld16(accr + (uint32_t)c0, v);
+            tmem_ld16(accr + (uint32_t)(BN + c0), v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float t = fmaf(v2[i], 1.f / 2048.f, v[i]);
+              racc[c0 + i] = run == 0 ? t : racc[c0 + i] + t;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(tempty_bar + 8u * abr);
+          ++gc;
+        }
+      }
+      const int ab = gc & 1;
+      mbar_wait(tfull_bar + 8u * ab, (uint32_t)((gc >> 1) & 1));
       tc_fence_after();
+      ++gc;
       const uint32_t acc = lane_base + (uint32_t)(ab * ACC_COLS);
-#pragma unroll 1
+#pragma unroll (CHUNKED ? BN / 16 : 1)
       for (int c0 = 0; c0 < BN; c0 += 16) {
         const int n = n0 + c0;
         float bs[16], rs[16];
@@ -397,6 +441,7 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float a = fmaf(v2[i], 1.f / 2048.f, v[i]);      // the cross terms carry the 2^11 scale of the lo parts
+            if constexpr (CHUNKED) { if (n_runs > 1) a += racc[c0 + i]; }
             if (p.bias) a += bs[i];
             if (p.res_after_act) a = apply_act(a, p.act);
             if (has_res) a += rs[i];

@@ -491,11 +491,22 @@ class LiftSplatShoot:
         bev = torch.empty((B, ny, nx, nz * self.CAM_C), dtype=torch.float32, device=dev)
         ops.lss_splat(dn, self.frustum, rots, trans, bev, n_img // B, self.D, self.lo, self.dx)
         ops.mark("lss_lift_splat")
-        x = bev
-        for i, (w, b, co) in enumerate(self.bevenc):
-            y = out if i == 3 else torch.empty((B, ny, nx, w.shape[-1]), dtype=torch.float32, device=dev)
-            ops.conv2d(x, w, b, y, 3, act=ACT_RELU)
-            x = y[..., :co]
+        tma = all(ops.tma_ok(w, (w.shape[1] if i == 0 else self.bevenc[i - 1][2]), w.shape[-1]) for i, (w, b, co) in enumerate(self.bevenc))
+        if tma:
+            # bevencode on the TMA-fed kernel: the splatted volume is split once, the three intermediate maps exist in split
+            # form only; K = 9 x 832 = 7488 here, which is where the chunked accumulation of tmagemm.cu matters most
+            xs = ops.split_rows(bev)
+            for i, (w, b, co) in enumerate(self.bevenc):
+                last = i == 3
+                ys = None if last else ops.Split.empty((B, ny, nx), w.shape[-1], dev)
+                ops.conv2d(xs, w, b, out if last else None, 3, act=ACT_RELU, out_s=ys)
+                xs = None if last else ys.slice(0, co)
+        else:
+            x = bev
+            for i, (w, b, co) in enumerate(self.bevenc):
+                y = out if i == 3 else torch.empty((B, ny, nx, w.shape[-1]), dtype=torch.float32, device=dev)
+                ops.conv2d(x, w, b, y, 3, act=ACT_RELU)
+                x = y[..., :co]
         ops.mark("lss_bevencode")
         return out, dn, bev
 
