@@ -284,28 +284,74 @@ __device__ __forceinline__ uint32_t probe_taps(int4 c, const Down& g, const uint
 // sort key of every output row: its tap mask with the bits permuted into rarity order
 __global__ void sp_tap_keys_kernel(const int* __restrict__ coors_out, const int* __restrict__ n_out_dev, int cap_out,
                                    Down g, TapOrder ord, const uint32_t* __restrict__ hkeys_in,
-                                   const int* __restrict__ hvals_in, int hmask_in, uint32_t* __restrict__ keys) {
+                                   const int* __restrict__ hvals_in, int hmask_in, uint32_t* __restrict__ keys,
+                                   int* __restrict__ nbr_u) {
   const int n = min(*n_out_dev, cap_out);
   const int kvol = g.k[0] * g.k[1] * g.k[2];
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     const int4 c = reinterpret_cast<const int4*>(coors_out)[o];
-    const uint32_t m = probe_taps(c, g, hkeys_in, hvals_in, hmask_in, kvol, nullptr);
+    int rows[27];
+    const uint32_t m = probe_taps(c, g, hkeys_in, hvals_in, hmask_in, kvol, nbr_u ? rows : nullptr);
     uint32_t key = 0;
     for (int t = 0; t < kvol; ++t) key |= ((m >> t) & 1u) << ord.bit[t];
     keys[o] = key;
+    // the probe results are kept (rows in the CURRENT order): ff3d_sp_nbr_permute re-orders them after the sort instead of
+    // probing the hash a second time
+    if (nbr_u)
+      for (int t = 0; t < kvol; ++t) nbr_u[(size_t)t * cap_out + o] = rows[t];
   }
 }
 
 // store a level in sorted order: coors_out[i] = coors_in[perm[i]]; the level's hash now answers with the NEW row index
 __global__ void sp_level_permute_kernel(const int* __restrict__ coors_in, const int* __restrict__ perm,
                                         const int* __restrict__ n_dev, int cap, int D, int H, int W, int* coors_out,
-                                        const uint32_t* __restrict__ hkeys, int* hvals, int hmask) {
+                                        const uint32_t* __restrict__ hkeys, int* hvals, int hmask, int* __restrict__ inv) {
   const int n = min(*n_dev, cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int4 c = reinterpret_cast<const int4*>(coors_in)[perm[i]];
+    const int old = perm[i];
+    const int4 c = reinterpret_cast<const int4*>(coors_in)[old];
     reinterpret_cast<int4*>(coors_out)[i] = c;
     const int s = hash_find(hkeys, hmask, lin_key(c.x, c.y, c.z, c.w, D, H, W));
     if (s >= 0) hvals[s] = i;
+    if (inv) inv[old] = i;                                   // old row -> new row
+  }
+}
+
+// Neighbour map in sorted tile order from the rows probed by sp_tap_keys_kernel (no second round of hash probes):
+// nbr[t][j] = remap(nbr_u[t][perm[j]]), remap = inv (SubM: the level itself was re-ordered) or identity; plus the tile
+// masks and the output row map like sp_nbr_build_kernel.  One 128-thread block per 128-row tile.
+__global__ void __launch_bounds__(128) sp_nbr_permute_kernel(const int* __restrict__ nbr_u, const int* __restrict__ perm,
+                                                             const int* __restrict__ inv, const int* __restrict__ coors_out,
+                                                             const int* __restrict__ n_out_dev, int cap_out, int kvol,
+                                                             int* __restrict__ nbr, uint32_t* __restrict__ tile_mask,
+                                                             int* __restrict__ y_off, int y_mode, int ldy, int Hb, int Wb, int Cc) {
+  __shared__ uint32_t wm[4];
+  const int n = min(*n_out_dev, cap_out);
+  const int n_tiles = (n + 127) >> 7;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int j = tile * 128 + threadIdx.x;
+    uint32_t m = 0;
+    if (j < n) {
+      const int o = perm ? perm[j] : j;
+      for (int t = 0; t < kvol; ++t) {
+        int r = nbr_u[(size_t)t * cap_out + o];
+        if (r >= 0) {
+          if (inv) r = inv[r];
+          m |= 1u << t;
+        }
+        nbr[(size_t)t * cap_out + j] = r;
+      }
+      if (y_mode == 1) y_off[j] = o;
+      else if (y_mode == 2) {
+        const int4 c = reinterpret_cast<const int4*>(coors_out)[o];
+        y_off[j] = ((c.x * Hb + c.z) * Wb + c.w) * ldy + c.y * Cc;
+      }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) tile_mask[tile] = wm[0] | wm[1] | wm[2] | wm[3];
+    __syncthreads();
   }
 }
 
@@ -445,24 +491,39 @@ static int fill_down(ff3d::Down& g, const int* k3, const int* s3, const int* p3,
 
 extern "C" int ff3d_sp_tap_keys(const int* coors_out, const int* n_out_dev, int cap_out, int D, int H, int W,
                                 const uint32_t* hkeys_in, const int* hvals_in, int hsize_in, const int* k3, const int* s3,
-                                const int* p3, uint32_t* keys, ff3d_stream_t stream) {
+                                const int* p3, uint32_t* keys, int* nbr_unsorted, ff3d_stream_t stream) {
   using namespace ff3d;
   FF3D_REQUIRE(is_pow2(hsize_in), "sp_tap_keys: hsize must be a power of two");
   Down g;
   const int kvol = fill_down(g, k3, s3, p3, D, H, W, 0, 0, 0);
   FF3D_REQUIRE(kvol >= 1 && kvol <= 27, "sp_tap_keys: kernel volume %d not in 1..27", kvol);
   sp_tap_keys_kernel<<<persistent_blocks(cap_out, 128), 128, 0, as_stream(stream)>>>(
-      coors_out, n_out_dev, cap_out, g, tap_order(k3), hkeys_in, hvals_in, hsize_in - 1, keys);
+      coors_out, n_out_dev, cap_out, g, tap_order(k3), hkeys_in, hvals_in, hsize_in - 1, keys, nbr_unsorted);
   return check_launch("ff3d_sp_tap_keys");
 }
 
 extern "C" int ff3d_sp_level_permute(const int* coors_in, const int* perm, const int* n_dev, int cap, int D, int H, int W,
-                                     int* coors_out, const uint32_t* hkeys, int* hvals, int hsize, ff3d_stream_t stream) {
+                                     int* coors_out, const uint32_t* hkeys, int* hvals, int hsize, int* inv,
+                                     ff3d_stream_t stream) {
   using namespace ff3d;
   FF3D_REQUIRE(is_pow2(hsize) && coors_in != coors_out, "sp_level_permute: bad arguments");
   sp_level_permute_kernel<<<persistent_blocks(cap, 256), 256, 0, as_stream(stream)>>>(coors_in, perm, n_dev, cap, D, H, W,
-                                                                                    coors_out, hkeys, hvals, hsize - 1);
+                                                                                    coors_out, hkeys, hvals, hsize - 1, inv);
   return check_launch("ff3d_sp_level_permute");
+}
+
+extern "C" int ff3d_sp_nbr_permute(const int* nbr_unsorted, const int* perm, const int* inv, const int* coors_out,
+                                   const int* n_out_dev, int cap_out, int kvol, int* nbr, uint32_t* tile_mask, int* y_off,
+                                   int y_mode, int ldy, int bev_h, int bev_w, int bev_c, ff3d_stream_t stream) {
+  using namespace ff3d;
+  FF3D_REQUIRE(nbr_unsorted && nbr && tile_mask && kvol >= 1 && kvol <= 27, "sp_nbr_permute: bad arguments");
+  FF3D_REQUIRE(y_mode == 0 || y_off != nullptr, "sp_nbr_permute: y_off missing");
+  FF3D_REQUIRE(y_mode != 2 || coors_out != nullptr, "sp_nbr_permute: BEV offsets need the output coordinates");
+  const int tiles = cdiv(cap_out, 128);
+  const int cap_blocks = num_sms() * 16;
+  sp_nbr_permute_kernel<<<tiles < cap_blocks ? (tiles < 1 ? 1 : tiles) : cap_blocks, 128, 0, as_stream(stream)>>>(
+      nbr_unsorted, perm, inv, coors_out, n_out_dev, cap_out, kvol, nbr, tile_mask, y_off, y_mode, ldy, bev_h, bev_w, bev_c);
+  return check_launch("ff3d_sp_nbr_permute");
 }
 
 extern "C" int ff3d_sp_nbr_build(const int* coors_out, const int* perm, const int* n_out_dev, int cap_out, int D, int H,

@@ -101,8 +101,12 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
   // 10x the fp32 SIMT kernel, gone when the same K is summed as 8 chunks).  So the K loop is cut into chunks of CHUNK
   // stages (32 MMA steps): every chunk accumulates into its own TMEM buffer (the two buffers alternate) and the epilogue
   // warps -- idle during the main loop anyway -- add each finished chunk into fp32 REGISTERS with round-to-nearest.
+  // Short K loops (<= CHUNK_MIN stages: the 3x3 convs on <= 256 channels) stay one run -- their bias is inside the parity
+  // budget and every extra drain is epilogue-warp time; the long ones (ROI MLP 294 stages, LSS bevencode 117, shared conv
+  // 72) are cut.  Measured at K = 8192: relative error 4.9e-5 (mean -4.7e-5) un-chunked -> 2.6e-6 chunked by 8 stages.
   constexpr bool CHUNKED = (NPW == 1);
-  constexpr int CHUNK = 8;
+  constexpr int CHUNK = 16;
+  constexpr int CHUNK_MIN = 40;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = TC_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
@@ -302,7 +306,8 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
         uint32_t d_main = 0, d_cross = 0;
         int ab = 0;
         for (int s = 0; s < nst; ++s) {
-          const int sc = CHUNKED ? s % CHUNK : s;        // stage inside the current accumulation run
+          const bool cut = CHUNKED && nst > CHUNK_MIN;
+          const int sc = cut ? s % CHUNK : s;            // stage inside the current accumulation run
           if (sc == 0) {
             // the epilogue that last read this accumulator buffer (two hand-overs ago) has drained it
             ab = gc & 1;
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
           }
           umma_commit(empty_bar + 8u * ring.slot);
           ring.advance(1, NS);
-          if (s == nst - 1 || (CHUNKED && sc == CHUNK - 1)) {
+          if (s == nst - 1 || (cut && sc == CHUNK - 1)) {
             umma_commit(tfull_bar + 8u * ab);            // this run's accumulator is complete
             ++gc;
           }
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
       const int mtile = tile / n_tiles_n;
       const int n0 = (tile - mtile * n_tiles_n) * BN;
       const int nst = stage_count(unit_mask(tile));
-      const int n_runs = CHUNKED ? (nst + CHUNK - 1) / CHUNK : 1;
+      const int n_runs = (CHUNKED && nst > CHUNK_MIN) ? (nst + CHUNK - 1) / CHUNK : 1;
       // output row of this thread
       bool rvalid;
       long long row = 0, rrow = 0;
@@ -377,12 +382,13 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
           const uint32_t accr = lane_base + (uint32_t)(abr * ACC_COLS);
 #pragma unroll
           for (int c0 = 0; c0 < BN; c0 += 16) {
-            float v[16], v2[16];
-            tmem_ld16(accr + (uint32_t)c0, v);
-            tmem_ld16(accr + (uint32_t)(BN + c0), v2);
+            uint32_t v[16], v2[16];
+            tmem_ld16_nowait(accr + (uint32_t)c0, v);            // main and cross in flight together, one wait
+            tmem_ld16_nowait(accr + (uint32_t)(BN + c0), v2);
+            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float t = fmaf(v2[i], 1.f / 2048.f, v[i]);
+              const float t = fmaf(__uint_as_float(v2[i]), 1.f / 2048.f, __uint_as_float(v[i]));
               racc[c0 + i] = run == 0 ? t : racc[c0 + i] + t;
             }
           }

@@ -54,10 +54,11 @@ SIGNATURES = {
                                 _I, _P, _P, _P]),
     "ff3d_sp_down_sites": (_I, [_P, _P, _I, _I, _I, _I, _I, _IP, _IP, _IP, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
     "ff3d_sp_down_sites_scratch_ints": (_I, [_I]),
-    "ff3d_sp_tap_keys": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P]),
+    "ff3d_sp_tap_keys": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P, _P]),
+    "ff3d_sp_nbr_permute": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ff3d_sort_workspace_bytes": (_SZ, [_I]),
     "ff3d_sort_pairs": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _SZ, _P]),
-    "ff3d_sp_level_permute": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "ff3d_sp_level_permute": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "ff3d_sp_nbr_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _IP, _IP, _IP, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ff3d_sp_gather_rows": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _P]),
     "ff3d_sp_bev_offsets": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),

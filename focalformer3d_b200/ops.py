@@ -681,35 +681,43 @@ class SparseLevel:
         _count(2)
 
     def _sorted_perm(self, out_coors, n_out, cap_out, k3, s3, p3):
-        """perm[j] = row (of out_coors) at sorted tile position j, ordered by the tap mask of the conv (k3, s3, p3)
-        whose INPUT level is self."""
+        """(perm, nbr_u): perm[j] = row (of out_coors) at sorted tile position j, ordered by the tap mask of the conv
+        (k3, s3, p3) whose INPUT level is self; nbr_u [kvol, cap_out] = the probed input rows in the CURRENT order."""
         D, H, W = self.shape
         dev = out_coors.device
+        kvol = k3[0] * k3[1] * k3[2]
         keys = torch.empty((cap_out,), dtype=torch.int32, device=dev)
+        nbr_u = torch.empty((kvol, cap_out), dtype=torch.int32, device=dev)
         check(lib.ff3d_sp_tap_keys(_ptr(out_coors), _ptr(n_out), cap_out, D, H, W, _ptr(self.hkeys), _ptr(self.hvals),
-                                   self.hsize, L.int_array(k3), L.int_array(s3), L.int_array(p3), _ptr(keys), _stream()),
-              "ff3d_sp_tap_keys")
+                                   self.hsize, L.int_array(k3), L.int_array(s3), L.int_array(p3), _ptr(keys), _ptr(nbr_u),
+                                   _stream()), "ff3d_sp_tap_keys")
         ws_bytes = lib.ff3d_sort_workspace_bytes(cap_out)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         skeys = torch.empty_like(keys)
         perm = torch.empty((cap_out,), dtype=torch.int32, device=dev)
-        kvol = k3[0] * k3[1] * k3[2]
         check(lib.ff3d_sort_pairs(_ptr(keys), None, _ptr(n_out), cap_out, kvol, _ptr(skeys), _ptr(perm), _ptr(ws), ws_bytes,
                                   _stream()), "ff3d_sort_pairs")
         _count(1 + 3 * ((kvol + 8) // 9))
-        return perm
+        return perm, nbr_u
 
-    def _rulebook(self, out_coors, perm, n_out, cap_out, k3, s3, p3, y_mode=0, ldy=0, bev=(0, 0, 0)):
+    def _rulebook(self, out_coors, perm, n_out, cap_out, k3, s3, p3, y_mode=0, ldy=0, bev=(0, 0, 0), nbr_u=None, inv=None):
+        """Rulebook in tile order.  With ``nbr_u`` (rows kept by the tap-key pass) the neighbour map is a re-ordering
+        (ff3d_sp_nbr_permute); without, the hash is probed (ff3d_sp_nbr_build: levels that were never sorted)."""
         D, H, W = self.shape
         dev = out_coors.device
         kvol = k3[0] * k3[1] * k3[2]
         nbr = torch.empty((kvol, cap_out), dtype=torch.int32, device=dev)
         tile_mask = torch.empty(((cap_out + 127) // 128,), dtype=torch.int32, device=dev)
         y_off = torch.empty((cap_out,), dtype=torch.int32, device=dev) if y_mode else None
-        check(lib.ff3d_sp_nbr_build(_ptr(out_coors), _ptr(perm), _ptr(n_out), cap_out, D, H, W, _ptr(self.hkeys),
-                                    _ptr(self.hvals), self.hsize, L.int_array(k3), L.int_array(s3), L.int_array(p3),
-                                    _ptr(nbr), _ptr(tile_mask), _ptr(y_off), y_mode, ldy, bev[0], bev[1], bev[2], _stream()),
-              "ff3d_sp_nbr_build")
+        if nbr_u is not None:
+            check(lib.ff3d_sp_nbr_permute(_ptr(nbr_u), _ptr(perm), _ptr(inv), _ptr(out_coors), _ptr(n_out), cap_out, kvol,
+                                          _ptr(nbr), _ptr(tile_mask), _ptr(y_off), y_mode, ldy, bev[0], bev[1], bev[2], _stream()),
+                  "ff3d_sp_nbr_permute")
+        else:
+            check(lib.ff3d_sp_nbr_build(_ptr(out_coors), _ptr(perm), _ptr(n_out), cap_out, D, H, W, _ptr(self.hkeys),
+                                        _ptr(self.hvals), self.hsize, L.int_array(k3), L.int_array(s3), L.int_array(p3),
+                                        _ptr(nbr), _ptr(tile_mask), _ptr(y_off), y_mode, ldy, bev[0], bev[1], bev[2], _stream()),
+                  "ff3d_sp_nbr_build")
         _count()
         return Rulebook(nbr, tile_mask, y_off if y_mode == 2 else None, y_off if y_mode == 1 else None)
 
@@ -717,19 +725,28 @@ class SparseLevel:
         """Re-store the level in SubM tap-mask order (all SubM convs of the level then run on homogeneous tiles).
         Returns perm (new row i <- old row perm[i]) so that the caller can move row data stored in the old order."""
         D, H, W = self.shape
-        perm = self._sorted_perm(self.coors, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
+        perm, nbr_u = self._sorted_perm(self.coors, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
         coors = torch.empty_like(self.coors)
+        inv = torch.empty((self.cap,), dtype=torch.int32, device=self.coors.device)
         check(lib.ff3d_sp_level_permute(_ptr(self.coors), _ptr(perm), _ptr(self.n_dev), self.cap, D, H, W, _ptr(coors),
-                                        _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _stream()), "ff3d_sp_level_permute")
+                                        _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _ptr(inv), _stream()),
+              "ff3d_sp_level_permute")
         _count()
         self.coors = coors
         self.subm = None
+        self._subm_src = (nbr_u, perm, inv)          # probed rows in the old order: subm_map() re-orders them
         return perm
 
     def subm_map(self):
         """SubM k=3 rulebook of the level (rows already in mask order: no row map)."""
         if self.subm is None:
-            self.subm = self._rulebook(self.coors, None, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
+            src = getattr(self, "_subm_src", None)
+            if src is not None:
+                nbr_u, perm, inv = src
+                self.subm = self._rulebook(self.coors, perm, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P, nbr_u=nbr_u, inv=inv)
+                self._subm_src = None
+            else:
+                self.subm = self._rulebook(self.coors, None, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
         return self.subm
 
     def downsample(self, k3, s3, p3, cap_out, overflow, ldy, sort_level=True, bev=None):
@@ -752,11 +769,11 @@ class SparseLevel:
         _count(5)
         if sort_level:
             lvl.sort_by_mask()
-        perm = self._sorted_perm(lvl.coors, n_o, cap_out, k3, s3, p3)
+        perm, nbr_u = self._sorted_perm(lvl.coors, n_o, cap_out, k3, s3, p3)
         if bev is not None:
-            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=2, ldy=ldy, bev=bev)
+            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=2, ldy=ldy, bev=bev, nbr_u=nbr_u)
         else:
-            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=1, ldy=ldy)
+            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=1, ldy=ldy, nbr_u=nbr_u)
         return lvl, rb
 
 

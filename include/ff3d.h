@@ -111,12 +111,19 @@ int ff3d_sp_down_sites(const int* coors_in, const int* n_in_dev, int cap_in, int
 int ff3d_sp_down_sites_scratch_ints(int hsize);
 int ff3d_sp_tap_keys(const int* coors_out, const int* n_out_dev, int cap_out, int D, int H, int W,
                      const uint32_t* hkeys_in, const int* hvals_in, int hsize_in, const int* k3, const int* s3,
-                     const int* p3, uint32_t* keys, ff3d_stream_t stream);
+                     const int* p3, uint32_t* keys, int* nbr_unsorted /* optional [kvol, cap_out]: the probed rows */,
+                     ff3d_stream_t stream);
 size_t ff3d_sort_workspace_bytes(int cap);
 int ff3d_sort_pairs(const uint32_t* keys_in, const int* vals_in, const int* n_dev, int cap, int key_bits,
                     uint32_t* keys_out, int* vals_out, void* workspace, size_t workspace_bytes, ff3d_stream_t stream);
 int ff3d_sp_level_permute(const int* coors_in, const int* perm, const int* n_dev, int cap, int D, int H, int W,
-                          int* coors_out, const uint32_t* hkeys, int* hvals, int hsize, ff3d_stream_t stream);
+                          int* coors_out, const uint32_t* hkeys, int* hvals, int hsize, int* inv /* optional: old row -> new */,
+                          ff3d_stream_t stream);
+/* ff3d_sp_nbr_build without a second round of hash probes: re-orders the rows ff3d_sp_tap_keys kept (nbr_unsorted) into
+ * tile order, remapping them through inv when the probed level itself was re-ordered (SubM) */
+int ff3d_sp_nbr_permute(const int* nbr_unsorted, const int* perm, const int* inv, const int* coors_out, const int* n_out_dev,
+                        int cap_out, int kvol, int* nbr, uint32_t* tile_mask, int* y_off, int y_mode, int ldy, int bev_h,
+                        int bev_w, int bev_c, ff3d_stream_t stream);
 int ff3d_sp_nbr_build(const int* coors_out, const int* perm, const int* n_out_dev, int cap_out, int D, int H, int W,
                       const uint32_t* hkeys_in, const int* hvals_in, int hsize_in, const int* k3, const int* s3,
                       const int* p3, int* nbr, uint32_t* tile_mask, int* y_off, int y_mode, int ldy, int bev_h, int bev_w,
