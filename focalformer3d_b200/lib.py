@@ -38,6 +38,28 @@ class GemmDesc(C.Structure):
     ]
 
 
+class DecoderLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "w_oa", "b_oa", "w_op", "b_op", "w_f1", "b_f1",
+                                          "w_f2", "b_f2")] + [("ln_gamma", C.c_void_p * 3), ("ln_beta", C.c_void_p * 3)]
+
+
+class DecoderStageDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("nq", C.c_int), ("n_layers", C.c_int), ("hidden", C.c_int), ("heads", C.c_int),
+        ("n_levels", C.c_int), ("n_points", C.c_int), ("ffn", C.c_int),
+        ("lvl_h", C.c_int * 4), ("lvl_w", C.c_int * 4), ("lvl_start", C.c_int * 4),
+        ("x_in", C.c_void_p), ("qpe", C.c_void_p), ("q_pos", C.c_void_p),
+        ("ref_w", C.c_float), ("ref_h", C.c_float),
+        ("value", C.c_void_p), ("ldv", C.c_int), ("v_bstride", C.c_longlong),
+        ("layers", DecoderLayerWeights * 4),
+        ("w_h1", C.c_void_p), ("b_h1", C.c_void_p), ("n_h1", C.c_int),
+        ("w_h2", C.c_void_p), ("b_h2", C.c_void_p), ("n_pred", C.c_int),
+        ("x_out", C.c_void_p), ("pred", C.c_void_p), ("ld_pred", C.c_int), ("pred_cols", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("overflow_dev", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/ff3d.h one to one
 _P, _I, _F, _LL, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 _IP = C.POINTER(C.c_int)
@@ -86,6 +108,8 @@ SIGNATURES = {
     "ff3d_msda": (_I, [_P, _I, _I, _LL, _IP, _IP, _IP, _I, _I, _P, _F, _F, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "ff3d_roi_sample": (_I, [_P, _I, _P, _I, _LL, _IP, _IP, _IP, _I, _I, _I, _F, _F, _F, _F, _F, _FP, _P, _I, _I, _P]),
     "ff3d_roi_sample_split": (_I, [_P, _I, _P, _I, _LL, _IP, _IP, _IP, _I, _I, _I, _F, _F, _F, _F, _F, _FP, _P, _I, _I, _P, _P]),
+    "ff3d_decoder_stage_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ff3d_decoder_stage": (_I, [C.POINTER(DecoderStageDesc), _P]),
     "ff3d_head_update": (_I, [_P, _I, _P, _P, _I, _I, _P]),
     "ff3d_box_decode": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _F, _F, _F, _F, _FP, _P, _P, _P, _P, _P]),
     "ff3d_assemble_sweeps": (_I, [_P, _I, _IP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _FP, C.POINTER(C.c_ubyte),

@@ -903,6 +903,32 @@ class FocalDecoder(ParamTree):
             st["head1"] = (pack_linear(torch.cat(w1), None, dev), vec(torch.cat(b1), dev))
             st["head2"] = (pack_linear(w2, None, dev), vec(torch.cat(b2), dev, _pad4(sum(ks))))
             st["pred_dim"] = sum(ks)
+            # the whole stage as one launch (csrc/decstage.cu): weights in MMA fragment order
+            n_oa = (self.num_heads * self.n_levels * self.n_points * 3 + 15) // 16 * 16
+            n_h1 = (64 * len(names) + 127) // 128 * 128
+            n_pred = (sum(ks) + 15) // 16 * 16
+            if (ops.FUSED_DECODER and hc == 128 and self.num_heads == 8 and 1 <= self.n_layers <= 4 and self.ffn_ch % 256 == 0
+                    and self.n_levels <= 4 and 32 * (n_oa + 4) * 4 <= 51200 and n_h1 <= 384):
+                fl = []
+                for j in range(self.n_layers):
+                    q = f"decoder.{i}.layers.{j}"
+                    woa = torch.cat([sd[f"{q}.attentions.1.sampling_offsets.weight"], sd[f"{q}.attentions.1.attention_weights.weight"]])
+                    boa = torch.cat([sd[f"{q}.attentions.1.sampling_offsets.bias"], sd[f"{q}.attentions.1.attention_weights.bias"]])
+                    fl.append(dict(
+                        w_qkv=ops.pack_frag(sd[f"{q}.attentions.0.attn.in_proj_weight"]).to(dev),
+                        b_qkv=vec(sd[f"{q}.attentions.0.attn.in_proj_bias"], dev),
+                        w_o=ops.pack_frag(sd[f"{q}.attentions.0.attn.out_proj.weight"]).to(dev),
+                        b_o=vec(sd[f"{q}.attentions.0.attn.out_proj.bias"], dev),
+                        w_oa=ops.pack_frag(woa, n_pad=n_oa).to(dev), b_oa=vec(boa, dev, n_oa),
+                        w_op=ops.pack_frag(sd[f"{q}.attentions.1.output_proj.weight"]).to(dev),
+                        b_op=vec(sd[f"{q}.attentions.1.output_proj.bias"], dev),
+                        w_f1=ops.pack_frag(sd[f"{q}.ffns.0.layers.0.0.weight"]).to(dev), b_f1=vec(sd[f"{q}.ffns.0.layers.0.0.bias"], dev),
+                        w_f2=ops.pack_frag(sd[f"{q}.ffns.0.layers.1.weight"]).to(dev), b_f2=vec(sd[f"{q}.ffns.0.layers.1.bias"], dev),
+                        ln=layers[j]["ln"]))
+                st["fused"] = dict(layers=fl, heads=self.num_heads, ffn=self.ffn_ch, n_oa=n_oa,
+                                   w_h1=ops.pack_frag(torch.cat(w1), n_pad=n_h1).to(dev), b_h1=vec(torch.cat(b1), dev, n_h1), n_h1=n_h1,
+                                   w_h2=ops.pack_frag(w2, n_pad=n_pred, k_pad=n_h1).to(dev), b_h2=vec(torch.cat(b2), dev, n_pred),
+                                   n_pred=n_pred)
             pk["stage"].append(st)
         self.pk = pk
         self._bev_pos_cache = {}
@@ -1022,7 +1048,11 @@ class FocalDecoder(ParamTree):
                 h2 = ops.linear(h1, pk["roi"][1][0], pk["roi"][1][1], act=ACT_RELU)
                 x = ops.linear(h2, pk["roi"][2][0], pk["roi"][2][1], act=ACT_RELU, res=x, res_after_act=True)
                 ops.mark(f"roi{i}")
-            for j in range(self.n_layers):                                                 # [upstream] decoder layer
+            fused = st.get("fused") if ops.FUSED_DECODER else None
+            if fused is not None:
+                # the stage's layers and prediction heads in one launch: query block resident in shared memory
+                x, pred = ops.decoder_stage(x, qpe, q_pos, W, H, vproj, geom, self.n_points, fused, B, nq, st["pred_dim"])
+            for j in range(self.n_layers if fused is None else 0):                         # [upstream] decoder layer
                 lay = st["layers"][j]
                 qk = ops.linear(x, lay["qk"][0], lay["qk"][1], x2=qpe)
                 v = ops.linear(x, lay["v"][0], lay["v"][1])
@@ -1038,8 +1068,9 @@ class FocalDecoder(ParamTree):
                 f = ops.linear(x2_, lay["f1"][0], lay["f1"][1], act=ACT_RELU)
                 y = ops.linear(f, lay["f2"][0], lay["f2"][1], res=x2_)
                 x = ops.layernorm(y, *lay["ln"][2])
-            hh = ops.linear(x, st["head1"][0], st["head1"][1], act=ACT_RELU)               # :939
-            pred = ops.linear(hh, st["head2"][0], st["head2"][1], cout=st["pred_dim"])
+            if fused is None:
+                hh = ops.linear(x, st["head1"][0], st["head1"][1], act=ACT_RELU)           # :939
+                pred = ops.linear(hh, st["head2"][0], st["head2"][1], cout=st["pred_dim"])
             if self.classaware_reg:                                                        # :940-943
                 gk = [self.common_heads[n][0] for n in self.common_heads]
                 pred = ops.class_select(pred, q_label, gk, nc, nc, _pad4(sum(gk) + nc))

@@ -880,6 +880,82 @@ def add_bcast_rows_split(a, p):
     return out
 
 
+def pack_frag(w, n_pad=None, k_pad=None):
+    """nn.Linear-style weight [N, K] (y = x @ w.T) -> int32 [N/8, K/16, 32, 4]: the B operand of mma.sync m16n8k16 in
+    FRAGMENT order with fp16 hi / lo parts (csrc/decstage.cu).  Lane (g, t) of n-tile j, k-step s holds
+    b0 = w[8j + g, 16s + 2t : +2], b1 = w[8j + g, 16s + 8 + 2t : +2]; the four words are (hi b0, hi b1, lo b0, lo b1)."""
+    w = w.detach().double().cpu()
+    N, K = w.shape
+    n_pad = n_pad or (N + 15) // 16 * 16
+    k_pad = k_pad or (K + 15) // 16 * 16
+    wp = torch.zeros((n_pad, k_pad), dtype=torch.float64)
+    wp[:N, :K] = w
+    hi, lo = split_f16(wp.float())
+    parts = []
+    for src in (hi, lo):
+        v = src.view(n_pad // 8, 8, k_pad // 16, 2, 4, 2)               # [j, g, s, b, t, pair]
+        parts.append(v.permute(0, 2, 1, 4, 3, 5))                       # [j, s, g, t, b, pair]
+    out = torch.stack(parts, dim=4).contiguous()                        # [j, s, g, t, (hi, lo), b, pair]
+    return out.view(n_pad // 8, k_pad // 16, 32, 4, 2).view(torch.int32).reshape(n_pad // 8, k_pad // 16, 32, 4)
+
+
+def unpack_frag(frag, N, K):
+    """Inverse of pack_frag (test helper): -> (hi, lo) fp32 [N, K]."""
+    nj, ns = frag.shape[0], frag.shape[1]
+    v = frag.contiguous().view(torch.float16).view(nj, ns, 8, 4, 2, 2, 2)      # [j, s, g, t, (hi, lo), b, pair]
+    out = []
+    for part in range(2):
+        x = v[:, :, :, :, part].permute(0, 2, 1, 4, 3, 5).reshape(nj * 8, ns * 16)   # [j, g, s, b, t, pair]
+        out.append(x.float()[:N, :K])
+    return out[0], out[1]
+
+
+FUSED_DECODER = _os.environ.get("FF3D_FUSED_DECODER", "1") != "0"
+
+
+def decoder_stage(x, qpe, q_pos, ref_w, ref_h, value, geom, n_points, stage_w, B, nq, pred_cols):
+    """One decoder stage (all its layers + prediction heads) in one launch (csrc/decstage.cu).  ``stage_w`` = dict from
+    model.FocalDecoder.prepare: layers = [dict(w_qkv, b_qkv, ...)], w_h1, b_h1, n_h1, w_h2, b_h2, n_pred, ffn.
+    Returns (x_out [B*nq, 128], pred [B*nq, pred_cols])."""
+    _chk_f32(x, "decoder_stage.x"); _chk_f32(qpe, "decoder_stage.qpe"); _chk_f32(q_pos, "decoder_stage.q_pos")
+    assert x.is_contiguous() and qpe.is_contiguous() and q_pos.is_contiguous() and value.is_contiguous()
+    dev = x.device
+    layers = stage_w["layers"]
+    d = L.DecoderStageDesc()
+    d.B, d.nq, d.n_layers, d.hidden, d.heads = B, nq, len(layers), x.shape[1], stage_w["heads"]
+    d.n_levels, d.n_points, d.ffn = geom.L, n_points, stage_w["ffn"]
+    for i, (h, w) in enumerate(geom.shapes):
+        d.lvl_h[i], d.lvl_w[i], d.lvl_start[i] = h, w, geom.starts[i]
+    d.x_in, d.qpe, d.q_pos = x.data_ptr(), qpe.data_ptr(), q_pos.data_ptr()
+    d.ref_w, d.ref_h = float(ref_w), float(ref_h)
+    ldv = value.stride(1)
+    d.value, d.ldv, d.v_bstride = value.data_ptr(), ldv, value.stride(0) // ldv
+    for i, lay in enumerate(layers):
+        lw = d.layers[i]
+        for k in ("w_qkv", "b_qkv", "w_o", "b_o", "w_oa", "b_oa", "w_op", "b_op", "w_f1", "b_f1", "w_f2", "b_f2"):
+            setattr(lw, k, lay[k].data_ptr())
+        for n in range(3):
+            lw.ln_gamma[n], lw.ln_beta[n] = lay["ln"][n][0].data_ptr(), lay["ln"][n][1].data_ptr()
+    d.w_h1, d.b_h1, d.n_h1 = stage_w["w_h1"].data_ptr(), stage_w["b_h1"].data_ptr(), stage_w["n_h1"]
+    d.w_h2, d.b_h2, d.n_pred = stage_w["w_h2"].data_ptr(), stage_w["b_h2"].data_ptr(), stage_w["n_pred"]
+    x_out = torch.empty_like(x)
+    pred = torch.empty((B * nq, pred_cols), dtype=torch.float32, device=dev)
+    d.x_out, d.pred, d.ld_pred, d.pred_cols = x_out.data_ptr(), pred.data_ptr(), pred.stride(0), pred_cols
+    ws_bytes = lib.ff3d_decoder_stage_workspace_bytes(B, nq, len(layers))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws_bytes
+    d.overflow_dev = gemm_flag(dev).data_ptr()
+    t0 = prof.begin()
+    check(lib.ff3d_decoder_stage(C.byref(d), _stream()), "ff3d_decoder_stage")
+    M = B * nq
+    ffn = stage_w["ffn"]
+    flops = len(layers) * (2.0 * M * 128 * (384 + 128 + stage_w["n_oa"] + 128 + 2 * ffn) + 4.0 * B * nq * nq * 128) \
+        + 2.0 * M * (128 * stage_w["n_h1"] + stage_w["n_h1"] * stage_w["n_pred"])
+    prof.end(t0, f"decoder_stage[{len(layers)}L x {M}]", flops, 4.0 * M * 128 * 4)
+    _count(2)
+    return x_out, pred
+
+
 def head_update(pred, query_pos, prev):
     check(lib.ff3d_head_update(_ptr(pred), pred.stride(0), _ptr(query_pos), _ptr(prev),
                                prev.stride(0) if prev is not None else 0, pred.shape[0], _stream()), "ff3d_head_update")

@@ -305,6 +305,42 @@ int ff3d_head_update(float* pred, int ldp, float* query_pos, const float* prev, 
 int ff3d_class_select(const float* full, int ld_full, const int* label, const int* group_k, int n_groups, int tail,
                       int num_classes, float* out, int ld_out, int rows, ff3d_stream_t stream);
 
+/* One decoder stage in ONE launch: the stage's `n_layers` DeformableTransformer decoder layers and its prediction heads.
+ * Replaces: focal_decoder.py:927-939 -- self.decoder[i](query_feat, ..., query_pos, value, reference_points) ([upstream]
+ *   mmcv BaseTransformerLayer, operation_order (self_attn, norm, cross_attn, norm, ffn, norm): nn.MultiheadAttention over the
+ *   scene's queries, MultiScaleDeformableAttention over the BEV pyramid, FFN 128 -> ffn -> 128, three LayerNorms) followed by
+ *   self.prediction_heads[i] (Conv1d 128->64 + BN + ReLU, Conv1d 64->k per head, here one GEMM + one block-diagonal GEMM).
+ * All weight matrices are nn.Linear-style [N, K] matrices packed in MMA B-fragment order with fp16 hi / lo parts
+ * (focalformer3d_b200/model.py pack_frag): int32 [N/8][K/16][32 lanes][4] = {hi b0, hi b1, lo b0, lo b1}, N zero-padded to a
+ * multiple of 16; biases fp32, zero-padded alike.  value = the batched value projection [B, n_tokens, ldv], layer j reading
+ * columns [128 j, 128 j + 128); q_pos [B*nq, 2] in cells, divided by (ref_w, ref_h) inside (focal_decoder.py:869).
+ * Outputs: x_out [B*nq, 128] (the stage's query features, may be NULL) and pred [B*nq, ld_pred] (first pred_cols columns).
+ * Built for hidden = 128, heads = 8; workspace from ff3d_decoder_stage_workspace_bytes (K / V exchange + counters). */
+typedef struct ff3d_decoder_layer_weights {
+  const void* w_qkv; const float* b_qkv;        /* in_proj [384, 128]: rows (q | k | v)                                  */
+  const void* w_o;   const float* b_o;          /* attention out_proj [128, 128]                                         */
+  const void* w_oa;  const float* b_oa;         /* sampling_offsets (heads*L*P*2) | attention_weights (heads*L*P) rows   */
+  const void* w_op;  const float* b_op;         /* MSDA output_proj [128, 128]                                           */
+  const void* w_f1;  const float* b_f1;         /* FFN [ffn, 128]                                                        */
+  const void* w_f2;  const float* b_f2;         /* FFN [128, ffn]                                                        */
+  const float* ln_gamma[3]; const float* ln_beta[3];
+} ff3d_decoder_layer_weights;
+typedef struct ff3d_decoder_stage_desc {
+  int B, nq, n_layers, hidden, heads, n_levels, n_points, ffn;
+  int lvl_h[4], lvl_w[4], lvl_start[4];
+  const float* x_in; const float* qpe; const float* q_pos;
+  float ref_w, ref_h;
+  const float* value; int ldv; long long v_bstride;
+  ff3d_decoder_layer_weights layers[4];
+  const void* w_h1; const float* b_h1; int n_h1;      /* heads, first layer: [n_h1, 128], ReLU                               */
+  const void* w_h2; const float* b_h2; int n_pred;    /* heads, second layer: [n_pred, n_h1] (n_pred padded to 16)           */
+  float* x_out; float* pred; int ld_pred, pred_cols;
+  void* workspace; size_t workspace_bytes;
+  int* overflow_dev;                                  /* raised when an activation leaves the fp16 range (like ff3d_tmagemm) */
+} ff3d_decoder_stage_desc;
+size_t ff3d_decoder_stage_workspace_bytes(int B, int nq, int n_layers);
+int ff3d_decoder_stage(const ff3d_decoder_stage_desc* desc, ff3d_stream_t stream);
+
 /* Final scoring + box decode (focal_decoder.py:1313-1321 + transfusion_bbox_coder.py:71-158, nms_type=None):
  * pred as above (class logits at column cls_col); boxes [rows, 9|7] = (x,y,z_bottom,w,l,h,yaw[,vx,vy]),
  * scores [rows], labels [rows] int32, keep [rows] uint8 (post_center_range test). */
