@@ -28,6 +28,8 @@
 namespace ff3d {
 
 constexpr int DS_R = 32;            // queries per CTA
+constexpr int DS_NW = 16;           // warps per CTA: (head, 16-row tile) units in the attention, one n-tile each in the projections
+constexpr int DS_NT = DS_NW * 32;
 constexpr int DS_C = 128;           // hidden channels
 constexpr int DS_HEADS = 8;
 constexpr int DS_D = 16;
@@ -161,15 +163,15 @@ __device__ __forceinline__ void for_acc(const float (&acc)[2][NT][4], const floa
       }
 }
 
-// LayerNorm over the 128 columns of the 32 rows of ys (warp w: rows 4w..4w+3, lane: 4 columns) -> xs (fp32) and, split,
+// LayerNorm over the 128 columns of the 32 rows of ys (warp w: rows 2w, 2w+1; lane: 4 columns) -> xs (fp32) and, split,
 // A (optionally + add[row][col], the positional embedding)
 __device__ __forceinline__ void layer_norm_rows(const float* ys, float* xs, const float* __restrict__ gamma,
                                                 const float* __restrict__ beta, __half* Ah, __half* Al, const float* add,
                                                 int warp, int lane, bool& ovf) {
   const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane), bt = __ldg(reinterpret_cast<const float4*>(beta) + lane);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = warp * 4 + i;
+  for (int i = 0; i < DS_R / DS_NW; ++i) {
+    const int row = warp * (DS_R / DS_NW) + i;
     const float4 v = *reinterpret_cast<const float4*>(ys + row * DS_LDY + lane * 4);
     float s = (v.x + v.y) + (v.z + v.w);
 #pragma unroll
@@ -193,7 +195,81 @@ __device__ __forceinline__ void layer_norm_rows(const float* ys, float* xs, cons
   }
 }
 
-__global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
+// MSDA: in-place pass over the offsets | weights block of one (query, head): offsets -> pixel coordinates of every
+// (level, point) sample, logits -> soft-max weights.  One thread per (query, head).
+__device__ __forceinline__ void msda_prepare(float* oas, int ldoa, const float* refs, const DsP& p, int tid) {
+  if (tid >= DS_R * DS_HEADS) return;
+  const int row = tid >> 3, h = tid & 7;
+  const int LP = p.L * p.P, n_off = DS_HEADS * LP * 2;
+  float* aw = oas + row * ldoa + n_off + h * LP;
+  float* of = oas + row * ldoa + h * LP * 2;
+  const float rx = refs[row * 2], ry = refs[row * 2 + 1];
+  float mxw = -INFINITY;
+  for (int i = 0; i < LP; ++i) mxw = fmaxf(mxw, aw[i]);
+  float den = 0.f;
+  for (int i = 0; i < LP; ++i) { const float e = expf(aw[i] - mxw); aw[i] = e; den += e; }
+  const float inv = 1.f / den;
+  for (int i = 0; i < LP; ++i) aw[i] *= inv;
+  for (int lv = 0; lv < p.L; ++lv) {
+    const float Hf = (float)p.lvl_h[lv], Wf = (float)p.lvl_w[lv];
+    for (int pt = 0; pt < p.P; ++pt) {
+      const int i = lv * p.P + pt;
+      const float lx = rx + of[i * 2] / Wf, ly = ry + of[i * 2 + 1] / Hf;      // mmcv: reference + offset / (W, H)
+      of[i * 2] = lx * Wf - 0.5f;                                              // grid_sample, align_corners = False
+      of[i * 2 + 1] = ly * Hf - 0.5f;
+    }
+  }
+}
+
+// MSDA sampling of one (query, head) by 16 lanes = 4 bilinear corners x 4 channel quads: all LP loads of the lane's corner
+// are issued before the first use (clamped address, zero weight outside the map).  LPC = compile-time L * P (0: generic).
+template <int LPC>
+__device__ __forceinline__ float4 msda_sample(const float* of, const float* aw, const float* __restrict__ vbase, const DsP& p,
+                                              int dx, int dy) {
+  float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (LPC > 0) {
+    float4 v[LPC];
+    float wg[LPC];
+#pragma unroll
+    for (int i = 0; i < LPC; ++i) {
+      const int lv = i / (LPC / 3);                                           // LPC = 3 levels x P points
+      const int H = p.lvl_h[lv], Wd = p.lvl_w[lv];
+      const float2 pxy = *reinterpret_cast<const float2*>(of + i * 2);
+      const float x0f = floorf(pxy.x), y0f = floorf(pxy.y);
+      const int xi = (int)x0f + dx, yi = (int)y0f + dy;
+      const float fx = pxy.x - x0f, fy = pxy.y - y0f;
+      const bool inb = xi >= 0 && xi < Wd && yi >= 0 && yi < H;
+      wg[i] = inb ? (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * aw[i] : 0.f;
+      const int xc = min(max(xi, 0), Wd - 1), yc = min(max(yi, 0), H - 1);
+      v[i] = __ldg(reinterpret_cast<const float4*>(vbase + ((size_t)p.lvl_start[lv] + (size_t)yc * Wd + xc) * p.ldv));
+    }
+#pragma unroll
+    for (int i = 0; i < LPC; ++i) {
+      acc4.x = fmaf(wg[i], v[i].x, acc4.x); acc4.y = fmaf(wg[i], v[i].y, acc4.y);
+      acc4.z = fmaf(wg[i], v[i].z, acc4.z); acc4.w = fmaf(wg[i], v[i].w, acc4.w);
+    }
+  } else {
+    for (int lv = 0; lv < p.L; ++lv) {
+      const int H = p.lvl_h[lv], Wd = p.lvl_w[lv];
+      for (int pt = 0; pt < p.P; ++pt) {
+        const int i = lv * p.P + pt;
+        const float px = of[i * 2], py = of[i * 2 + 1];
+        const float x0f = floorf(px), y0f = floorf(py);
+        const int xi = (int)x0f + dx, yi = (int)y0f + dy;
+        const float fx = px - x0f, fy = py - y0f;
+        if (xi >= 0 && xi < Wd && yi >= 0 && yi < H) {
+          const float wgt = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * aw[i];
+          const float4 v = __ldg(reinterpret_cast<const float4*>(vbase + ((size_t)p.lvl_start[lv] + (size_t)yi * Wd + xi) * p.ldv));
+          acc4.x = fmaf(wgt, v.x, acc4.x); acc4.y = fmaf(wgt, v.y, acc4.y);
+          acc4.z = fmaf(wgt, v.z, acc4.z); acc4.w = fmaf(wgt, v.w, acc4.w);
+        }
+      }
+    }
+  }
+  return acc4;
+}
+
+__global__ void __launch_bounds__(DS_NT, 1) decoder_stage_kernel(const DsP p) {
   extern __shared__ __align__(16) uint8_t ds_smem[];
   float* xs = reinterpret_cast<float*>(ds_smem);                         // [32][128]   layer input / residual
   float* qpes = xs + DS_R * DS_C;                                        // [32][128]
@@ -216,7 +292,7 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
   bool ovf = false;
 
   // ---- load the query block
-  for (int e = tid; e < DS_R * (DS_C / 4); e += 256) {
+  for (int e = tid; e < DS_R * (DS_C / 4); e += DS_NT) {
     const int row = e >> 5, c4 = e & 31;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (row < n_valid) {
@@ -240,7 +316,7 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
   for (int l = 0; l < p.n_layers; ++l) {
     const DsLayer& W = p.lay[l];
     // ---- A1 = split(x + qpe), A2 = split(x)
-    for (int e = tid; e < DS_R * (DS_C / 4); e += 256) {
+    for (int e = tid; e < DS_R * (DS_C / 4); e += DS_NT) {
       const int row = e >> 5, c = (e & 31) * 4;
       const float4 a = reinterpret_cast<const float4*>(xs)[e], b = reinterpret_cast<const float4*>(qpes)[e];
       uint32_t h01, h23, l01, l23;
@@ -252,19 +328,19 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
       *reinterpret_cast<uint2*>(A1l + row * DS_LDA + c) = make_uint2(l01, l23);
     }
     __syncthreads();
-    // ---- q | k | v projection: 24 pairs of n-tiles, three per warp; q,k read x + qpe, v reads x
+    // ---- q | k | v projection: 48 n-tiles, warp w owns q tile w, k tile w, v tile w; q,k read x + qpe, v reads x
     {
       float* kvst = reinterpret_cast<float*>(big);                       // [32][260]: k | v
+#pragma unroll 1
       for (int i = 0; i < 3; ++i) {
-        const int pair = warp * 3 + i, n0 = pair * 16;
-        float acc[2][2][4], accx[2][2][4];
-        zero_acc<2>(acc, accx);
-        const bool qk = n0 < 2 * DS_C;
-        gemm8<2>(qk ? A1h : A2h, qk ? A1l : A2l, DS_LDA, 0, W.w_qkv, 8, pair * 2, 0, lane, acc, accx);
-        for_acc<2>(acc, accx, n0, lane, [&](int row, int col, float v0, float v1) {
+        const int nt = i * DS_NW + warp, n0 = nt * 8;
+        float acc[2][1][4], accx[2][1][4];
+        zero_acc<1>(acc, accx);
+        gemm8<1>(i < 2 ? A1h : A2h, i < 2 ? A1l : A2l, DS_LDA, 0, W.w_qkv, 8, nt, 0, lane, acc, accx);
+        for_acc<1>(acc, accx, n0, lane, [&](int row, int col, float v0, float v1) {
           v0 += __ldg(W.b_qkv + col);
           v1 += __ldg(W.b_qkv + col + 1);
-          if (col < DS_C) {                                              // q, scaled by 1 / sqrt(d) = 1/4 (exact)
+          if (i == 0) {                                                  // q, scaled by 1 / sqrt(d) = 1/4 (exact)
             uint32_t h, lo;
             split2(v0 * 0.25f, v1 * 0.25f, h, lo, ovf);
             *reinterpret_cast<uint32_t*>(Qh + row * DS_LDA + col) = h;
@@ -278,7 +354,7 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
       // ---- this block's keys / values -> global, in fragment order (rows past nq are zero)
       uint4* kf = p.kf + (size_t)(l * n_scenes + scene) * DS_HEADS * nkb8 * 32;
       uint4* vf = p.vf + (size_t)(l * n_scenes + scene) * DS_HEADS * p.nkb16 * 64;
-      for (int item = tid; item < 1024; item += 256) {
+      for (int item = tid; item < 1024; item += DS_NT) {
         // K: item = (head, 8-key block kb of the 4 in this block, lane' = (g', t'))
         const int h = item >> 7, kb = (item >> 5) & 3, ln = item & 31, gg = ln >> 2, tt = ln & 3;
         const int rl = kb * 8 + gg;
@@ -290,7 +366,7 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
         }
         kf[((size_t)h * nkb8 + blk * 4 + kb) * 32 + ln] = o;
       }
-      for (int item = tid; item < 1024; item += 256) {
+      for (int item = tid; item < 1024; item += DS_NT) {
         // V: item = (head, 16-key block kb of the 2 in this block, d n-tile, lane' = (g', t')): b0 = keys 2t', 2t'+1 ; b1 = +8
         const int h = item >> 7, kb = (item >> 6) & 1, nt = (item >> 5) & 1, ln = item & 31, gg = ln >> 2, tt = ln & 3;
         const int k0 = kb * 16 + 2 * tt;
@@ -306,125 +382,117 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
       if (tid == 0) {
         atomicAdd(p.counters + scene, 1);
         const int target = p.nblk * (l + 1);
-        while (ld_acquire(p.counters + scene) < target) __nanosleep(64);
+        while (ld_acquire(p.counters + scene) < target) __nanosleep(32);
       }
       __syncthreads();
-      // ---- self-attention: warp = head, both 16-row tiles together
+      // ---- self-attention: warp = (head, 16-row tile)
       {
-        const int h = warp;
+        const int h = warp & 7, m = warp >> 3;
         const uint4* kfh = kf + (size_t)h * nkb8 * 32 + lane;
         const uint4* vfh = vf + (size_t)h * p.nkb16 * 64 + lane;
-        uint32_t qh[2][4], ql[2][4];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
+        uint32_t qh[4], ql[4];
+        {
           const __half* ph = Qh + (m * 16 + g) * DS_LDA + h * DS_D + 2 * t;
           const __half* pl = Ql + (m * 16 + g) * DS_LDA + h * DS_D + 2 * t;
-          qh[m][0] = *reinterpret_cast<const uint32_t*>(ph);
-          qh[m][1] = *reinterpret_cast<const uint32_t*>(ph + 8 * DS_LDA);
-          qh[m][2] = *reinterpret_cast<const uint32_t*>(ph + 8);
-          qh[m][3] = *reinterpret_cast<const uint32_t*>(ph + 8 * DS_LDA + 8);
-          ql[m][0] = *reinterpret_cast<const uint32_t*>(pl);
-          ql[m][1] = *reinterpret_cast<const uint32_t*>(pl + 8 * DS_LDA);
-          ql[m][2] = *reinterpret_cast<const uint32_t*>(pl + 8);
-          ql[m][3] = *reinterpret_cast<const uint32_t*>(pl + 8 * DS_LDA + 8);
+          qh[0] = *reinterpret_cast<const uint32_t*>(ph);
+          qh[1] = *reinterpret_cast<const uint32_t*>(ph + 8 * DS_LDA);
+          qh[2] = *reinterpret_cast<const uint32_t*>(ph + 8);
+          qh[3] = *reinterpret_cast<const uint32_t*>(ph + 8 * DS_LDA + 8);
+          ql[0] = *reinterpret_cast<const uint32_t*>(pl);
+          ql[1] = *reinterpret_cast<const uint32_t*>(pl + 8 * DS_LDA);
+          ql[2] = *reinterpret_cast<const uint32_t*>(pl + 8);
+          ql[3] = *reinterpret_cast<const uint32_t*>(pl + 8 * DS_LDA + 8);
         }
-        // scores of one 8-key tile for 16-row tile m: s[0..1] = row g, keys 2t, 2t+1 ; s[2..3] = row g+8
-        auto scores = [&](int m, const uint4& kq, float (&s)[4]) {
+        // scores of one 8-key tile: s[0..1] = row g, keys 2t, 2t+1 ; s[2..3] = row g+8
+        auto scores = [&](const uint4& kq, float (&s)[4]) {
           float c[4] = {0.f, 0.f, 0.f, 0.f}, cx[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c, qh[m], kq.x, kq.y);
-          mma16816(cx, qh[m], kq.z, kq.w);
-          mma16816(cx, ql[m], kq.x, kq.y);
+          mma16816(c, qh, kq.x, kq.y);
+          mma16816(cx, qh, kq.z, kq.w);
+          mma16816(cx, ql, kq.x, kq.y);
 #pragma unroll
           for (int i = 0; i < 4; ++i) s[i] = fmaf(cx[i], 1.f / 2048.f, c[i]);
         };
-        float mx[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
-#pragma unroll 4
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll 8
         for (int kb = 0; kb < nkb8; ++kb) {
           const uint4 kq = __ldcg(kfh + (size_t)kb * 32);
           const int key = kb * 8 + 2 * t;
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            float s[4];
-            scores(m, kq, s);
-            if (key < p.nq) { mx[m][0] = fmaxf(mx[m][0], s[0]); mx[m][1] = fmaxf(mx[m][1], s[2]); }
-            if (key + 1 < p.nq) { mx[m][0] = fmaxf(mx[m][0], s[1]); mx[m][1] = fmaxf(mx[m][1], s[3]); }
-          }
+          float s[4];
+          scores(kq, s);
+          if (key < p.nq) { mx[0] = fmaxf(mx[0], s[0]); mx[1] = fmaxf(mx[1], s[2]); }
+          if (key + 1 < p.nq) { mx[0] = fmaxf(mx[0], s[1]); mx[1] = fmaxf(mx[1], s[3]); }
         }
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int i = 0; i < 2; ++i) {
+          mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+          mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+        }
+        // exp(s - max) = 2^((s - max) * log2 e): one FFMA + MUFU.EX2 per score
+        const float L2E = 1.4426950408889634f;
+        const float mb[2] = {mx[0] * L2E, mx[1] * L2E};
+        float sum[2] = {0.f, 0.f};
+        float o[2][4], ox[2][4];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            mx[m][i] = fmaxf(mx[m][i], __shfl_xor_sync(0xffffffffu, mx[m][i], 1));
-            mx[m][i] = fmaxf(mx[m][i], __shfl_xor_sync(0xffffffffu, mx[m][i], 2));
-          }
-        float sum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-        float o[2][2][4], ox[2][2][4];
-        zero_acc<2>(o, ox);
-#pragma unroll 2
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { o[nt][i] = 0.f; ox[nt][i] = 0.f; }
+#pragma unroll 4
         for (int kb = 0; kb < p.nkb16; ++kb) {
           const uint4 ka = __ldcg(kfh + (size_t)(2 * kb) * 32), kbq = __ldcg(kfh + (size_t)(2 * kb + 1) * 32);
           const uint4 v0 = __ldcg(vfh + (size_t)kb * 64), v1 = __ldcg(vfh + (size_t)kb * 64 + 32);
           const int key = kb * 16 + 2 * t;
+          float sa[4], sb[4];
+          scores(ka, sa);
+          scores(kbq, sb);
+          float pa[4], pb[4];
 #pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            float sa[4], sb[4];
-            scores(m, ka, sa);
-            scores(m, kbq, sb);
-            float pa[4], pb[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float mrow = mx[m][i >> 1];
-              pa[i] = (key + (i & 1) < p.nq) ? expf(sa[i] - mrow) : 0.f;
-              pb[i] = (key + 8 + (i & 1) < p.nq) ? expf(sb[i] - mrow) : 0.f;
-            }
-            sum[m][0] += (pa[0] + pa[1]) + (pb[0] + pb[1]);
-            sum[m][1] += (pa[2] + pa[3]) + (pb[2] + pb[3]);
-            uint32_t ah[4], al[4];
-            bool dummy = false;                                          // probabilities are in [0, 1]
-            split2(pa[0], pa[1], ah[0], al[0], dummy);
-            split2(pa[2], pa[3], ah[1], al[1], dummy);
-            split2(pb[0], pb[1], ah[2], al[2], dummy);
-            split2(pb[2], pb[3], ah[3], al[3], dummy);
-            mma16816(o[m][0], ah, v0.x, v0.y);
-            mma16816(ox[m][0], ah, v0.z, v0.w);
-            mma16816(ox[m][0], al, v0.x, v0.y);
-            mma16816(o[m][1], ah, v1.x, v1.y);
-            mma16816(ox[m][1], ah, v1.z, v1.w);
-            mma16816(ox[m][1], al, v1.x, v1.y);
+          for (int i = 0; i < 4; ++i) {
+            pa[i] = (key + (i & 1) < p.nq) ? exp2f(fmaf(sa[i], L2E, -mb[i >> 1])) : 0.f;
+            pb[i] = (key + 8 + (i & 1) < p.nq) ? exp2f(fmaf(sb[i], L2E, -mb[i >> 1])) : 0.f;
           }
+          sum[0] += (pa[0] + pa[1]) + (pb[0] + pb[1]);
+          sum[1] += (pa[2] + pa[3]) + (pb[2] + pb[3]);
+          uint32_t ah[4], al[4];
+          bool dummy = false;                                            // probabilities are in [0, 1]
+          split2(pa[0], pa[1], ah[0], al[0], dummy);
+          split2(pa[2], pa[3], ah[1], al[1], dummy);
+          split2(pb[0], pb[1], ah[2], al[2], dummy);
+          split2(pb[2], pb[3], ah[3], al[3], dummy);
+          mma16816(o[0], ah, v0.x, v0.y);
+          mma16816(ox[0], ah, v0.z, v0.w);
+          mma16816(ox[0], al, v0.x, v0.y);
+          mma16816(o[1], ah, v1.x, v1.y);
+          mma16816(ox[1], ah, v1.z, v1.w);
+          mma16816(ox[1], al, v1.x, v1.y);
         }
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            sum[m][i] += __shfl_xor_sync(0xffffffffu, sum[m][i], 1);
-            sum[m][i] += __shfl_xor_sync(0xffffffffu, sum[m][i], 2);
-          }
+        for (int i = 0; i < 2; ++i) {
+          sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+          sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+        }
         // attention output (split) -> A1: the out-projection's operand
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int hr = 0; hr < 2; ++hr) {
-              const float inv = 1.f / sum[m][hr];
-              const float a = fmaf(ox[m][nt][2 * hr], 1.f / 2048.f, o[m][nt][2 * hr]) * inv;
-              const float b = fmaf(ox[m][nt][2 * hr + 1], 1.f / 2048.f, o[m][nt][2 * hr + 1]) * inv;
-              const int row = m * 16 + g + 8 * hr, col = h * DS_D + nt * 8 + 2 * t;
-              uint32_t hh, ll;
-              split2(a, b, hh, ll, ovf);
-              *reinterpret_cast<uint32_t*>(A1h + row * DS_LDA + col) = hh;
-              *reinterpret_cast<uint32_t*>(A1l + row * DS_LDA + col) = ll;
-            }
+          for (int hr = 0; hr < 2; ++hr) {
+            const float inv = 1.f / sum[hr];
+            const float a = fmaf(ox[nt][2 * hr], 1.f / 2048.f, o[nt][2 * hr]) * inv;
+            const float b = fmaf(ox[nt][2 * hr + 1], 1.f / 2048.f, o[nt][2 * hr + 1]) * inv;
+            const int row = m * 16 + g + 8 * hr, col = h * DS_D + nt * 8 + 2 * t;
+            uint32_t hh, ll;
+            split2(a, b, hh, ll, ovf);
+            *reinterpret_cast<uint32_t*>(A1h + row * DS_LDA + col) = hh;
+            *reinterpret_cast<uint32_t*>(A1l + row * DS_LDA + col) = ll;
+          }
       }
       __syncthreads();
     }
     // ---- attention out-projection + residual -> LayerNorm 0 -> x1 ; A1 = split(x1 + qpe)
     {
-      float acc[2][2][4], accx[2][2][4];
-      zero_acc<2>(acc, accx);
-      gemm8<2>(A1h, A1l, DS_LDA, 0, W.w_o, 8, warp * 2, 0, lane, acc, accx);
-      for_acc<2>(acc, accx, warp * 16, lane, [&](int row, int col, float v0, float v1) {
+      float acc[2][1][4], accx[2][1][4];
+      zero_acc<1>(acc, accx);
+      gemm8<1>(A1h, A1l, DS_LDA, 0, W.w_o, 8, warp, 0, lane, acc, accx);
+      for_acc<1>(acc, accx, warp * 8, lane, [&](int row, int col, float v0, float v1) {
         const float2 r = *reinterpret_cast<const float2*>(xs + row * DS_C + col);
         *reinterpret_cast<float2*>(ys + row * DS_LDY + col) = make_float2(v0 + __ldg(W.b_o + col) + r.x, v1 + __ldg(W.b_o + col + 1) + r.y);
       });
@@ -435,52 +503,33 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
     // ---- sampling offsets | attention weights = (x1 + qpe) W_oa
     float* oas = reinterpret_cast<float*>(big);                          // [32][n_oa + 4]
     const int ldoa = p.n_oa + 4;
-    for (int pair = warp; pair < p.n_oa / 16; pair += 8) {
-      float acc[2][2][4], accx[2][2][4];
-      zero_acc<2>(acc, accx);
-      gemm8<2>(A1h, A1l, DS_LDA, 0, W.w_oa, 8, pair * 2, 0, lane, acc, accx);
-      for_acc<2>(acc, accx, pair * 16, lane, [&](int row, int col, float v0, float v1) {
+#pragma unroll 1
+    for (int nt = warp; nt < p.n_oa / 8; nt += DS_NW) {
+      float acc[2][1][4], accx[2][1][4];
+      zero_acc<1>(acc, accx);
+      gemm8<1>(A1h, A1l, DS_LDA, 0, W.w_oa, 8, nt, 0, lane, acc, accx);
+      for_acc<1>(acc, accx, nt * 8, lane, [&](int row, int col, float v0, float v1) {
         *reinterpret_cast<float2*>(oas + row * ldoa + col) = make_float2(v0 + __ldg(W.b_oa + col), v1 + __ldg(W.b_oa + col + 1));
       });
     }
     __syncthreads();
     // ---- multi-scale deformable sampling -> A2 (split): 16 lanes per (query, head) = 4 corners x 4 channel quads
+    msda_prepare(oas, ldoa, refs, p, tid);
+    __syncthreads();
     {
       const int LP = p.L * p.P, n_off = DS_HEADS * LP * 2;
       const int sub = tid >> 4, l16 = tid & 15, corner = l16 >> 2, c4 = l16 & 3;
       const int dy = corner >> 1, dx = corner & 1;
-      const float* vbase = p.value + (size_t)scene * p.v_bstride * p.ldv + l * DS_C;
-      for (int it = 0; it < (DS_R * DS_HEADS) / 16; ++it) {
-        const int pairi = it * 16 + sub, row = pairi >> 3, h = pairi & 7;
+      const bool fixed12 = p.L == 3 && p.P == 4;
+      const float* vscene = p.value + (size_t)scene * p.v_bstride * p.ldv + l * DS_C + c4 * 4;
+#pragma unroll 1
+      for (int it = 0; it < (DS_R * DS_HEADS) / (DS_NT / 16); ++it) {
+        const int pairi = it * (DS_NT / 16) + sub, row = pairi >> 3, h = pairi & 7;
         float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < n_valid) {
           const float* aw = oas + row * ldoa + n_off + h * LP;
           const float* of = oas + row * ldoa + h * LP * 2;
-          const float rx = refs[row * 2], ry = refs[row * 2 + 1];
-          float mxw = -INFINITY;
-          for (int i = 0; i < LP; ++i) mxw = fmaxf(mxw, aw[i]);
-          float den = 0.f;
-          for (int i = 0; i < LP; ++i) den += expf(aw[i] - mxw);
-          const float inv = 1.f / den;
-          for (int lv = 0; lv < p.L; ++lv) {
-            const int H = p.lvl_h[lv], Wd = p.lvl_w[lv];
-            const float* base = vbase + (size_t)p.lvl_start[lv] * p.ldv + h * DS_D + c4 * 4;
-#pragma unroll 4
-            for (int pt = 0; pt < p.P; ++pt) {
-              const int i = lv * p.P + pt;
-              const float lx = rx + of[i * 2] / (float)Wd, ly = ry + of[i * 2 + 1] / (float)H;
-              const float px = lx * (float)Wd - 0.5f, py = ly * (float)H - 0.5f;
-              const float x0f = floorf(px), y0f = floorf(py);
-              const int xi = (int)x0f + dx, yi = (int)y0f + dy;
-              const float fx = px - x0f, fy = py - y0f;
-              if (xi >= 0 && xi < Wd && yi >= 0 && yi < H) {
-                const float wgt = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (expf(aw[i] - mxw) * inv);
-                const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yi * Wd + xi) * p.ldv));
-                acc4.x = fmaf(wgt, v.x, acc4.x); acc4.y = fmaf(wgt, v.y, acc4.y);
-                acc4.z = fmaf(wgt, v.z, acc4.z); acc4.w = fmaf(wgt, v.w, acc4.w);
-              }
-            }
-          }
+          acc4 = fixed12 ? msda_sample<12>(of, aw, vscene + h * DS_D, p, dx, dy) : msda_sample<0>(of, aw, vscene + h * DS_D, p, dx, dy);
         }
         // sum the four corners (lane bits 2, 3 of the 16-lane group)
 #pragma unroll
@@ -501,10 +550,10 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
     __syncthreads();
     // ---- MSDA output projection + residual -> LayerNorm 1 -> x2 ; A1 = split(x2)
     {
-      float acc[2][2][4], accx[2][2][4];
-      zero_acc<2>(acc, accx);
-      gemm8<2>(A2h, A2l, DS_LDA, 0, W.w_op, 8, warp * 2, 0, lane, acc, accx);
-      for_acc<2>(acc, accx, warp * 16, lane, [&](int row, int col, float v0, float v1) {
+      float acc[2][1][4], accx[2][1][4];
+      zero_acc<1>(acc, accx);
+      gemm8<1>(A2h, A2l, DS_LDA, 0, W.w_op, 8, warp, 0, lane, acc, accx);
+      for_acc<1>(acc, accx, warp * 8, lane, [&](int row, int col, float v0, float v1) {
         const float2 r = *reinterpret_cast<const float2*>(xs + row * DS_C + col);
         *reinterpret_cast<float2*>(ys + row * DS_LDY + col) = make_float2(v0 + __ldg(W.b_op + col) + r.x, v1 + __ldg(W.b_op + col + 1) + r.y);
       });
@@ -516,16 +565,18 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
     {
       __half* Hh = reinterpret_cast<__half*>(big);                       // [32][264] x 2 planes
       __half* Hl = Hh + DS_R * DS_LDH;
-      float accy[2][2][4], accyx[2][2][4];
-      zero_acc<2>(accy, accyx);
+      float accy[2][1][4], accyx[2][1][4];
+      zero_acc<1>(accy, accyx);
       const int n_chunks = p.ffn / DS_FCH, ks2 = p.ffn / 16;
+#pragma unroll 1
       for (int ch = 0; ch < n_chunks; ++ch) {
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int pair = warp * 2 + i;                                 // pair inside the chunk: columns 16 pair ..
-          float acc[2][2][4], accx[2][2][4];
-          zero_acc<2>(acc, accx);
-          gemm8<2>(A1h, A1l, DS_LDA, 0, W.w_f1, 8, ch * (DS_FCH / 8) + pair * 2, 0, lane, acc, accx);
-          for_acc<2>(acc, accx, pair * 16, lane, [&](int row, int col, float v0, float v1) {
+          const int nt = i * DS_NW + warp;                               // n-tile inside the chunk: columns 8 nt ..
+          float acc[2][1][4], accx[2][1][4];
+          zero_acc<1>(acc, accx);
+          gemm8<1>(A1h, A1l, DS_LDA, 0, W.w_f1, 8, ch * (DS_FCH / 8) + nt, 0, lane, acc, accx);
+          for_acc<1>(acc, accx, nt * 8, lane, [&](int row, int col, float v0, float v1) {
             const int gc = ch * DS_FCH + col;
             uint32_t hh, ll;
             split2(fmaxf(v0 + __ldg(W.b_f1 + gc), 0.f), fmaxf(v1 + __ldg(W.b_f1 + gc + 1), 0.f), hh, ll, ovf);
@@ -534,11 +585,11 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
           });
         }
         __syncthreads();
-        gemm8<2>(Hh, Hl, DS_LDH, 0, W.w_f2, ks2, warp * 2, ch * 16, lane, accy, accyx);
-        gemm8<2>(Hh, Hl, DS_LDH, 128, W.w_f2, ks2, warp * 2, ch * 16 + 8, lane, accy, accyx);
+        gemm8<1>(Hh, Hl, DS_LDH, 0, W.w_f2, ks2, warp, ch * 16, lane, accy, accyx);
+        gemm8<1>(Hh, Hl, DS_LDH, 128, W.w_f2, ks2, warp, ch * 16 + 8, lane, accy, accyx);
         __syncthreads();
       }
-      for_acc<2>(accy, accyx, warp * 16, lane, [&](int row, int col, float v0, float v1) {
+      for_acc<1>(accy, accyx, warp * 8, lane, [&](int row, int col, float v0, float v1) {
         const float2 r = *reinterpret_cast<const float2*>(xs + row * DS_C + col);
         *reinterpret_cast<float2*>(ys + row * DS_LDY + col) = make_float2(v0 + __ldg(W.b_f2 + col) + r.x, v1 + __ldg(W.b_f2 + col + 1) + r.y);
       });
@@ -550,7 +601,7 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
 
   // ---- stage output: query features
   if (p.x_out) {
-    for (int e = tid; e < DS_R * (DS_C / 4); e += 256) {
+    for (int e = tid; e < DS_R * (DS_C / 4); e += DS_NT) {
       const int row = e >> 5, c4 = e & 31;
       if (row < n_valid) reinterpret_cast<float4*>(p.x_out + (grow0 + row) * DS_C)[c4] = reinterpret_cast<const float4*>(xs)[e];
     }
@@ -560,11 +611,12 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
     const int ldhh = p.n_h1 + 8;
     __half* HHh = reinterpret_cast<__half*>(big);
     __half* HHl = HHh + DS_R * ldhh;
-    for (int pair = warp; pair < p.n_h1 / 16; pair += 8) {
-      float acc[2][2][4], accx[2][2][4];
-      zero_acc<2>(acc, accx);
-      gemm8<2>(A1h, A1l, DS_LDA, 0, p.w_h1, 8, pair * 2, 0, lane, acc, accx);
-      for_acc<2>(acc, accx, pair * 16, lane, [&](int row, int col, float v0, float v1) {
+#pragma unroll 1
+    for (int nt = warp; nt < p.n_h1 / 8; nt += DS_NW) {
+      float acc[2][1][4], accx[2][1][4];
+      zero_acc<1>(acc, accx);
+      gemm8<1>(A1h, A1l, DS_LDA, 0, p.w_h1, 8, nt, 0, lane, acc, accx);
+      for_acc<1>(acc, accx, nt * 8, lane, [&](int row, int col, float v0, float v1) {
         uint32_t hh, ll;
         split2(fmaxf(v0 + __ldg(p.b_h1 + col), 0.f), fmaxf(v1 + __ldg(p.b_h1 + col + 1), 0.f), hh, ll, ovf);
         *reinterpret_cast<uint32_t*>(HHh + row * ldhh + col) = hh;
@@ -573,11 +625,13 @@ __global__ void __launch_bounds__(256, 1) decoder_stage_kernel(const DsP p) {
     }
     __syncthreads();
     const int ks2 = p.n_h1 / 16;
-    for (int pair = warp; pair < p.n_pred / 16; pair += 8) {
-      float acc[2][2][4], accx[2][2][4];
-      zero_acc<2>(acc, accx);
-      for (int k8 = 0; k8 < ks2 / 8; ++k8) gemm8<2>(HHh, HHl, ldhh, k8 * 128, p.w_h2, ks2, pair * 2, k8 * 8, lane, acc, accx);
-      for_acc<2>(acc, accx, pair * 16, lane, [&](int row, int col, float v0, float v1) {
+#pragma unroll 1
+    for (int nt = warp; nt < p.n_pred / 8; nt += DS_NW) {
+      float acc[2][1][4], accx[2][1][4];
+      zero_acc<1>(acc, accx);
+#pragma unroll 1
+      for (int k8 = 0; k8 < ks2 / 8; ++k8) gemm8<1>(HHh, HHl, ldhh, k8 * 128, p.w_h2, ks2, nt, k8 * 8, lane, acc, accx);
+      for_acc<1>(acc, accx, nt * 8, lane, [&](int row, int col, float v0, float v1) {
         if (row < n_valid) {
           float* pr = p.pred + (grow0 + row) * p.ld_pred;
           if (col < p.pred_cols) pr[col] = v0 + __ldg(p.b_h2 + col);
@@ -668,7 +722,7 @@ extern "C" int ff3d_decoder_stage(const ff3d_decoder_stage_desc* d, ff3d_stream_
     p.counters = counters + s0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ns * nblk));
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(DS_NT);
     cfg.dynamicSmemBytes = DS_SMEM;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
