@@ -90,6 +90,21 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& 
   l = *reinterpret_cast<uint32_t*>(&ll);
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+// split of two values known to lie in the fp16 range (soft-max probabilities): packed conversions, no clamps
+__device__ __forceinline__ void split2_unit(float a, float b, uint32_t& h, uint32_t& l) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
+  h = *reinterpret_cast<const uint32_t*>(&hh);
+  l = *reinterpret_cast<const uint32_t*>(&ll);
+}
+
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -108,23 +123,17 @@ __device__ __forceinline__ void gemm8(const __half* __restrict__ Ah, const __hal
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) b[nt][ks] = __ldg(wf + ((size_t)(nt0 + nt) * ks_total + ks0 + ks) * 32 + lane);
-  const int g = lane >> 2, t = lane & 3;
+  // ldmatrix.x4: lanes 0-7 / 8-15 / 16-23 / 24-31 address the rows of the (rows 0-7, k 0-7) / (rows 8-15, k 0-7) /
+  // (rows 0-7, k 8-15) / (rows 8-15, k 8-15) 8x8 blocks = the a0..a3 registers of the m16n8k16 A fragment
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
+  const uint32_t ah_base = smem_u32(Ah + lrow * lda + kofs + lcol), al_base = smem_u32(Al + lrow * lda + kofs + lcol);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const int k = kofs + ks * 16 + 2 * t;
     uint32_t ah[2][4], al[2][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      const __half* ph = Ah + (m * 16 + g) * lda + k;
-      const __half* pl = Al + (m * 16 + g) * lda + k;
-      ah[m][0] = *reinterpret_cast<const uint32_t*>(ph);
-      ah[m][1] = *reinterpret_cast<const uint32_t*>(ph + 8 * lda);
-      ah[m][2] = *reinterpret_cast<const uint32_t*>(ph + 8);
-      ah[m][3] = *reinterpret_cast<const uint32_t*>(ph + 8 * lda + 8);
-      al[m][0] = *reinterpret_cast<const uint32_t*>(pl);
-      al[m][1] = *reinterpret_cast<const uint32_t*>(pl + 8 * lda);
-      al[m][2] = *reinterpret_cast<const uint32_t*>(pl + 8);
-      al[m][3] = *reinterpret_cast<const uint32_t*>(pl + 8 * lda + 8);
+      ldmatrix_x4(ah[m], ah_base + (uint32_t)((m * 16 * lda + ks * 16) * 2));
+      ldmatrix_x4(al[m], al_base + (uint32_t)((m * 16 * lda + ks * 16) * 2));
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
@@ -453,11 +462,10 @@ __global__ void __launch_bounds__(DS_NT, 1) decoder_stage_kernel(const DsP p) {
           sum[0] += (pa[0] + pa[1]) + (pb[0] + pb[1]);
           sum[1] += (pa[2] + pa[3]) + (pb[2] + pb[3]);
           uint32_t ah[4], al[4];
-          bool dummy = false;                                            // probabilities are in [0, 1]
-          split2(pa[0], pa[1], ah[0], al[0], dummy);
-          split2(pa[2], pa[3], ah[1], al[1], dummy);
-          split2(pb[0], pb[1], ah[2], al[2], dummy);
-          split2(pb[2], pb[3], ah[3], al[3], dummy);
+          split2_unit(pa[0], pa[1], ah[0], al[0]);                       // probabilities are in [0, 1]
+          split2_unit(pa[2], pa[3], ah[1], al[1]);
+          split2_unit(pb[0], pb[1], ah[2], al[2]);
+          split2_unit(pb[2], pb[3], ah[3], al[3]);
           mma16816(o[0], ah, v0.x, v0.y);
           mma16816(ox[0], ah, v0.z, v0.w);
           mma16816(ox[0], al, v0.x, v0.y);

@@ -151,6 +151,7 @@ class SparseEncoder(ParamTree):
         self.pk = None
         # row-capacity growth per strided conv (level-2 sites measured at 1.25-2.4x level 1; overflow raises)
         self.cap_growth = (3.0, 1.0, 1.0, 1.0)
+        self._side, self._plan_keepalive = None, None
 
     def prepare(self, dev):
         sd = self.flat()
@@ -174,19 +175,69 @@ class SparseEncoder(ParamTree):
         pk["conv_out"] = sp("conv_out.0.weight", "conv_out.1")
         self.pk = pk
 
-    def forward(self, vox, batch, bev_out, overflow):
-        """vox: dict from ops.voxelize; bev_out [B,H,W,2*C] zero-initialised NHWC buffer (channel = d*C + c).
-        Every level is stored in tap-mask order (ops.SparseLevel.sort_by_mask): the voxeliser's first-appearance order
-        (the reference's, checked by the parity tests) stays untouched in ``vox``; row order inside the sparse encoder is
-        implementation-defined in spconv too and vanishes in the dense BEV scatter."""
-        dev = vox["mean"].device
+    def _plan(self, vox, batch, overflow, bev_shape, record):
+        """Rulebooks of all 21 convs (hash tables, mask-ordered levels, neighbour maps, tile masks): coordinates only, no
+        features.  ``record(k)`` is called after level k's maps are complete (k = 0: input level incl. the row permutation
+        of the voxel features).  Returns dict(perm, levels=[(level, subm rulebook, down rulebook into it)], out=...)."""
         cap1 = vox["coors"].shape[0]
         lvl = ops.SparseLevel(vox["coors"], vox["n_dev"][:1], cap1, batch, self.sparse_shape)
         lvl.build_hash()
         perm = lvl.sort_by_mask()
-        feats = ops.gather_rows(vox["mean"], perm, lvl.n_dev, vox["mean"].shape[1])
-        if ops.tma_ok(self.pk["conv_input"][0], feats.shape[1], self.pk["conv_input"][0].shape[-1], sparse=True):
-            feats = ops.split_rows(feats, n_dev=lvl.n_dev, zero_row=True)
+        levels = [(lvl, lvl.subm_map(), None)]
+        record(0)
+        for i, blocks in enumerate(self.encoder_channels):
+            if i == len(self.encoder_channels) - 1:
+                break
+            pad = self.encoder_paddings[i][len(blocks) - 1]
+            p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
+            cap_out = int(lvl.cap * self.cap_growth[i])
+            nl, rb = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow, ldy=blocks[-1])
+            levels.append((nl, nl.subm_map(), rb))
+            lvl = nl
+            record(i + 1)
+        Hb, Wb, ld = bev_shape
+        Cc = self.output_channels
+        nl, rb = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), lvl.cap, overflow, ldy=ld, sort_level=False, bev=(Hb, Wb, Cc))
+        assert ld == nl.shape[0] * Cc and (Hb, Wb) == tuple(nl.shape[1:])
+        record(len(levels))
+        return dict(perm=perm, levels=levels, out=(nl, rb))
+
+    def forward(self, vox, batch, bev_out, overflow):
+        """vox: dict from ops.voxelize; bev_out [B,H,W,2*C] zero-initialised NHWC buffer (channel = d*C + c).
+        Every level is stored in tap-mask order (ops.SparseLevel.sort_by_mask): the voxeliser's first-appearance order
+        (the reference's, checked by the parity tests) stays untouched in ``vox``; row order inside the sparse encoder is
+        implementation-defined in spconv too and vanishes in the dense BEV scatter.
+
+        Two streams: the rulebooks depend on coordinates only, so the whole chain (hash inserts, probes, radix sorts --
+        latency / L2 bound small kernels, ~2 ms at bs = 4) runs on a side stream ahead of the gather-GEMMs of the main
+        stream, which wait per level on an event.  Inside a CUDA-graph capture the side stream becomes a parallel branch."""
+        dev = vox["mean"].device
+        assert bev_out.is_contiguous()
+        bev_shape = (bev_out.shape[1], bev_out.shape[2], bev_out.shape[3])
+        main = torch.cuda.current_stream()
+        if ops.SPARSE_OVERLAP:
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side, events = self._side, []
+
+            def record(k):
+                e = torch.cuda.Event()
+                e.record(side)
+                events.append(e)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                plan = self._plan(vox, batch, overflow, bev_shape, record)
+
+            def ready(k):
+                main.wait_event(events[k])
+        else:
+            plan = self._plan(vox, batch, overflow, bev_shape, lambda k: None)
+
+            def ready(k):
+                pass
+        # everything the side stream allocated stays referenced until the next forward (the caching allocator must not hand
+        # those blocks out again while main-stream kernels still read them)
+        self._plan_keepalive = plan
 
         def conv(x, rb, n_dev, wb, cap_out, act, res=None):
             """One sparse conv.  With the TMA / cp.async kernel every level lives in split form (ops.Split: a row of C
@@ -202,32 +253,32 @@ class SparseEncoder(ParamTree):
             ops.sparse_conv(x, rb, n_dev, w, b, y, act=act, res=res)
             return y
 
-        x = conv(feats, lvl.subm_map(), lvl.n_dev, self.pk["conv_input"], cap1, ACT_RELU)
+        ready(0)
+        lvl, subm, _ = plan["levels"][0]
+        feats = ops.gather_rows(vox["mean"], plan["perm"], lvl.n_dev, vox["mean"].shape[1])
+        if ops.tma_ok(self.pk["conv_input"][0], feats.shape[1], self.pk["conv_input"][0].shape[-1], sparse=True):
+            feats = ops.split_rows(feats, n_dev=lvl.n_dev, zero_row=True)
+        x = conv(feats, subm, lvl.n_dev, self.pk["conv_input"], lvl.cap, ACT_RELU)
         self.level_sizes = [lvl.n_dev]
         for i, blocks in enumerate(self.encoder_channels):
             for j, cout in enumerate(blocks):
                 q = f"encoder_layers.encoder_layer{i + 1}.{j}"
                 if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
-                    pad = self.encoder_paddings[i][j]
-                    p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
-                    cap_out = int(lvl.cap * self.cap_growth[i])
-                    nl, rb = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow, ldy=cout)
-                    x = conv(x, rb, nl.n_dev, self.pk[q], nl.cap, ACT_RELU)
-                    lvl = nl
+                    ready(i + 1)
+                    lvl, subm, rb = plan["levels"][i + 1]
+                    x = conv(x, rb, lvl.n_dev, self.pk[q], lvl.cap, ACT_RELU)
                     self.level_sizes.append(lvl.n_dev)
                 else:
-                    rb = lvl.subm_map()
-                    t = conv(x, rb, lvl.n_dev, self.pk[q + ".1"], lvl.cap, ACT_RELU)
-                    x = conv(t, rb, lvl.n_dev, self.pk[q + ".2"], lvl.cap, ACT_RELU, res=x)
+                    t = conv(x, subm, lvl.n_dev, self.pk[q + ".1"], lvl.cap, ACT_RELU)
+                    x = conv(t, subm, lvl.n_dev, self.pk[q + ".2"], lvl.cap, ACT_RELU, res=x)
         # conv_out: SparseConv3d k(3,1,1) s(2,1,1) p0 + BN + ReLU, scattered straight into the NHWC BEV grid
-        Cc = self.output_channels
-        assert bev_out.is_contiguous()
-        Hb, Wb, ld = bev_out.shape[1], bev_out.shape[2], bev_out.shape[3]
-        nl, rb = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), lvl.cap, overflow, ldy=ld, sort_level=False, bev=(Hb, Wb, Cc))
+        ready(len(plan["levels"]))
+        nl, rb = plan["out"]
         self.level_sizes.append(nl.n_dev)
-        assert ld == nl.shape[0] * Cc and (Hb, Wb) == tuple(nl.shape[1:])
         w, b = self.pk["conv_out"]
-        ops.sparse_conv(x, rb, nl.n_dev, w, b, bev_out, act=ACT_RELU, cout=Cc)
+        ops.sparse_conv(x, rb, nl.n_dev, w, b, bev_out, act=ACT_RELU, cout=self.output_channels)
+        if ops.SPARSE_OVERLAP:
+            main.wait_stream(self._side)
         return bev_out
 
 
