@@ -87,6 +87,9 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 // arrive on `bar` when all cp.async copies issued so far by this thread have completed; .noinc: the arrival is one of the
 // barrier's expected arrivals (it was counted at init)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -94,8 +97,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 }
 
 template <int MODE, int BN, int NS, int NPW, bool CPA = false>
-__global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid_constant__ CUtensorMap tmA, const TmP p) {
+__global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_kernel(const __grid_constant__ CUtensorMap tmA, const TmP p) {
   constexpr int MMA_WARP = NPW;
+  constexpr int IDX_WARP = NPW + 5;                               // CPA only: stages the tiles' neighbour maps in shared memory
   // Chunked accumulation (dense modes, one producer warp): the tensor core's fp32 accumulate TRUNCATES, once per MMA
   // (16 products); over a long K that is a systematic bias (measured at K = 8192, all-positive products: -4.7e-5 relative,
   // 10x the fp32 SIMT kernel, gone when the same K is summed as 8 chunks).  So the K loop is cut into chunks of CHUNK
@@ -119,6 +123,12 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
   const uint32_t tfull_bar = empty_bar + 8u * NS;                // [2]
   const uint32_t tempty_bar = tfull_bar + 16u;                   // [2]
   const uint32_t tmem_ptr = tempty_bar + 16u;
+  // CPA: neighbour-map double buffer [2][27 taps][128 rows] int32, filled one to two tiles ahead by the index warp (the
+  // producers' own index loads sat on the critical path: 36 % of their stall samples waited for an nbr value)
+  const uint32_t ifull_bar = tmem_ptr + 16u;                      // [2]
+  const uint32_t iempty_bar = ifull_bar + 16u;                    // [2]
+  const uint32_t idx_buf = iempty_bar + 16u;
+  constexpr uint32_t IDX_TILE_BYTES = TC_MAX_TAPS * TC_BM * 4;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int Mv = p.M;
@@ -148,6 +158,8 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(full_bar + 8u * s, CPA ? NPW * 32 + 1 : NPW); mbar_init(empty_bar + 8u * s, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8u * i, 1); mbar_init(tempty_bar + 8u * i, 128); }
+    if (CPA)
+      for (int i = 0; i < 2; ++i) { mbar_init(ifull_bar + 8u * i, 32); mbar_init(iempty_bar + 8u * i, NPW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -174,31 +186,28 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
       const int j = lane & 7, q = lane >> 3;
       const char* xbase = reinterpret_cast<const char*>(p.xs);
       const size_t row_bytes = (size_t)p.ldxs * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;                                                  // tiles processed by this CTA (index buffer = it & 1)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int mtile = tile / n_tiles_n;
         const int ntile = tile - mtile * n_tiles_n;
         const uint8_t* wsrc = wbase + (size_t)ntile * p.n_stages * stage_bytes;
-        const int m0 = mtile * TC_BM;
         uint32_t mm = masked ? unit_mask(tile) : (p.n_units >= 32 ? 0xFFFFFFFFu : ((1u << p.n_units) - 1u));
         // this lane's tap inside unit u and its channel offset: cin >= 64 -> tap u, the lane's 8 channels of chunk c;
         // cin < 64 -> the K-step packs tps taps: 16-byte chunk j belongs to tap u*tps + (8j / cin)
         const int lane_tap = p.tps > 1 ? (j * 8) / p.cin : 0;
         const int lane_col = p.tps > 1 ? (j * 8) % p.cin : j * 8;
-        int idx[RI], nidx[RI];
-        auto load_idx = [&](int u, int* dst) {
+        // the tile's neighbour map, staged by the index warp: [tap][row] (rows past the count and absent taps hold -1)
+        const uint32_t ib = idx_buf + (uint32_t)(it & 1) * IDX_TILE_BYTES + (uint32_t)(warp * RPW + q) * 4u;
+        const uint32_t tmk = masked ? __ldg(p.tile_mask + mtile) : 0xFFFFFFFFu;
+        mbar_wait(ifull_bar + 8u * (it & 1), (uint32_t)((it >> 1) & 1));
+        while (mm) {
+          const int u = __ffs(mm) - 1;
+          mm &= mm - 1u;
           const int t = u * p.tps + lane_tap;
+          const bool tap_ok = t < p.taps && ((tmk >> t) & 1u);      // taps the index warp skipped hold stale rows
+          int idx[RI];
 #pragma unroll
-          for (int i = 0; i < RI; ++i) {
-            const int m = m0 + warp * RPW + q + 4 * i;
-            dst[i] = (t < p.taps && m < Mv) ? __ldg(p.nbr + (size_t)t * p.nbr_stride + m) : -1;
-          }
-        };
-        int u = __ffs(mm) - 1;
-        mm &= mm - 1u;
-        load_idx(u, idx);
-        while (u >= 0) {
-          const int un = mm ? __ffs(mm) - 1 : -1;                 // prefetch the next unit's row indices
-          if (un >= 0) { mm &= mm - 1u; load_idx(un, nidx); }
+          for (int i = 0; i < RI; ++i) idx[i] = tap_ok ? lds32(ib + (uint32_t)(t * TC_BM + 4 * i) * 4u) : -1;
           for (int c = 0; c < p.cpt; ++c) {
             const uint32_t slot_a = smem + (uint32_t)ring.slot * SLOT_BYTES;
             const uint32_t bar = full_bar + 8u * ring.slot;
@@ -224,12 +233,11 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
             // the hardware arrives on the stage's barrier once THIS thread's copies have landed (the CUTLASS sm100
             // cp.async + UMMA pipeline): exact signalling, nothing to wait for here
             cp_async_arrive_noinc(bar);
-            ring.advance(1, NS);
+            if (++ring.slot == NS) { ring.slot = 0; ring.phase ^= 1u; }
           }
-          u = un;
-#pragma unroll
-          for (int i = 0; i < RI; ++i) idx[i] = nidx[i];
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(iempty_bar + 8u * (it & 1));     // this warp is done with the index buffer
       }
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -337,6 +345,29 @@ __global__ void __launch_bounds__(32 * (NPW + 5), 1) tmagemm_kernel(const __grid
       }
     }
     __syncwarp();
+  } else if (CPA && warp == IDX_WARP) {
+    // =========================== index warp (CPA): neighbour maps of the coming tiles -> shared memory ===========================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mtile = tile / n_tiles_n;
+      const int m0 = mtile * TC_BM;
+      const uint32_t tm = masked ? __ldg(p.tile_mask + mtile) : 0xFFFFFFFFu;      // tap-level mask of the tile
+      if (it >= 2) mbar_wait(iempty_bar + 8u * (it & 1), (uint32_t)(((it >> 1) - 1) & 1));
+      const uint32_t ib = idx_buf + (uint32_t)(it & 1) * IDX_TILE_BYTES;
+      // lane l: rows l, l+32, l+64, l+96 of every present tap, as 4-byte cp.async copies (128-byte coalesced per warp
+      // instruction, no registers, all ~100 copies of the tile in flight at once); rows past the count are zero-filled:
+      // they gather row 0 and their outputs are never stored
+      for (int t = 0; t < p.taps; ++t) {
+        if (!((tm >> t) & 1u)) continue;
+        const int* nb = p.nbr + (size_t)t * p.nbr_stride + m0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = m0 + lane + 32 * i < Mv;
+          cp_async4(ib + (uint32_t)(t * TC_BM + lane + 32 * i) * 4u, ok ? nb + lane + 32 * i : p.nbr, ok ? 4u : 0u);
+        }
+      }
+      cp_async_arrive_noinc(ifull_bar + 8u * (it & 1));              // 32 arrivals, each when that lane's copies have landed
+    }
   } else {
     // =========================== epilogue (four warps: TMEM lane quarter = warp % 4) ===========================
     const int r = (warp & 3) * 32 + lane;                     // tile row <-> TMEM lane
@@ -564,16 +595,19 @@ static int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_
 
 template <int MODE, int BN, int NPW, bool CPA>
 static int launch_tm_cfg(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
-  constexpr int NS = BN == 128 ? 3 : (BN == 64 ? 4 : 5);          // 64 / 48 / 40 / 36 KB per stage
+  // 64 / 48 / 40 / 36 KB per stage; the cp.async gather also holds two neighbour-map tiles (27 KB)
+  constexpr int NS = BN == 128 ? 3 : (BN == 64 ? 4 : ((CPA && BN == 32) ? 4 : 5));
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
-  const size_t smem = NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + 1024;
+  constexpr size_t IDX_BYTES = CPA ? 2 * (size_t)TC_MAX_TAPS * TC_BM * 4 + 32 : 0;
+  const size_t smem = NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + IDX_BYTES + 1024;
+  static_assert(NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + IDX_BYTES + 1024 <= 227 * 1024, "shared memory budget");
   static const cudaError_t attr =
       cudaFuncSetAttribute(tmagemm_kernel<MODE, BN, NS, NPW, CPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr != cudaSuccess) { set_error("ff3d_tmagemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr)); return FF3D_ECUDA; }
   const long long tiles = m_tiles * (p.cout / BN);
   const long long resident = num_sms();
   dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-  tmagemm_kernel<MODE, BN, NS, NPW, CPA><<<grid, 32 * (NPW + 5), smem, st>>>(tm, p);
+  tmagemm_kernel<MODE, BN, NS, NPW, CPA><<<grid, 32 * (NPW + 5 + (CPA ? 1 : 0)), smem, st>>>(tm, p);
   return check_launch("ff3d_tmagemm");
 }
 
@@ -590,11 +624,22 @@ static int sparse_gather_cfg() {
   return v;
 }
 
+// producer warps of the cp.async gather: FF3D_CPA_NPW = 4 / 8 (default 8); read once
+static int cpa_npw() {
+  static const int v = []() {
+    const char* e = getenv("FF3D_CPA_NPW");
+    const int n = e ? atoi(e) : 8;
+    return n == 4 ? 4 : 8;
+  }();
+  return v;
+}
+
 template <int MODE, int BN>
 static int launch_tm(const CUtensorMap& tm, const TmP& p, long long m_tiles, cudaStream_t st) {
   if constexpr (MODE == FF3D_GEMM_SPARSE) {
     switch (p.tps > 1 ? 0 : sparse_gather_cfg()) {
-      case 0: return launch_tm_cfg<MODE, BN, 8, true>(tm, p, m_tiles, st);
+      case 0: return cpa_npw() == 4 ? launch_tm_cfg<MODE, BN, 4, true>(tm, p, m_tiles, st)
+                                    : launch_tm_cfg<MODE, BN, 8, true>(tm, p, m_tiles, st);
       case 1: return launch_tm_cfg<MODE, BN, 1, false>(tm, p, m_tiles, st);
       case 4: return launch_tm_cfg<MODE, BN, 4, false>(tm, p, m_tiles, st);
       default: return launch_tm_cfg<MODE, BN, 8, false>(tm, p, m_tiles, st);
@@ -610,8 +655,8 @@ static int launch_tm_bn(const CUtensorMap& tm, const TmP& p, long long m_tiles, 
   if (bn == 64) return launch_tm<MODE, 64>(tm, p, m_tiles, st);
   if constexpr (MODE == FF3D_GEMM_SPARSE) {
     // narrow levels of the sparse encoder (C = 16 / 32): cp.async gather only
-    if (bn == 32) return launch_tm_cfg<MODE, 32, 8, true>(tm, p, m_tiles, st);
-    if (bn == 16) return launch_tm_cfg<MODE, 16, 8, true>(tm, p, m_tiles, st);
+    if (bn == 32) return cpa_npw() == 4 ? launch_tm_cfg<MODE, 32, 4, true>(tm, p, m_tiles, st) : launch_tm_cfg<MODE, 32, 8, true>(tm, p, m_tiles, st);
+    if (bn == 16) return cpa_npw() == 4 ? launch_tm_cfg<MODE, 16, 4, true>(tm, p, m_tiles, st) : launch_tm_cfg<MODE, 16, 8, true>(tm, p, m_tiles, st);
   } else {
     // narrow dense outputs (e.g. the 128 -> 10(16) heat-map conv)
     if (bn == 32) return launch_tm_cfg<MODE, 32, 1, false>(tm, p, m_tiles, st);
