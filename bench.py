@@ -416,8 +416,9 @@ def run_ours(args):
         # pair that exists) over the measured dense-bf16 tensor peak.  The split-precision kernel EXECUTES 3 MMAs per
         # product (hi*hi, hi*lo, lo*hi) on kind::f16 (bf16-rate) or kind::tf32 (half that rate), times the tile-padding
         # factor exe_ratio: `executed` below is what the tensor pipe really ran.
-        roof = {"kernel": f"tcgemm_kernel{'<SPARSE>' if sparse else ''} {dom} (tcgen05 "
-                          f"{'fp16 hi/lo' if f16 else '3xTF32'} split, {'mask-sorted rulebook gather-GEMM' if sparse else 'implicit GEMM'})",
+        roof = {"kernel": f"{'tmagemm_kernel' if ops.tma_enabled() else 'tcgemm_kernel'}{'<SPARSE>' if sparse else ''} {dom} (tcgen05 "
+                          f"{'fp16 hi/lo' if f16 else '3xTF32'} split, "
+                          f"{'mask-sorted rulebook, cp.async gather-GEMM' if sparse else 'TMA-fed implicit GEMM'})",
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                 "traffic": traffic, "algorithmic_flops_per_launch": fl_l, "algorithmic_bytes_per_launch": by_l,
                 "ms_per_launch": t_l, "launches_per_step": n_launch, "share_of_step": t / step_ms,
@@ -431,8 +432,9 @@ def run_ours(args):
                                      "pipe-% uses is the hardware's nominal rate at the running clock, ~1.1 PF/s for TF32)"},
                 "hbm": {"achieved_GBps": by_l / (t_l * 1e-3) / 1e9, "peak_GBps": pk["hbm"],
                         "frac": by_l / (t_l * 1e-3) / 1e9 / pk["hbm"],
-                        "note": "algorithmic bytes only; at 27 taps x 128 channels the gather-GEMM does 864 flop/byte and "
-                                "cannot be HBM-bound at fp32-grade precision"}}
+                        "note": "algorithmic bytes only; the gather-GEMM does 390-860 flop per algorithmic byte at C >= 64 "
+                                "(tensor side at fp32-grade precision); what it actually moves is one 4C-byte row per executed "
+                                "(row, tap) pair from L2 plus the re-streamed weight stages (DESIGN.md 4.1)"}}
         if ncu_detail:
             roof["ncu"] = ncu_detail
         roof["by_kernel_family_ms"] = {k: round(v[0], 3) for k, v in kinds.items()}

@@ -9,6 +9,7 @@ names reproduce the reference checkpoint keys, so ``load_state_dict`` / ``load_c
 arithmetic runs in libff3d.so (no PyTorch compute fallback: without the library the import of ``.ops`` fails).
 """
 import math
+import contextlib
 import torch
 from torch import nn
 
@@ -175,32 +176,65 @@ class SparseEncoder(ParamTree):
         pk["conv_out"] = sp("conv_out.0.weight", "conv_out.1")
         self.pk = pk
 
-    def _plan(self, vox, batch, overflow, bev_shape, record):
+    def _plan(self, vox, batch, overflow, bev_shape, streams):
         """Rulebooks of all 21 convs (hash tables, mask-ordered levels, neighbour maps, tile masks): coordinates only, no
-        features.  ``record(k)`` is called after level k's maps are complete (k = 0: input level incl. the row permutation
-        of the voxel features).  Returns dict(perm, levels=[(level, subm rulebook, down rulebook into it)], out=...)."""
-        cap1 = vox["coors"].shape[0]
-        lvl = ops.SparseLevel(vox["coors"], vox["n_dev"][:1], cap1, batch, self.sparse_shape)
-        lvl.build_hash()
-        perm = lvl.sort_by_mask()
-        levels = [(lvl, lvl.subm_map(), None)]
-        record(0)
-        for i, blocks in enumerate(self.encoder_channels):
-            if i == len(self.encoder_channels) - 1:
-                break
-            pad = self.encoder_paddings[i][len(blocks) - 1]
-            p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
-            cap_out = int(lvl.cap * self.cap_growth[i])
-            nl, rb = lvl.downsample((3, 3, 3), (2, 2, 2), p3, cap_out, overflow, ldy=blocks[-1])
-            levels.append((nl, nl.subm_map(), rb))
-            lvl = nl
-            record(i + 1)
+        features.  Three phases: (A) the site sets of every level (each needs only its input level's coordinates);
+        (B) per level, independently: tap-mask sort + SubM map; (C) per strided conv: its rulebook, once both of its levels
+        are in final order.  With ``streams`` (one per level) the B / C chains of the levels run concurrently -- they are
+        latency-bound small kernels -- and every rulebook gets an event the gather-GEMMs wait on.
+        Returns dict(perm, levels=[(level, subm rulebook, down rulebook into it)], out=..., ready=[event per level], ...)."""
+        main = torch.cuda.current_stream()
+        ctx = (lambda k: torch.cuda.stream(streams[k % len(streams)])) if streams else (lambda k: contextlib.nullcontext())
+
+        def event(k):
+            if not streams:
+                return None
+            e = torch.cuda.Event()
+            e.record(streams[k % len(streams)])
+            return e
+
+        def wait(k, e):
+            if streams and e is not None:
+                streams[k % len(streams)].wait_event(e)
+        if streams:
+            streams[0].wait_stream(main)
+        n_lv = len(self.encoder_channels)
         Hb, Wb, ld = bev_shape
         Cc = self.output_channels
-        nl, rb = lvl.downsample((3, 1, 1), (2, 1, 1), (0, 0, 0), lvl.cap, overflow, ldy=ld, sort_level=False, bev=(Hb, Wb, Cc))
-        assert ld == nl.shape[0] * Cc and (Hb, Wb) == tuple(nl.shape[1:])
-        record(len(levels))
-        return dict(perm=perm, levels=levels, out=(nl, rb))
+        with ctx(0):                                                     # ---- A: site sets
+            cap1 = vox["coors"].shape[0]
+            lv = ops.SparseLevel(vox["coors"], vox["n_dev"][:1], cap1, batch, self.sparse_shape)
+            lv.build_hash()
+            lvls, geo = [lv], []
+            for i, blocks in enumerate(self.encoder_channels[:-1]):
+                pad = self.encoder_paddings[i][len(blocks) - 1]
+                p3 = tuple(pad) if isinstance(pad, (list, tuple)) else (pad,) * 3
+                geo.append(((3, 3, 3), (2, 2, 2), p3, blocks[-1]))
+                lvls.append(lvls[-1].create_down_level((3, 3, 3), (2, 2, 2), p3, int(lvls[-1].cap * self.cap_growth[i]), overflow))
+            out_lvl = lvls[-1].create_down_level((3, 1, 1), (2, 1, 1), (0, 0, 0), lvls[-1].cap, overflow)
+            assert ld == out_lvl.shape[0] * Cc and (Hb, Wb) == tuple(out_lvl.shape[1:])
+            ev_sites = event(0)
+        perm, subm, ev_sub = None, [None] * n_lv, [None] * n_lv
+        for k in range(n_lv):                                            # ---- B: mask order + SubM map per level
+            wait(k, ev_sites)
+            with ctx(k):
+                pk_ = lvls[k].sort_by_mask()
+                if k == 0:
+                    perm = pk_
+                subm[k] = lvls[k].subm_map()
+                ev_sub[k] = event(k)
+        down, ready = [None] * n_lv, [None] * (n_lv + 1)
+        ready[0] = ev_sub[0]
+        for k in range(1, n_lv):                                         # ---- C: strided rulebooks
+            wait(k, ev_sub[k - 1])
+            with ctx(k):
+                k3, s3, p3, ldy = geo[k - 1]
+                down[k] = lvls[k - 1].down_rulebook(lvls[k], k3, s3, p3, ldy)
+                ready[k] = event(k)
+        with ctx(n_lv - 1):
+            rb_out = lvls[-1].down_rulebook(out_lvl, (3, 1, 1), (2, 1, 1), (0, 0, 0), ld, bev=(Hb, Wb, Cc))
+            ready[n_lv] = event(n_lv - 1)
+        return dict(perm=perm, levels=[(lvls[k], subm[k], down[k]) for k in range(n_lv)], out=(out_lvl, rb_out), ready=ready)
 
     def forward(self, vox, batch, bev_out, overflow):
         """vox: dict from ops.voxelize; bev_out [B,H,W,2*C] zero-initialised NHWC buffer (channel = d*C + c).
@@ -208,35 +242,26 @@ class SparseEncoder(ParamTree):
         (the reference's, checked by the parity tests) stays untouched in ``vox``; row order inside the sparse encoder is
         implementation-defined in spconv too and vanishes in the dense BEV scatter.
 
-        Two streams: the rulebooks depend on coordinates only, so the whole chain (hash inserts, probes, radix sorts --
-        latency / L2 bound small kernels, ~2 ms at bs = 4) runs on a side stream ahead of the gather-GEMMs of the main
-        stream, which wait per level on an event.  Inside a CUDA-graph capture the side stream becomes a parallel branch."""
+        Streams: the rulebooks depend on coordinates only, so their chains (hash inserts, probes, radix sorts -- latency /
+        L2 bound small kernels, ~2 ms at bs = 4 when serialised) run on side streams, one per level, ahead of the
+        gather-GEMMs of the main stream, which wait per level on an event.  Inside a CUDA-graph capture the side streams
+        become parallel branches."""
         dev = vox["mean"].device
         assert bev_out.is_contiguous()
         bev_shape = (bev_out.shape[1], bev_out.shape[2], bev_out.shape[3])
         main = torch.cuda.current_stream()
+        streams = None
         if ops.SPARSE_OVERLAP:
-            if self._side is None or self._side.device != dev:
-                self._side = torch.cuda.Stream(device=dev)
-            side, events = self._side, []
+            if self._side is None or self._side[0].device != dev:
+                self._side = [torch.cuda.Stream(device=dev) for _ in range(len(self.encoder_channels))]
+            streams = self._side
+        plan = self._plan(vox, batch, overflow, bev_shape, streams)
 
-            def record(k):
-                e = torch.cuda.Event()
-                e.record(side)
-                events.append(e)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                plan = self._plan(vox, batch, overflow, bev_shape, record)
-
-            def ready(k):
-                main.wait_event(events[k])
-        else:
-            plan = self._plan(vox, batch, overflow, bev_shape, lambda k: None)
-
-            def ready(k):
-                pass
-        # everything the side stream allocated stays referenced until the next forward (the caching allocator must not hand
-        # those blocks out again while main-stream kernels still read them)
+        def ready(k):
+            if streams:
+                main.wait_event(plan["ready"][k])
+        # everything the side streams allocated stays referenced until the next forward (the caching allocator must not hand
+        # those blocks out again while kernels of another stream still read them)
         self._plan_keepalive = plan
 
         def conv(x, rb, n_dev, wb, cap_out, act, res=None):
@@ -277,8 +302,9 @@ class SparseEncoder(ParamTree):
         self.level_sizes.append(nl.n_dev)
         w, b = self.pk["conv_out"]
         ops.sparse_conv(x, rb, nl.n_dev, w, b, bev_out, act=ACT_RELU, cout=self.output_channels)
-        if ops.SPARSE_OVERLAP:
-            main.wait_stream(self._side)
+        if streams:
+            for st in streams:
+                main.wait_stream(st)
         return bev_out
 
 

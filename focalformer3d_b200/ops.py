@@ -732,6 +732,7 @@ class SparseLevel:
                                         _ptr(self.hkeys), _ptr(self.hvals), self.hsize, _ptr(inv), _stream()),
               "ff3d_sp_level_permute")
         _count()
+        self._unsorted_coors = self.coors            # stays referenced: kernels of other streams may still read it
         self.coors = coors
         self.subm = None
         self._subm_src = (nbr_u, perm, inv)          # probed rows in the old order: subm_map() re-orders them
@@ -749,10 +750,9 @@ class SparseLevel:
                 self.subm = self._rulebook(self.coors, None, self.n_dev, self.cap, SUBM_K, SUBM_S, SUBM_P)
         return self.subm
 
-    def downsample(self, k3, s3, p3, cap_out, overflow, ldy, sort_level=True, bev=None):
-        """SparseConv3d (k3, s3, p3): creates the output level and the conv's rulebook.  The new level is stored in ITS
-        SubM mask order (``sort_level``); the conv runs over its own mask order and writes through ``y_off``
-        (row * ldy, or -- ``bev=(H, W, C)`` -- straight into the NHWC BEV grid).  Returns (level, Rulebook)."""
+    def create_down_level(self, k3, s3, p3, cap_out, overflow):
+        """Site-creation half of a SparseConv3d (k3, s3, p3): the output level (coordinates, count, hash) in hash-slot order.
+        Needs only this level's coordinates (in any order), not its mask sort."""
         D, H, W = self.shape
         oshape = tuple((self.shape[i] + 2 * p3[i] - k3[i]) // s3[i] + 1 for i in range(3))
         cells = self.batch * oshape[0] * oshape[1] * oshape[2]
@@ -767,14 +767,24 @@ class SparseLevel:
                                      oshape[1], oshape[2], _ptr(lvl.hkeys), _ptr(lvl.hvals), lvl.hsize, _ptr(overflow),
                                      _ptr(scratch), _stream()), "ff3d_sp_down_sites")
         _count(5)
+        return lvl
+
+    def down_rulebook(self, lvl, k3, s3, p3, ldy, bev=None):
+        """Rulebook of the SparseConv3d (k3, s3, p3) from this level into ``lvl`` (both in their FINAL row order): the conv
+        runs over its own mask order and writes through ``y_off`` (row * ldy, or -- ``bev=(H, W, C)`` -- straight into the
+        NHWC BEV grid)."""
+        perm, nbr_u = self._sorted_perm(lvl.coors, lvl.n_dev, lvl.cap, k3, s3, p3)
+        if bev is not None:
+            return self._rulebook(lvl.coors, perm, lvl.n_dev, lvl.cap, k3, s3, p3, y_mode=2, ldy=ldy, bev=bev, nbr_u=nbr_u)
+        return self._rulebook(lvl.coors, perm, lvl.n_dev, lvl.cap, k3, s3, p3, y_mode=1, ldy=ldy, nbr_u=nbr_u)
+
+    def downsample(self, k3, s3, p3, cap_out, overflow, ldy, sort_level=True, bev=None):
+        """SparseConv3d (k3, s3, p3): creates the output level and the conv's rulebook.  The new level is stored in ITS
+        SubM mask order (``sort_level``).  Returns (level, Rulebook)."""
+        lvl = self.create_down_level(k3, s3, p3, cap_out, overflow)
         if sort_level:
             lvl.sort_by_mask()
-        perm, nbr_u = self._sorted_perm(lvl.coors, n_o, cap_out, k3, s3, p3)
-        if bev is not None:
-            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=2, ldy=ldy, bev=bev, nbr_u=nbr_u)
-        else:
-            rb = self._rulebook(lvl.coors, perm, n_o, cap_out, k3, s3, p3, y_mode=1, ldy=ldy, nbr_u=nbr_u)
-        return lvl, rb
+        return lvl, self.down_rulebook(lvl, k3, s3, p3, ldy, bev)
 
 
 def gather_rows(src, perm, n_dev, cols):
