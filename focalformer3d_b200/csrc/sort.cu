@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) rs_scatter_kernel(const uint32_t* __restr
     const int d = i < n ? (int)((kreg[r] >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     if (i < n && (peers & ((1u << lane) - 1u)) == 0u) wh[w][d] += __popc(peers);     // this warp's private row: no atomics
+    __syncwarp();                                        // the next round's leader of digit d may be another lane
   }
   __syncthreads();
   for (int d = tid; d < RS_BINS; d += blockDim.x) {

@@ -211,14 +211,13 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
           for (int c = 0; c < p.cpt; ++c) {
             const uint32_t slot_a = smem + (uint32_t)ring.slot * SLOT_BYTES;
             const uint32_t bar = full_bar + 8u * ring.slot;
-            if (lane == 0) {
-              mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
-              if (warp == 0) {
-                mbar_arrive_expect_tx(bar, 2 * B_BYTES);
-                bulk_g2s(slot_a + 2 * A_BYTES, wsrc + (size_t)(u * p.cpt + c) * stage_bytes, 2 * B_BYTES, bar);
-              }
+            // every lane polls the slot's barrier itself (same word, same phase: the warp stays converged -- the
+            // lane-0 wait + __syncwarp of the first version cost 8 % of the kernel's samples in branch resolution)
+            mbar_wait(empty_bar + 8u * ring.slot, ring.phase ^ 1u);
+            if (warp == 0 && lane == 0) {
+              mbar_arrive_expect_tx(bar, 2 * B_BYTES);
+              bulk_g2s(slot_a + 2 * A_BYTES, wsrc + (size_t)(u * p.cpt + c) * stage_bytes, 2 * B_BYTES, bar);
             }
-            __syncwarp();
 #pragma unroll
             for (int plane = 0; plane < 2; ++plane) {
               const size_t col_bytes = (size_t)(plane * p.xs_lo + c * 64 + lane_col) * 2;
