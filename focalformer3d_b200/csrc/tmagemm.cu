@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
   const uint32_t tmem_ptr = tempty_bar + 16u;
   // CPA: neighbour-map double buffer [2][27 taps][128 rows] int32, filled one to two tiles ahead by the index warp (the
   // producers' own index loads sat on the critical path: 36 % of their stall samples waited for an nbr value)
-  const uint32_t ifull_bar = tmem_ptr + 16u;                      // [2]
+  // bias of the tile's BN columns, staged once per tile by the epilogue warps (double buffer): the per-chunk __ldg of the
+  // bias sat on the epilogue's critical path (15 % of the samples of the K = 128 layers waited for it)
+  const uint32_t bias_s = tmem_ptr + 16u;                         // [2][128] floats
+  const uint32_t ifull_bar = bias_s + 2u * 128u * 4u;             // [2]
   const uint32_t iempty_bar = ifull_bar + 16u;                    // [2]
   const uint32_t idx_buf = iempty_bar + 16u;
   constexpr uint32_t IDX_TILE_BYTES = TC_MAX_TAPS * TC_BM * 4;
@@ -373,9 +376,20 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     bool ovf = false;
     int gc = 0;                                          // accumulator hand-overs consumed so far
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // branch-free epilogue arithmetic: activation as a clamp, the residual added before and / or after it through 0 / 1
+    // multipliers (an absent bias or residual is a zero addend)
+    const float act_lo = p.act == FF3D_ACT_NONE ? -INFINITY : 0.f, act_hi = p.act == FF3D_ACT_RELU6 ? 6.f : INFINITY;
+    const float m_pre = p.res_after_act ? 0.f : 1.f, m_post = 1.f - m_pre;
+    const int et = (warp & 3) * 32 + lane;               // epilogue thread index 0..127
+    int eit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++eit) {
       const int mtile = tile / n_tiles_n;
       const int n0 = (tile - mtile * n_tiles_n) * BN;
+      // stage the bias of this tile's columns (one value per thread); one named barrier per tile among the four epilogue
+      // warps (two buffers: a warp is never more than one tile ahead of another)
+      const uint32_t bsm = bias_s + (uint32_t)(eit & 1) * 512u;
+      if (et < BN) sts32(bsm + (uint32_t)et * 4u, p.bias ? __float_as_int(__ldg(p.bias + n0 + et)) : 0);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int nst = stage_count(unit_mask(tile));
       const int n_runs = (CHUNKED && nst > CHUNK_MIN) ? (nst + CHUNK - 1) / CHUNK : 1;
       // output row of this thread
@@ -435,14 +449,9 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
 #pragma unroll (CHUNKED ? BN / 16 : 1)
       for (int c0 = 0; c0 < BN; c0 += 16) {
         const int n = n0 + c0;
-        float bs[16], rs[16];
-        if (p.bias) {
+        float rs[16];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-            bs[i] = t.x; bs[i + 1] = t.y; bs[i + 2] = t.z; bs[i + 3] = t.w;
-          }
-        }
+        for (int i = 0; i < 16; ++i) rs[i] = 0.f;
         const bool has_res = (p.res != nullptr || p.res_s != nullptr);
         if (has_res && rvalid) {
           if (p.res_s) {
@@ -470,19 +479,30 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
             }
           }
         }
-        float v[16], v2[16];
-        tmem_ld16(acc + (uint32_t)c0, v);                   // warp-collective: all lanes execute
-        tmem_ld16(acc + (uint32_t)(BN + c0), v2);
+        float v[16];
+        {
+          uint32_t ua[16], ub[16];
+          tmem_ld16_nowait(acc + (uint32_t)c0, ua);          // warp-collective: all lanes execute; one wait for both
+          tmem_ld16_nowait(acc + (uint32_t)(BN + c0), ub);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(ub[i]), 1.f / 2048.f, __uint_as_float(ua[i]));   // cross terms: 2^11 scale
+        }
         if (rvalid) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = fmaf(v2[i], 1.f / 2048.f, v[i]);      // the cross terms carry the 2^11 scale of the lo parts
-            if constexpr (CHUNKED) { if (n_runs > 1) a += racc[c0 + i]; }
-            if (p.bias) a += bs[i];
-            if (p.res_after_act) a = apply_act(a, p.act);
-            if (has_res) a += rs[i];
-            if (!p.res_after_act) a = apply_act(a, p.act);
-            v[i] = a;
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+            const int4 b4 = lds128i(bsm + (uint32_t)(c0 + i4) * 4u);
+            const float bb[4] = {__int_as_float(b4.x), __int_as_float(b4.y), __int_as_float(b4.z), __int_as_float(b4.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i4 + j;
+              float a = v[i];
+              if constexpr (CHUNKED) { if (n_runs > 1) a += racc[c0 + i]; }
+              a += bb[j];
+              a = fmaf(m_pre, rs[i], a);
+              a = fminf(fmaxf(a, act_lo), act_hi);
+              v[i] = fmaf(m_post, rs[i], a);
+            }
           }
           if (yp) {
 #pragma unroll
@@ -597,7 +617,7 @@ static int launch_tm_cfg(const CUtensorMap& tm, const TmP& p, long long m_tiles,
   // 64 / 48 / 40 / 36 KB per stage; the cp.async gather also holds two neighbour-map tiles (27 KB)
   constexpr int NS = BN == 128 ? 3 : (BN == 64 ? 4 : ((CPA && BN == 32) ? 4 : 5));
   constexpr size_t SLOT_BYTES = 2 * (size_t)TC_BM * 128 + 2 * (size_t)BN * 128;
-  constexpr size_t IDX_BYTES = CPA ? 2 * (size_t)TC_MAX_TAPS * TC_BM * 4 + 32 : 0;
+  constexpr size_t IDX_BYTES = 2 * 128 * 4 + (CPA ? 2 * (size_t)TC_MAX_TAPS * TC_BM * 4 + 32 : 0);   // bias staging (+ index maps)
   const size_t smem = NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + IDX_BYTES + 1024;
   static_assert(NS * SLOT_BYTES + (2 * NS + 4) * sizeof(uint64_t) + 32 + IDX_BYTES + 1024 <= 227 * 1024, "shared memory budget");
   static const cudaError_t attr =
