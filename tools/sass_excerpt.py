@@ -28,7 +28,8 @@ def main(out_path):
                 c = per[fn].setdefault(w, [0, None])
                 c[0] += 1
                 if c[1] is None:
-                    c[1] = re.sub(r"\s+", " ", line.split("*/")[1] if "*/" in line else line).strip()[:110]
+                    txt1 = re.sub(r"\s+", " ", line.split("*/")[1] if "*/" in line else line).strip()
+                    c[1] = re.sub(r"\s*;\s*/\*.*$", "", txt1)[:110]
     lines = ["# SASS excerpt of focalformer3d_b200/libff3d.so (cuobjdump -sass, sm_100a): instruction counts per kernel + one sample",
              "# UTCHMMA = tcgen05.mma, UTMALDG = cp.async.bulk.tensor (TMA tile / gather4 loads), UBLKCP = cp.async.bulk,",
              "# LDGSTS = cp.async, HMMA.16816 = mma.sync m16n8k16, LDSM = ldmatrix, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit", ""]
