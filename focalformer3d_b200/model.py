@@ -278,7 +278,12 @@ class SparseEncoder(ParamTree):
             ops.sparse_conv(x, rb, n_dev, w, b, y, act=act, res=res)
             return y
 
+        fine = ops.SPARSE_MARKS
+        if fine:
+            ops.mark("sp:plan-issue")
         ready(0)
+        if fine:
+            ops.mark("sp:wait-level1-maps")
         lvl, subm, _ = plan["levels"][0]
         feats = ops.gather_rows(vox["mean"], plan["perm"], lvl.n_dev, vox["mean"].shape[1])
         if ops.tma_ok(self.pk["conv_input"][0], feats.shape[1], self.pk["conv_input"][0].shape[-1], sparse=True):
@@ -289,7 +294,11 @@ class SparseEncoder(ParamTree):
             for j, cout in enumerate(blocks):
                 q = f"encoder_layers.encoder_layer{i + 1}.{j}"
                 if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                    if fine:
+                        ops.mark(f"sp:level{i + 1}-convs")
                     ready(i + 1)
+                    if fine:
+                        ops.mark(f"sp:wait-level{i + 2}-maps")
                     lvl, subm, rb = plan["levels"][i + 1]
                     x = conv(x, rb, lvl.n_dev, self.pk[q], lvl.cap, ACT_RELU)
                     self.level_sizes.append(lvl.n_dev)
@@ -297,6 +306,8 @@ class SparseEncoder(ParamTree):
                     t = conv(x, subm, lvl.n_dev, self.pk[q + ".1"], lvl.cap, ACT_RELU)
                     x = conv(t, subm, lvl.n_dev, self.pk[q + ".2"], lvl.cap, ACT_RELU, res=x)
         # conv_out: SparseConv3d k(3,1,1) s(2,1,1) p0 + BN + ReLU, scattered straight into the NHWC BEV grid
+        if fine:
+            ops.mark(f"sp:level{len(plan['levels'])}-convs")
         ready(len(plan["levels"]))
         nl, rb = plan["out"]
         self.level_sizes.append(nl.n_dev)

@@ -923,6 +923,8 @@ def unpack_frag(frag, N, K):
 FUSED_DECODER = _os.environ.get("FF3D_FUSED_DECODER", "1") != "0"
 # sparse encoder: build the rulebooks on a side stream, concurrently with the gather-GEMMs of earlier levels
 SPARSE_OVERLAP = _os.environ.get("FF3D_SPARSE_OVERLAP", "1") != "0"
+# FF3D_SPARSE_MARKS=1: per-level stage markers inside the sparse encoder (main-stream waits for the side streams included)
+SPARSE_MARKS = _os.environ.get("FF3D_SPARSE_MARKS", "0") == "1"
 
 
 def decoder_stage(x, qpe, q_pos, ref_w, ref_h, value, geom, n_points, stage_w, B, nq, pred_cols):
