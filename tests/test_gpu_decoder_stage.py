@@ -41,6 +41,7 @@ def _run(cfg_name, num_proposals, n_scenes, seed, bev=24, **synth_kw):
     ("focalformer3d_l", 50, 3, {}),             # nq = 100: four blocks, the last with 4 queries
     ("focalformer3d_waymo_l", 30, 2, dict(n_beams=64)),   # three HIP stages (nq = 90), no velocity head
     ("deformformer3d_l", 40, 2, {}),            # single-stage head: one decoder stage, nq = 40
+    ("focalformer3d_l", 300, 8, {}),            # nq = 600 x 8 scenes: 19 blocks per scene -> two cooperative launches (7 + 1 scenes)
 ])
 def test_fused_stage_matches_unfused(cfg_name, num_proposals, n_scenes, kw):
     out = _run(cfg_name, num_proposals, n_scenes, seed=11, **kw)
