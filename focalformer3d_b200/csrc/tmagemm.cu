@@ -44,6 +44,8 @@ struct TmP {
   // CONV2D (stride 1): output patch bw x bh per tile
   int B, Ho, Wo, kw, pad, bw, bh, tiles_x, tiles_y;
   long long y_bstride, res_bstride;   // rows per batch element of y / ys / res
+  int ux, uy, dx, dy;                 // output lattice (transposed conv, kernel == stride): row = (oy*uy + dy, ox*ux + dx)
+  long long y_row0;
   // SPARSE
   const int* nbr; int nbr_stride;
   const int* y_off;              // element offsets into y (BEV scatter), fp32 output only
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
         const int dy = r / p.bw, dx = r - dy * p.bw;
         const int oy = (q / p.tiles_x) * p.bh + dy, ox = (q - (q / p.tiles_x) * p.tiles_x) * p.bw + dx;
         rvalid = r < p.bw * p.bh && oy < p.Ho && ox < p.Wo;
-        row = cb * p.y_bstride + (long long)oy * p.Wo + ox;
+        row = cb * p.y_bstride + p.y_row0 + (long long)(oy * p.uy + p.dy) * (p.Wo * p.ux) + ox * p.ux + p.dx;
         rrow = cb * p.res_bstride + (long long)oy * p.Wo + ox;
       } else {
         const int m = mtile * TC_BM + r;
@@ -706,7 +708,7 @@ extern "C" int ff3d_tmagemm_supported(const ff3d_gemm_desc* d) {
     return (wide_out || narrow_out) ? 1 : 0;
   }
   if (!wide_in || !(wide_out || narrow_out)) return 0;
-  if (d->mode == FF3D_GEMM_CONV2D && (d->stride != 1 || (d->ux > 1) || (d->uy > 1))) return 0;
+  if (d->mode == FF3D_GEMM_CONV2D && d->stride != 1) return 0;
   return 1;
 }
 
@@ -786,6 +788,9 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   const long long xbs = d->x_bstride ? d->x_bstride : (long long)d->H * d->W;
   p.y_bstride = d->y_bstride ? d->y_bstride : (long long)d->Ho * d->Wo;
   p.res_bstride = (long long)d->Ho * d->Wo;
+  p.ux = d->ux > 0 ? d->ux : 1; p.uy = d->uy > 0 ? d->uy : 1; p.dx = d->dx; p.dy = d->dy; p.y_row0 = d->y_row0;
+  FF3D_REQUIRE((p.ux == 1 && p.uy == 1) || (!d->res && !d->res_s), "ff3d_tmagemm: no residual on an up-sampling lattice");
+  if (!d->y_bstride) p.y_bstride = (long long)d->Ho * p.uy * d->Wo * p.ux;
   {
     cuuint64_t dims[4] = {(cuuint64_t)(d->xs_lo + d->cin), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t str[3] = {row_bytes, row_bytes * (cuuint64_t)d->W, row_bytes * (cuuint64_t)xbs};

@@ -419,7 +419,9 @@ class SECONDFPN(ParamTree):
             else:
                 for dy in range(st):
                     for dx in range(st):
-                        ops.conv2d(x, w[dy * st + dx], b, view, 1, act=ACT_RELU, up=(st, dy, dx), out_s=view_s)
+                        wl = w[dy * st + dx]
+                        use_tma = x_s is not None and ops.tma_ok(wl, wl.shape[1], oc)      # lattice GEMM on the TMA-fed kernel
+                        ops.conv2d(x_s if use_tma else x, wl, b, view, 1, act=ACT_RELU, up=(st, dy, dx), out_s=view_s)
             c0 += oc
         return out
 

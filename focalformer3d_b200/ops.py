@@ -421,7 +421,7 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     else:
         if out_s is None:
             raise L.Ff3dError("conv2d: no output")
-        cout, ybs = out_s.channels, Ho * Wo
+        cout, ybs = out_s.channels, Ho * u * Wo * u
     d.mode, d.M, d.cin, d.cout, d.taps = GEMM_CONV2D, B * Ho * Wo, cin, cout, k * k
     if split_in:
         _attach_split(d, xs=x, xs_rows=B * H * W)
@@ -440,8 +440,7 @@ def conv2d(x, w, bias, out, k, stride=1, pad=None, act=ACT_NONE, res=None, up=No
     d.x_bstride, d.y_bstride, d.y_row0 = xbs, ybs, 0
     d.ux, d.uy, d.dx, d.dy = u, u, dx, dy
     if out_s is not None:
-        if out_s.t.dim() != 4 or tuple(out_s.t.shape[:3]) != (B, Ho * u, Wo * u) or (out is not None and ybs != Ho * u * Wo * u) \
-                or (split_in and u != 1):
+        if out_s.t.dim() != 4 or tuple(out_s.t.shape[:3]) != (B, Ho * u, Wo * u) or (out is not None and ybs != Ho * u * Wo * u):
             raise L.Ff3dError("conv2d: the split output is a batch-dense [B, Ho*u, Wo*u, 2C] buffer (same rows as out)")
         _attach_split(d, out_s=out_s)
     t0 = prof.begin()
