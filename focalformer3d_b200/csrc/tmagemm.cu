@@ -44,6 +44,7 @@ struct TmP {
   // CONV2D (stride 1): output patch bw x bh per tile
   int B, Ho, Wo, kw, pad, bw, bh, tiles_x, tiles_y;
   long long y_bstride, res_bstride;   // rows per batch element of y / ys / res
+  int stride;                         // CONV2D input stride (TMA traversal stride of the W / H dimensions)
   int ux, uy, dx, dy;                 // output lattice (transposed conv, kernel == stride): row = (oy*uy + dy, ox*ux + dx)
   long long y_row0;
   // SPARSE
@@ -272,8 +273,9 @@ __global__ void __launch_bounds__(32 * (NPW + 5 + (CPA ? 1 : 0)), 1) tmagemm_ker
             tma_load_2d(slot_a + A_BYTES, &tmA, p.xs_lo + c * 64, m0, bar);
           } else if (MODE == FF3D_GEMM_CONV2D) {
             const int ky = t / p.kw, kx = t - ky * p.kw;
-            tma_load_4d(slot_a, &tmA, c * 64, x0 + kx - p.pad, y0 + ky - p.pad, cb, bar);
-            tma_load_4d(slot_a + A_BYTES, &tmA, p.xs_lo + c * 64, x0 + kx - p.pad, y0 + ky - p.pad, cb, bar);
+            const int ix0 = x0 * p.stride + kx - p.pad, iy0 = y0 * p.stride + ky - p.pad;    // first input pixel of the box
+            tma_load_4d(slot_a, &tmA, c * 64, ix0, iy0, cb, bar);
+            tma_load_4d(slot_a + A_BYTES, &tmA, p.xs_lo + c * 64, ix0, iy0, cb, bar);
           }
         }
         __syncwarp();
@@ -603,10 +605,11 @@ static PFN_encodeTiled encode_tiled() {
 
 // tensor map over split activation rows: rank 2 = (halves of a row, rows), rank 4 = (halves, W, H, B)
 static int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
+                    const cuuint32_t* box, int pixel_stride = 1) {
   PFN_encodeTiled enc = encode_tiled();
   if (!enc) { set_error("ff3d_tmagemm: cuTensorMapEncodeTiled is not available from this driver"); return FF3D_ECUDA; }
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // strided conv: the W / H dimensions are traversed with the conv stride (every stride-th pixel of the box is copied)
+  cuuint32_t estr[4] = {1, (cuuint32_t)pixel_stride, (cuuint32_t)pixel_stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -708,7 +711,7 @@ extern "C" int ff3d_tmagemm_supported(const ff3d_gemm_desc* d) {
     return (wide_out || narrow_out) ? 1 : 0;
   }
   if (!wide_in || !(wide_out || narrow_out)) return 0;
-  if (d->mode == FF3D_GEMM_CONV2D && d->stride != 1) return 0;
+  if (d->mode == FF3D_GEMM_CONV2D && (d->stride < 1 || d->stride > 2 || (d->stride != 1 && (d->ux > 1 || d->uy > 1)))) return 0;
   return 1;
 }
 
@@ -781,7 +784,9 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   }
   FF3D_REQUIRE(d->mode == FF3D_GEMM_CONV2D && d->taps == d->kh * d->kw && (long long)d->B * d->Ho * d->Wo == d->M,
                "ff3d_tmagemm: bad conv geometry");
-  FF3D_REQUIRE(d->Ho == d->H + 2 * d->pad - d->kh + 1 && d->Wo == d->W + 2 * d->pad - d->kw + 1, "ff3d_tmagemm: stride-1 geometry");
+  FF3D_REQUIRE(d->Ho == (d->H + 2 * d->pad - d->kh) / d->stride + 1 && d->Wo == (d->W + 2 * d->pad - d->kw) / d->stride + 1,
+               "ff3d_tmagemm: conv output geometry");
+  p.stride = d->stride;
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo; p.kw = d->kw; p.pad = d->pad;
   ff3d_tmagemm_conv_patch(d->Ho, d->Wo, &p.bw, &p.bh);
   p.tiles_x = cdiv(d->Wo, p.bw); p.tiles_y = cdiv(d->Ho, p.bh);
@@ -794,8 +799,9 @@ extern "C" int ff3d_tmagemm(const ff3d_gemm_desc* d, const void* wimg16, int bn,
   {
     cuuint64_t dims[4] = {(cuuint64_t)(d->xs_lo + d->cin), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t str[3] = {row_bytes, row_bytes * (cuuint64_t)d->W, row_bytes * (cuuint64_t)xbs};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
-    int rc = make_map(&tm, d->xs, 4, dims, str, box);
+    cuuint32_t box[4] = {64, (cuuint32_t)((p.bw - 1) * d->stride + 1), (cuuint32_t)((p.bh - 1) * d->stride + 1), 1};
+    FF3D_REQUIRE(box[1] <= 256 && box[2] <= 256, "ff3d_tmagemm: strided box exceeds the TMA limit");
+    int rc = make_map(&tm, d->xs, 4, dims, str, box, d->stride);
     if (rc) return rc;
   }
   return launch_tm_bn<FF3D_GEMM_CONV2D>(tm, p, (long long)d->B * p.tiles_y * p.tiles_x, bn, st);

@@ -363,7 +363,7 @@ class SECOND(ParamTree):
                 Ho, Wo = ((H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1)
                 cin, cout = w.shape[1], self.out_channels[i]
                 last = l == len(layers) - 1
-                use_tma = s == 1 and ops.tma_ok(w, cin, cout)
+                use_tma = (s == 1 or (ops.TMA_STRIDED and xs is not None)) and ops.tma_ok(w, cin, cout)
                 if use_tma and xs is None:
                     xs = ops.split_rows(x)                          # one elementwise pass (the BEV scatter output is fp32)
                 nxt = layers[l + 1][0] if not last else None

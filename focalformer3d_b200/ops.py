@@ -922,6 +922,8 @@ def unpack_frag(frag, N, K):
 FUSED_DECODER = _os.environ.get("FF3D_FUSED_DECODER", "1") != "0"
 # sparse encoder: build the rulebooks on a side stream, concurrently with the gather-GEMMs of earlier levels
 SPARSE_OVERLAP = _os.environ.get("FF3D_SPARSE_OVERLAP", "1") != "0"
+# stride-2 3x3 convs on the TMA-fed kernel (tensor map with a traversal stride on W / H) when their input exists in split form
+TMA_STRIDED = _os.environ.get("FF3D_TMA_STRIDED", "1") != "0"
 # FF3D_SPARSE_MARKS=1: per-level stage markers inside the sparse encoder (main-stream waits for the side streams included)
 SPARSE_MARKS = _os.environ.get("FF3D_SPARSE_MARKS", "0") == "1"
 

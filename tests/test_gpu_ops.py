@@ -754,6 +754,56 @@ def test_tma_conv2d_vs_fp64(ops, cin, cout, k, H, W):
     assert int(ops.gemm_flag().item()) == 0
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(128, 256, 30, 37), (64, 128, 17, 16)])
+def test_tma_conv2d_stride2_vs_fp64(ops, cin, cout, H, W):
+    """ff3d_tmagemm CONV2D with stride 2: tensor map with a traversal stride of 2 on W / H (every second pixel of the box),
+    odd and even map sizes, boxes that start at -1 and overhang the map."""
+    if not ops.tma_enabled():
+        pytest.skip("TMA path disabled")
+    g = torch.Generator().manual_seed(cin + H)
+    B = 2
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    pw = _pack_conv(w)
+    xs = ops.split_rows(x.permute(0, 2, 3, 1).contiguous().cuda())
+    xq = ops.unsplit_rows(xs, B * H * W).cpu().view(B, H, W, cin).permute(0, 3, 1, 2).double()
+    ref = F.conv2d(xq, w.double(), b.double(), stride=2, padding=1).clamp(min=0)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    out = torch.empty((B, Ho, Wo, cout), device="cuda")
+    ys = ops.Split.empty((B, Ho, Wo), cout, "cuda")
+    ops.conv2d(xs, pw, b.cuda(), out, 3, stride=2, act=1, out_s=ys)
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max().item() < 3e-5
+    back = ops.unsplit_rows(ys, B * Ho * Wo).cpu().view(B, Ho, Wo, cout).permute(0, 3, 1, 2)
+    assert (back.double() - got).abs().max().item() < 1e-5
+    assert int(ops.gemm_flag().item()) == 0
+
+
+def test_tma_transposed_conv_lattice(ops):
+    """ConvTranspose2d with kernel == stride as one 1x1 GEMM per output lattice position on the TMA-fed kernel (split input,
+    fp32 + split outputs on the (oy*u + dy, ox*u + dx) lattice)."""
+    if not ops.tma_enabled():
+        pytest.skip("TMA path disabled")
+    g = torch.Generator().manual_seed(5)
+    B, H, W, cin, cout, u = 2, 13, 11, 128, 128, 2
+    x = torch.randn(B, cin, H, W, generator=g)
+    wt = torch.randn(cin, cout, u, u, generator=g) / cin ** 0.5                    # ConvTranspose2d layout
+    xs = ops.split_rows(x.permute(0, 2, 3, 1).contiguous().cuda())
+    xq = ops.unsplit_rows(xs, B * H * W).cpu().view(B, H, W, cin).permute(0, 3, 1, 2).double()
+    ref = F.conv_transpose2d(xq, wt.double(), stride=u)
+    out = torch.zeros((B, H * u, W * u, cout), device="cuda")
+    ys = ops.Split.empty((B, H * u, W * u), cout, "cuda")
+    for dy in range(u):
+        for dx in range(u):
+            pw = _pack_conv(wt[:, :, dy, dx].t().reshape(cout, cin, 1, 1).contiguous())
+            ops.conv2d(xs, pw, None, out, 1, up=(u, dy, dx), out_s=ys)
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max().item() < 3e-5
+    back = ops.unsplit_rows(ys, B * H * u * W * u).cpu().view(B, H * u, W * u, cout).permute(0, 3, 1, 2)
+    assert (back.double() - got).abs().max().item() < 1e-5
+
+
 def test_tma_conv2d_channel_slices(ops):
     """concat-free views: the conv reads channels [64, 192) of a 256-channel split buffer and writes its fp32 and split
     outputs into channel slices of wider buffers."""
