@@ -371,7 +371,7 @@ def run_ours(args):
         head_start = int(os.environ.get("FF3D_BENCH_HEAD_START_CYCLES", "8000000"))
         for _ in range(reps):                  # pass A: stage markers only (per-stage ms)
             ops.prof.start(records=False)
-            if head_start > 0:
+            if head_start > 0 and hasattr(torch.cuda, "_sleep"):
                 torch.cuda._sleep(head_start)
             model.forward_raw(dev, img=dimg, img_metas=metas)
             torch.cuda.synchronize()
